@@ -1,0 +1,190 @@
+/*
+ * lattice_b200.h -- C ABI of the B200-native permutohedral-lattice backend.
+ *
+ * Drop-in boundary for the lattice hot path of AIS-Bonn/lattice_net.  The reference exposes
+ * this path as a pybind11 C++ class (`Lattice`, /root/reference/src/PyBridge.cxx:41-113) whose
+ * methods allocate torch tensors and then call one `LatticeGPU::<op>()` launcher each
+ * (/root/reference/include/lattice_net/kernels/LatticeGPU.cuh:42-412).  This header declares
+ * one `extern "C"` entry point per launcher: raw DEVICE pointers, sizes, a `cudaStream_t`
+ * passed as `void*`, and an `int` status.  No torch / C++ types cross the boundary; the host
+ * side (lattice_net_b200/lattice.py, or a maintainer's own pybind stub)
+ * owns all memory.
+ *
+ * Conventions
+ *   - all floating data is fp32, all indices / keys are int32 (as in the reference);
+ *   - `stream` is a cudaStream_t (0 = legacy default stream);
+ *   - every function returns LN_OK (0) or a negative LN_ERR_* code; ln_last_error() returns a
+ *     thread-local human-readable message for the last failure;
+ *   - functions are asynchronous with respect to the host unless stated otherwise;
+ *   - a hash table is described by four device arrays exactly like the reference's
+ *     HashTableGPU (/root/reference/include/lattice_net/kernels/HashTableGPU.cuh:23-28):
+ *        keys      int32 [capacity x pos_dim]  compact, row id == vertex id
+ *        entries   int32 [capacity]            slot -> vertex id, -1 empty, -2 being written
+ *        nr_filled int32 [1]                   number of vertices
+ *     plus `capacity` and `pos_dim` passed by value.  `values` [nv x val_dim] are separate.
+ *   - index / weight tables are [n_points * (pos_dim+1)], point-major; -1 / -1.0f mean
+ *     "not inserted / not found" (/root/reference/src/Lattice.cpp: fill_(-1) at Lattice.cu:214-215).
+ *   - supported pos_dim: 3 and 5 (the reference's shipped configs use 3; its sweep uses 5).
+ */
+#ifndef LATTICE_B200_H_
+#define LATTICE_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LN_OK 0
+#define LN_ERR_BAD_ARG (-1)        /* null pointer, negative size, unsupported pos_dim ...   */
+#define LN_ERR_CUDA (-2)           /* a CUDA runtime call / launch failed                     */
+#define LN_ERR_UNSUPPORTED (-3)    /* shape outside what the kernels implement                */
+#define LN_ERR_TABLE_FULL (-4)     /* reported by ln_table_status(): an insert found no slot  */
+
+/* Version / build info: "lattice_b200 <ver> sm_100a". */
+const char* ln_version(void);
+/* Message describing the last error returned on this host thread. */
+const char* ln_last_error(void);
+/* Number of kernels launched by this library on this host thread since the last reset
+ * (bench.py reports it as `gpu_launches`). */
+long long ln_launch_count(void);
+void ln_reset_launch_count(void);
+
+/* ---- hash table ---------------------------------------------------------------------------
+ * Replaces HashTable::clear() (/root/reference/src/HashTable.cu:49-57) for the structural
+ * part: entries <- -1, nr_filled <- 0, status <- 0.  keys need no clearing (rows >= nr_filled
+ * are never read).  `status` is a device int32[2]: [0] overflow flag, [1] max probe length. */
+int ln_table_clear(int* entries, int* nr_filled, int* status, int capacity, void* stream);
+
+/* Synchronous: copies nr_filled and the status words to the host (one D2H of 12 bytes).
+ * Replaces Lattice::nr_lattice_vertices() (/root/reference/src/Lattice.cu:1326-1346).
+ * Returns LN_ERR_TABLE_FULL if an insert overflowed (the reference would spin forever,
+ * HashTableGPU.cuh:443-484 has no probe limit). */
+int ln_table_status(const int* nr_filled, const int* status, int* nr_filled_host, int* max_probe_host, void* stream);
+
+/* ---- splat: build structure -----------------------------------------------------------------
+ * Replaces kernel_splat<d,V> (LatticeGPU.cuh:707-842) + the host prep of
+ * Lattice::splat_standalone / just_create_verts (/root/reference/src/Lattice.cu:196-290):
+ * positions_raw / sigmas, simplex + barycentric computation, insertion of the pos_dim+1 simplex
+ * vertices, and (if indices/weights != NULL) the splatting tables.
+ *   positions_raw [n x pos_dim], sigmas [pos_dim] (device), indices/weights [n*(pos_dim+1)] or NULL */
+int ln_splat_build(const float* positions_raw, const float* sigmas, int n, int pos_dim,
+                   int* keys, int* entries, int* nr_filled, int* status, int capacity,
+                   int* indices, float* weights, void* stream);
+
+/* Replaces splatCacheNaive<d,V> (LatticeGPU.cuh:926-973):
+ *   lattice_values[indices[p,r], :] += values[p, :] * weights[p,r]      (rows with index < 0 skipped)
+ * lattice_values must be zero-initialised by the caller (HashTable::clear does it in the reference). */
+int ln_splat_accumulate(const float* values, const int* indices, const float* weights,
+                        int n, int pos_dim, int val_dim, float* lattice_values, void* stream);
+
+/* Replaces distribute<d,V> (LatticeGPU.cuh:534-650) + host prep of Lattice::distribute
+ * (/root/reference/src/Lattice.cu:351-410).  As ln_splat_build, plus
+ *   distributed [n*(pos_dim+1) x (pos_dim+val_dim+1)], row p*(pos_dim+1)+r =
+ *        [ positions_raw[p]/sigmas | values[p] | barycentric_r ]                                */
+int ln_distribute(const float* positions_raw, const float* sigmas, const float* values,
+                  int n, int pos_dim, int val_dim,
+                  int* keys, int* entries, int* nr_filled, int* status, int capacity,
+                  int* indices, float* weights, float* distributed, void* stream);
+
+/* Structure part of slice_no_precomputation<d,V> (LatticeGPU.cuh:2598-2750): recompute the simplex
+ * of every position and *retrieve* (never insert) its vertices; not-found -> index -1, weight -1. */
+int ln_lookup_simplex(const float* positions_raw, const float* sigmas, int n, int pos_dim,
+                      const int* keys, const int* entries, int capacity,
+                      int* indices, float* weights, void* stream);
+
+/* Replaces coarsen<d> (LatticeGPU.cuh:2314-2514) used by Lattice::create_coarse_verts
+ * (/root/reference/src/Lattice.cu:670-703): every fine vertex whose key is all-even inserts key/2
+ * into the coarse table, plus the coarse image of each of its existing fine 1-hop neighbours.
+ * nv_fine is read from fine_nr_filled on the device. */
+int ln_coarsen_keys(const int* fine_keys, const int* fine_entries, const int* fine_nr_filled, int fine_capacity,
+                    int* coarse_keys, int* coarse_entries, int* coarse_nr_filled, int* coarse_status, int coarse_capacity,
+                    int pos_dim, int nv_fine_upper, void* stream);
+
+/* ---- neighbourhood ---------------------------------------------------------------------------
+ * The traversal of im2row / im2rowindices / row2im (LatticeGPU.cuh:1464-1688, 1690-1920, 2067-2305)
+ * done ONCE per (query lattice, neighbour lattice, dilation): neighbours[q, slot] = vertex id in the
+ * neighbour lattice or -1.  Slot order (filter_extent F = 2(pos_dim+1)+1): slot 2a = "np" of axis a,
+ * slot 2a+1 = "nm" of axis a, slot F-1 = centre.  lvl_diff = query_lvl - neighbour_lvl in {-1,0,1}. */
+int ln_neighbour_table(const int* query_keys, int nv_query, int pos_dim,
+                       const int* nbr_keys, const int* nbr_entries, int nbr_capacity,
+                       int lvl_diff, int dilation, int* neighbours, void* stream);
+
+/* API-parity materialisations (the conv kernels below never need them).
+ * rowified [nv_query x F*val_dim]; `flip` swaps the np/nm slots (LatticeGPU.cuh:1626,1649). */
+int ln_im2row(const float* nbr_values, const int* neighbours, int nv_query, int filter_extent,
+              int val_dim, int flip, float* rowified, void* stream);
+/* int32 variant: neighbour vertex id replicated val_dim times; slots without a neighbour stay 0
+ * exactly like the reference's zeros-initialised buffer (/root/reference/src/Lattice.cu:600). */
+int ln_im2rowindices(const int* neighbours, int nv_query, int filter_extent, int val_dim, int flip,
+                     int* rowified, void* stream);
+/* out[v, :] = sum over slots of rowified[neighbour(v, slot), opposite(slot) chunk] + centre chunk
+ * (LatticeGPU.cuh:2067-2305); `neighbours` is the table of the lattice itself. out [nv x val_dim]. */
+int ln_row2im(const float* rowified, const int* neighbours, int nv, int filter_extent, int val_dim,
+              float* out, void* stream);
+
+/* ---- lattice convolution (implicit GEMM, no im2row buffer) -------------------------------------
+ * Replaces im2row + `lattice_rowified.mm(filter_bank)` in Lattice::convolve_im2row_standalone
+ * (/root/reference/src/Lattice.cu:424-474):
+ *   out[q, co] = sum_slot sum_ci nbr_values[neighbours[q, slot'], ci] * filter[slot*c_in + ci, co] (+ bias[co])
+ * slot' = slot^1 for slot < F-1 when flip != 0 (the data-gradient convolution of
+ * /root/reference/latticenet_py/lattice/lattice_funcs.py:307-313), else slot.
+ * precision: 0 = exact fp32 FMA (SIMT), 1 = tcgen05 3xTF32 (fp32-equivalent), 2 = tcgen05 1xTF32.
+ * bias may be NULL. */
+int ln_conv_fwd(const float* nbr_values, const int* neighbours, const float* filter, const float* bias,
+                int nv_query, int filter_extent, int c_in, int c_out, int flip, int precision,
+                float* out, void* stream);
+
+/* Weight gradient, replaces `lattice_rowified.transpose(0,1).mm(grad)` (lattice_funcs.py:302,378,443):
+ *   grad_filter[slot*c_in + ci, co] = sum_q nbr_values[neighbours[q, slot], ci] * grad_out[q, co]
+ * grad_filter [F*c_in x c_out] is overwritten (zeroed, then accumulated with fp32 reductions). */
+int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* grad_out,
+                  int nv_query, int filter_extent, int c_in, int c_out,
+                  float* grad_filter, void* stream);
+
+/* filter_bw[(slot*c_out + co), ci] = filter[(slot*c_in + ci), co]: the re-layout done with
+ * transpose/view/contiguous in lattice_funcs.py:304-311. */
+int ln_filter_for_dgrad(const float* filter, int filter_extent, int c_in, int c_out, float* filter_bw, void* stream);
+
+/* ---- slice family -------------------------------------------------------------------------------
+ * slice_with_precomputation<d,V> (LatticeGPU.cuh:2552-2595): out[p,:] = sum_r w[p,r]*values[idx[p,r],:] */
+int ln_slice_fwd(const float* lattice_values, const int* indices, const float* weights,
+                 int n, int pos_dim, int val_dim, float* out, void* stream);
+/* slice_backwards_with_precomputation_no_homogeneous<d,V> (LatticeGPU.cuh:3540-3623):
+ *   grad_values[idx[p,r], :] += grad_out[p,:] * w[p,r]      (grad_values pre-zeroed by caller) */
+int ln_slice_bwd(const float* grad_out, const int* indices, const float* weights,
+                 int n, int pos_dim, int val_dim, float* grad_values, void* stream);
+/* gather_with_precomputation<d,V> (LatticeGPU.cuh:2886-2929): out [n x (pos_dim+1)(val_dim+1)],
+ * chunk r = [ w_r * values[idx_r,:] | w_r ], zeros where idx_r < 0. */
+int ln_gather_fwd(const float* lattice_values, const int* indices, const float* weights,
+                  int n, int pos_dim, int val_dim, float* out, void* stream);
+/* gather_backwards_with_precomputation<d,V> (LatticeGPU.cuh:3761-3817). grad_values pre-zeroed. */
+int ln_gather_bwd(const float* grad_out, const int* indices, const float* weights,
+                  int n, int pos_dim, int val_dim, float* grad_values, void* stream);
+/* slice_classify_with_precomputation<d,V,nc> (LatticeGPU.cuh:3387-3464):
+ *   logits[p,c] = bias[c] + sum_v W[c,v] * sum_r (w[p,r]+dw[p,r]) * values[idx[p,r], v]            */
+int ln_slice_classify_fwd(const float* lattice_values, const int* indices, const float* weights,
+                          const float* delta_weights, const float* cls_weight, const float* cls_bias,
+                          int n, int pos_dim, int val_dim, int nr_classes, float* logits, void* stream);
+/* slice_classify_backwards_with_precomputation<d,V,nc> (LatticeGPU.cuh:3628-3756): accumulates into
+ * the four caller-zeroed gradients (/root/reference/latticenet_py/lattice/lattice_funcs.py:553-556). */
+int ln_slice_classify_bwd(const float* grad_logits, const float* lattice_values, const int* indices,
+                          const float* weights, const float* delta_weights, const float* cls_weight,
+                          int n, int pos_dim, int val_dim, int nr_classes,
+                          float* grad_lattice_values, float* grad_delta_weights,
+                          float* grad_cls_weight, float* grad_cls_bias, void* stream);
+
+/* ---- PointNet glue on lattice vertices ---------------------------
+ * Segmented reductions over the points that splat onto each vertex, replacing the torch_scatter
+ * calls of /root/reference/latticenet_py/lattice/lattice_modules.py:78,688,692.
+ * index [m] (already clamped to >= 0), src [m x c]; out_* are [nv x c].
+ * scatter_max: out_max[v,c] = max over rows, out_arg[v,c] = row attaining it (m if none, value 0 if none)
+ *              -- torch_scatter.scatter_max semantics. */
+int ln_scatter_max(const float* src, const int* index, int m, int c, int nv,
+                   float* out_max, int* out_arg, unsigned long long* workspace /* [nv x c] */, void* stream);
+/* out_sum[v,c] = sum, out_count[v] = number of rows (float) */
+int ln_scatter_sum_count(const float* src, const int* index, int m, int c, int nv,
+                         float* out_sum, float* out_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LATTICE_B200_H_ */

@@ -1,0 +1,57 @@
+// Host-side plumbing of the C ABI: error strings, launch accounting, table status readback.
+#include <cstdarg>
+#include <cstdio>
+#include "ln_common.cuh"
+
+namespace ln {
+
+static thread_local char g_error[512] = "";
+static thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(err));
+        return LN_ERR_CUDA;
+    }
+    return LN_OK;
+}
+
+void count_launch(int n) { g_launches += n; }
+
+}  // namespace ln
+
+extern "C" {
+
+const char* ln_version(void) { return "lattice_b200 0.1 sm_100a"; }
+const char* ln_last_error(void) { return ln::g_error; }
+long long ln_launch_count(void) { return ln::g_launches; }
+void ln_reset_launch_count(void) { ln::g_launches = 0; }
+
+int ln_table_status(const int* nr_filled, const int* status, int* nr_filled_host, int* max_probe_host, void* stream) {
+    LN_REQUIRE(nr_filled && nr_filled_host, "ln_table_status: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    int st[2] = {0, 0};
+    cudaError_t err = cudaMemcpyAsync(nr_filled_host, nr_filled, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess && status) err = cudaMemcpyAsync(st, status, 2 * sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+    if (err != cudaSuccess) {
+        ln::set_error("ln_table_status: %s", cudaGetErrorString(err));
+        return LN_ERR_CUDA;
+    }
+    if (max_probe_host) *max_probe_host = st[1];
+    if (st[0] != 0) {
+        ln::set_error("hash table full: an insert found no free slot (nr_filled=%d); raise hash_table_capacity", *nr_filled_host);
+        return LN_ERR_TABLE_FULL;
+    }
+    return LN_OK;
+}
+
+}  // extern "C"

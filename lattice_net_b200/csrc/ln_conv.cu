@@ -1,0 +1,224 @@
+// Lattice convolution as an implicit GEMM over the neighbour table -- exact-fp32 SIMT path,
+// weight gradient, and the filter re-layout for the data gradient.  The tcgen05 tensor-core path
+// lives in ln_conv_tc.cu and is selected with precision = 1 / 2.
+//
+// Reference: Lattice::convolve_im2row_standalone (/root/reference/src/Lattice.cu:424-474) =
+// im2row kernel (LatticeGPU.cuh:1464-1688) + cuBLAS SGEMM; backward algebra in
+// /root/reference/latticenet_py/lattice/lattice_funcs.py:294-313.
+#include "ln_common.cuh"
+
+namespace ln {
+
+int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
+                int F, int c_in, int c_out, int flip, int precision, float* out, cudaStream_t s);   // ln_conv_tc.cu
+
+constexpr int kThreads = 256;
+constexpr int BM = 64, BN = 64, BK = 16;
+
+// out[q0:q0+64, n0:n0+64] tile per block, 4x4 outputs per thread, K walked slot by slot.
+__global__ void __launch_bounds__(kThreads)
+conv_fwd_simt_kernel(const float* __restrict__ values, const int* __restrict__ neighbours,
+                     const float* __restrict__ filter, const float* __restrict__ bias, int nv_query, int F, int c_in,
+                     int c_out, int flip, float* __restrict__ out) {
+    __shared__ float a_sh[BK][BM + 4];
+    __shared__ float b_sh[BK][BN + 4];
+    __shared__ int nbr_sh[BM];
+    const int q0 = blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+
+    const int a_row = tid >> 2;          // 0..63
+    const int a_col = (tid & 3) * 4;     // 0,4,8,12
+    const int b_row = tid >> 4;          // 0..15
+    const int b_col = (tid & 15) * 4;    // 0..60
+
+    for (int slot = 0; slot < F; slot++) {
+        const int src_slot = (flip && slot < F - 1) ? (slot ^ 1) : slot;
+        __syncthreads();
+        if (tid < BM) {
+            const int q = q0 + tid;
+            nbr_sh[tid] = (q < nv_query) ? __ldg(neighbours + (size_t)q * F + src_slot) : -1;
+        }
+        __syncthreads();
+        for (int c0 = 0; c0 < c_in; c0 += BK) {
+            // stage A: gathered neighbour rows (zeros where the neighbour is absent)
+            {
+                const int id = nbr_sh[a_row];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int c = c0 + a_col + k;
+                    a_sh[a_col + k][a_row] = (id >= 0 && c < c_in) ? __ldg(values + (size_t)id * c_in + c) : 0.0f;
+                }
+            }
+            // stage B: filter rows slot*c_in + c0 .. +BK
+            {
+                const int c = c0 + b_row;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int n = n0 + b_col + k;
+                    b_sh[b_row][b_col + k] = (c < c_in && n < c_out) ? __ldg(filter + ((size_t)slot * c_in + c) * c_out + n) : 0.0f;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < BK; k++) {
+                float a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) a[i] = a_sh[k][ty * 4 + i];
+#pragma unroll
+                for (int j = 0; j < 4; j++) b[j] = b_sh[k][tx * 4 + j];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int q = q0 + ty * 4 + i;
+        if (q >= nv_query) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int n = n0 + tx * 4 + j;
+            if (n < c_out) out[(size_t)q * c_out + n] = acc[i][j] + (bias ? __ldg(bias + n) : 0.0f);
+        }
+    }
+}
+
+// grad_filter[slot*c_in + ci, co] += sum_{q in chunk} values[nbr[q,slot], ci] * grad_out[q, co]
+// grid: x = q-chunk, y = (ci tile, co tile), z = slot
+__global__ void __launch_bounds__(kThreads)
+conv_wgrad_simt_kernel(const float* __restrict__ values, const int* __restrict__ neighbours,
+                       const float* __restrict__ grad_out, int nv_query, int F, int c_in, int c_out, int q_chunk,
+                       int co_tiles, float* __restrict__ grad_filter) {
+    __shared__ float a_sh[BK][BM + 4];   // [q][ci]
+    __shared__ float g_sh[BK][BN + 4];   // [q][co]
+    const int slot = blockIdx.z;
+    const int ci0 = (blockIdx.y / co_tiles) * BM;
+    const int co0 = (blockIdx.y % co_tiles) * BN;
+    const int q_begin = blockIdx.x * q_chunk;
+    const int q_end = min(q_begin + q_chunk, nv_query);
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+    const int l_row = tid >> 4;          // 0..15  (q within the step)
+    const int l_col = (tid & 15) * 4;    // 0..60
+    for (int qs = q_begin; qs < q_end; qs += BK) {
+        const int q = qs + l_row;
+        const int id = (q < q_end) ? __ldg(neighbours + (size_t)q * F + slot) : -1;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int ci = ci0 + l_col + k;
+            a_sh[l_row][l_col + k] = (id >= 0 && ci < c_in) ? __ldg(values + (size_t)id * c_in + ci) : 0.0f;
+            const int co = co0 + l_col + k;
+            g_sh[l_row][l_col + k] = (q < q_end && co < c_out) ? __ldg(grad_out + (size_t)q * c_out + co) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; k++) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = a_sh[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = g_sh[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int ci = ci0 + ty * 4 + i;
+        if (ci >= c_in) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int co = co0 + tx * 4 + j;
+            if (co < c_out) atomicAdd(grad_filter + ((size_t)slot * c_in + ci) * c_out + co, acc[i][j]);
+        }
+    }
+}
+
+// filter_bw[(slot*c_out + co), ci] = filter[(slot*c_in + ci), co]
+__global__ void __launch_bounds__(kThreads)
+filter_for_dgrad_kernel(const float* __restrict__ filter, int c_in, int c_out, float* __restrict__ filter_bw) {
+    __shared__ float tile[32][33];
+    const int slot = blockIdx.z;
+    const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const float* src = filter + (size_t)slot * c_in * c_out;
+    float* dst = filter_bw + (size_t)slot * c_in * c_out;
+    for (int r = ty; r < 32; r += 8) {
+        const int ci = ci0 + r, co = co0 + tx;
+        tile[r][tx] = (ci < c_in && co < c_out) ? __ldg(src + (size_t)ci * c_out + co) : 0.0f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int co = co0 + r, ci = ci0 + tx;
+        if (co < c_out && ci < c_in) dst[(size_t)co * c_in + ci] = tile[tx][r];
+    }
+}
+
+}  // namespace ln
+
+using namespace ln;
+
+extern "C" {
+
+int ln_conv_fwd(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
+                int filter_extent, int c_in, int c_out, int flip, int precision, float* out, void* stream) {
+    LN_REQUIRE(nbr_values && neighbours && filter && out, "ln_conv_fwd: null pointer");
+    LN_REQUIRE(nv_query >= 0 && filter_extent >= 3 && (filter_extent & 1) && c_in >= 1 && c_out >= 1, "ln_conv_fwd: bad size");
+    LN_REQUIRE(precision >= 0 && precision <= 2, "ln_conv_fwd: precision must be 0 (fp32), 1 (3xTF32) or 2 (TF32)");
+    if (nv_query == 0) return LN_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (precision != 0) return conv_fwd_tc(nbr_values, neighbours, filter, bias, nv_query, filter_extent, c_in, c_out, flip, precision, out, s);
+    dim3 grid(cdiv(nv_query, BM), cdiv(c_out, BN));
+    conv_fwd_simt_kernel<<<grid, kThreads, 0, s>>>(nbr_values, neighbours, filter, bias, nv_query, filter_extent, c_in, c_out, flip, out);
+    count_launch();
+    return check_launch("conv_fwd_simt");
+}
+
+int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query,
+                  int filter_extent, int c_in, int c_out, float* grad_filter, void* stream) {
+    LN_REQUIRE(nbr_values && neighbours && grad_out && grad_filter, "ln_conv_wgrad: null pointer");
+    LN_REQUIRE(nv_query >= 0 && filter_extent >= 3 && c_in >= 1 && c_out >= 1, "ln_conv_wgrad: bad size");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t bytes = (size_t)filter_extent * c_in * c_out * sizeof(float);
+    if (cudaMemsetAsync(grad_filter, 0, bytes, s) != cudaSuccess) return check_launch("conv_wgrad memset");
+    if (nv_query == 0) return LN_OK;
+    const int ci_tiles = cdiv(c_in, BM), co_tiles = cdiv(c_out, BN);
+    // enough q-chunks to fill the machine (~4 waves of 148 SMs), at least 256 rows each
+    const int tiles = ci_tiles * co_tiles * filter_extent;
+    int chunks = max(1, min(cdiv(nv_query, 256), cdiv(148 * 4, tiles)));
+    int q_chunk = cdiv(cdiv(nv_query, chunks), BK) * BK;
+    chunks = cdiv(nv_query, q_chunk);
+    dim3 grid(chunks, ci_tiles * co_tiles, filter_extent);
+    conv_wgrad_simt_kernel<<<grid, kThreads, 0, s>>>(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, q_chunk, co_tiles, grad_filter);
+    count_launch();
+    return check_launch("conv_wgrad_simt");
+}
+
+int ln_filter_for_dgrad(const float* filter, int filter_extent, int c_in, int c_out, float* filter_bw, void* stream) {
+    LN_REQUIRE(filter && filter_bw, "ln_filter_for_dgrad: null pointer");
+    LN_REQUIRE(filter_extent >= 1 && c_in >= 1 && c_out >= 1, "ln_filter_for_dgrad: bad size");
+    dim3 grid(cdiv(c_out, 32), cdiv(c_in, 32), filter_extent);
+    filter_for_dgrad_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(filter, c_in, c_out, filter_bw);
+    count_launch();
+    return check_launch("filter_for_dgrad");
+}
+
+}  // extern "C"

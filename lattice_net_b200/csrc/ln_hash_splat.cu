@@ -1,0 +1,340 @@
+// Lattice construction: table clear, splat-build (simplex + warp-deduplicated insertion),
+// distribute, simplex lookup, value accumulation and key coarsening.
+//
+// Reference semantics: kernel_splat / distribute / splatCacheNaive / coarsen in
+// /root/reference/include/lattice_net/kernels/LatticeGPU.cuh:707-842, 534-650, 926-973, 2314-2514.
+#include "ln_common.cuh"
+
+namespace ln {
+
+constexpr int kBlock = 256;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) table_clear_kernel(int4* __restrict__ entries4, int* __restrict__ entries,
+                                                             int* nr_filled, int* status, int capacity) {
+    const int n4 = capacity >> 2;
+    const int stride = gridDim.x * blockDim.x;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = tid; i < n4; i += stride) entries4[i] = make_int4(kEmpty, kEmpty, kEmpty, kEmpty);
+    for (int i = (n4 << 2) + tid; i < capacity; i += stride) entries[i] = kEmpty;
+    if (tid == 0) {
+        *nr_filled = 0;
+        status[0] = 0;
+        status[1] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One thread per point.  The D+1 simplex vertices of spatially close points coincide most of the
+// time, so before touching the table each warp groups equal keys with __match_any_sync and only
+// the group leader probes / inserts; the vertex id is broadcast back with a shuffle.
+template <int D, bool kDistribute, bool kInsert>
+__global__ void __launch_bounds__(kBlock)
+splat_build_kernel(const float* __restrict__ positions_raw, const float* __restrict__ sigmas,
+                   const float* __restrict__ values, int n, int val_dim, TableView table,
+                   int* __restrict__ indices, float* __restrict__ weights, float* __restrict__ distributed) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = idx < n;
+    const unsigned valid_mask = __ballot_sync(kFull, valid);
+
+    Simplex<D> s;
+    float p[D];
+    if (valid) {
+        load_scaled_position<D>(positions_raw, sigmas, idx, p);
+        compute_simplex<D>(p, s);
+    }
+
+    int ids[D + 1];
+#pragma unroll
+    for (int r = 0; r <= D; r++) {
+        int key[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) key[i] = 0;
+        uint32_t h = 0;
+        if (valid) {
+            simplex_key<D>(s, r, key);
+            h = key_hash<D>(key);
+        }
+        int id = -1;
+        if (kInsert) {
+            const unsigned peers = __match_any_sync(kFull, h) & valid_mask;
+            const int leader = valid ? (__ffs(peers) - 1) : lane;
+            bool same = valid;   // same key as the group leader (hash collisions are possible)
+#pragma unroll
+            for (int i = 0; i < D; i++) same &= (__shfl_sync(kFull, key[i], leader) == key[i]);
+            if (valid && (lane == leader || !same)) id = table_insert<D>(table, key, h);
+            const int leader_id = __shfl_sync(kFull, id, leader);
+            if (valid && same) id = leader_id;
+        } else if (valid) {
+            ConstTableView ct{table.keys, table.entries, table.capacity};
+            id = table_find<D>(ct, key);
+        }
+        ids[r] = id;
+    }
+    if (!valid) return;
+
+    if (indices != nullptr) {
+        int* irow = indices + (size_t)idx * (D + 1);
+        float* wrow = weights + (size_t)idx * (D + 1);
+        if (D == 3) {
+            *reinterpret_cast<int4*>(irow) = make_int4(ids[0], ids[1], ids[2], ids[3]);
+            *reinterpret_cast<float4*>(wrow) =
+                make_float4(ids[0] >= 0 ? s.bary[0] : -1.0f, ids[1] >= 0 ? s.bary[1] : -1.0f,
+                            ids[2] >= 0 ? s.bary[2] : -1.0f, ids[3] >= 0 ? s.bary[3] : -1.0f);
+        } else {
+#pragma unroll
+            for (int r = 0; r <= D; r++) {
+                irow[r] = ids[r];
+                wrow[r] = ids[r] >= 0 ? s.bary[r] : -1.0f;
+            }
+        }
+    }
+    if (kDistribute) {
+        // row p*(D+1)+r = [ scaled position | value | barycentric_r ]  (LatticeGPU.cuh:633-645)
+        const int row_len = D + val_dim + 1;
+        float* out = distributed + (size_t)idx * (D + 1) * row_len;
+        const float* v = values + (size_t)idx * val_dim;
+#pragma unroll
+        for (int r = 0; r <= D; r++) {
+            float* o = out + r * row_len;
+#pragma unroll
+            for (int i = 0; i < D; i++) o[i] = p[i];
+            for (int i = 0; i < val_dim; i++) o[D + i] = __ldg(v + i);
+            o[D + val_dim] = s.bary[r];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// values[idx,:] += val[p,:]*w.  Small V (<=4, not a multiple of 4 lanes-wise): one thread per
+// (point, simplex vertex); lanes that target the same vertex are summed in-warp first
+// (warp-aggregated atomics), one RED per distinct vertex per warp.
+template <int V>
+__global__ void __launch_bounds__(kBlock)
+splat_accumulate_small_kernel(const float* __restrict__ values, const int* __restrict__ indices,
+                              const float* __restrict__ weights, int n, int spv /* D+1 */,
+                              float* __restrict__ lattice_values) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)n * spv;
+    const bool valid = t < total;
+    int id = -1;
+    float v[V];
+#pragma unroll
+    for (int j = 0; j < V; j++) v[j] = 0.0f;
+    if (valid) {
+        id = __ldg(indices + t);
+        if (id >= 0) {
+            const float w = __ldg(weights + t);
+            const int p = (int)(t / spv);
+#pragma unroll
+            for (int j = 0; j < V; j++) v[j] = __ldg(values + (size_t)p * V + j) * w;
+        }
+    }
+    const unsigned active = __ballot_sync(kFull, id >= 0);
+    if (id < 0) return;
+    const unsigned peers = __match_any_sync(active, id);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; j++) acc[j] = 0.0f;
+    for (unsigned m = peers; m; m &= m - 1) {   // ascending lane order: deterministic per warp
+        const int src = __ffs(m) - 1;
+#pragma unroll
+        for (int j = 0; j < V; j++) acc[j] += __shfl_sync(peers, v[j], src);
+    }
+    if (lane == leader) {
+        float* out = lattice_values + (size_t)id * V;
+#pragma unroll
+        for (int j = 0; j < V; j++) atomicAdd(out + j, acc[j]);
+    }
+}
+
+// General V: one thread per (point, simplex vertex, channel vector).  Consecutive lanes cover
+// consecutive channels of one vertex row, so every atomic instruction is a run of coalesced
+// 16-byte vector reductions (red.global.add.v4.f32, sm_90+).
+template <int VEC>
+__global__ void __launch_bounds__(kBlock)
+splat_accumulate_vec_kernel(const float* __restrict__ values, const int* __restrict__ indices,
+                            const float* __restrict__ weights, int n, int spv, int val_dim,
+                            float* __restrict__ lattice_values) {
+    const int vpr = val_dim / VEC;   // vectors per row
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)n * spv * vpr;
+    if (t >= total) return;
+    const int j = (int)(t % vpr);
+    const long long pr = t / vpr;
+    const int id = __ldg(indices + pr);
+    if (id < 0) return;
+    const float w = __ldg(weights + pr);
+    const int p = (int)(pr / spv);
+    if (VEC == 4) {
+        float4 x = __ldg(reinterpret_cast<const float4*>(values + (size_t)p * val_dim) + j);
+        x.x *= w; x.y *= w; x.z *= w; x.w *= w;
+        atomicAdd(reinterpret_cast<float4*>(lattice_values + (size_t)id * val_dim) + j, x);
+    } else {
+        atomicAdd(lattice_values + (size_t)id * val_dim + j, __ldg(values + (size_t)p * val_dim + j) * w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// coarsen<d>: one thread per (fine vertex, task); task 0 inserts key/2, task 1+2a / 2+2a handle the
+// np / nm neighbour of axis a.
+template <int D>
+__global__ void __launch_bounds__(kBlock)
+coarsen_kernel(ConstTableView fine, const int* __restrict__ fine_nr_filled, TableView coarse, int nv_upper) {
+    constexpr int kTasks = 1 + 2 * (D + 1);
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = (int)(t / kTasks);
+    const int task = (int)(t % kTasks);
+    if (v >= nv_upper || v >= __ldg(fine_nr_filled)) return;
+    int key[D];
+    bool all_even = true;
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        key[i] = __ldg(fine.keys + (size_t)v * D + i);
+        all_even &= ((key[i] & 1) == 0);
+        sum += key[i];
+    }
+    all_even &= ((sum & 1) == 0);   // the implied last coordinate is -sum
+    if (!all_even) return;
+    int half[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) half[i] = key[i] / 2;   // exact: all coordinates are even
+    if (task == 0) {
+        table_insert<D>(coarse, half, key_hash<D>(half));
+        return;
+    }
+    const int axis = (task - 1) >> 1;
+    const int sgn = ((task - 1) & 1) ? -1 : 1;   // +1: "np", -1: "nm"
+    int nk[D], ck[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        const int step = (i == axis) ? -sgn * D : sgn;
+        nk[i] = key[i] + step;
+        ck[i] = half[i] + step;
+    }
+    if (table_find<D>(fine, nk) >= 0) table_insert<D>(coarse, ck, key_hash<D>(ck));
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int D>
+static int launch_splat_build(const float* positions_raw, const float* sigmas, const float* values, int n, int val_dim,
+                              TableView t, int* indices, float* weights, float* distributed, bool insert,
+                              cudaStream_t s) {
+    if (n == 0) return LN_OK;
+    const int grid = cdiv(n, kBlock);
+    if (distributed != nullptr)
+        splat_build_kernel<D, true, true><<<grid, kBlock, 0, s>>>(positions_raw, sigmas, values, n, val_dim, t, indices, weights, distributed);
+    else if (insert)
+        splat_build_kernel<D, false, true><<<grid, kBlock, 0, s>>>(positions_raw, sigmas, values, n, val_dim, t, indices, weights, nullptr);
+    else
+        splat_build_kernel<D, false, false><<<grid, kBlock, 0, s>>>(positions_raw, sigmas, values, n, val_dim, t, indices, weights, nullptr);
+    count_launch();
+    return check_launch("splat_build");
+}
+
+}  // namespace ln
+
+using namespace ln;
+
+extern "C" {
+
+int ln_table_clear(int* entries, int* nr_filled, int* status, int capacity, void* stream) {
+    LN_REQUIRE(entries && nr_filled && status && capacity > 0, "ln_table_clear: bad argument");
+    const int grid = min(cdiv(max(capacity / 4, 1), kBlock), 148 * 8);
+    table_clear_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(reinterpret_cast<int4*>(entries), entries, nr_filled, status, capacity);
+    count_launch();
+    return check_launch("table_clear");
+}
+
+int ln_splat_build(const float* positions_raw, const float* sigmas, int n, int pos_dim, int* keys, int* entries,
+                   int* nr_filled, int* status, int capacity, int* indices, float* weights, void* stream) {
+    LN_REQUIRE(positions_raw && sigmas && keys && entries && nr_filled && status, "ln_splat_build: null pointer");
+    LN_REQUIRE(n >= 0 && capacity > 0, "ln_splat_build: bad size n=%d capacity=%d", n, capacity);
+    LN_REQUIRE((indices == nullptr) == (weights == nullptr), "ln_splat_build: indices and weights must both be given or both be NULL");
+    TableView t{keys, entries, nr_filled, status, capacity};
+    switch (pos_dim) {
+        case 3: return launch_splat_build<3>(positions_raw, sigmas, nullptr, n, 0, t, indices, weights, nullptr, true, (cudaStream_t)stream);
+        case 5: return launch_splat_build<5>(positions_raw, sigmas, nullptr, n, 0, t, indices, weights, nullptr, true, (cudaStream_t)stream);
+    }
+    set_error("ln_splat_build: unsupported pos_dim %d (3 and 5 are built)", pos_dim);
+    return LN_ERR_UNSUPPORTED;
+}
+
+int ln_distribute(const float* positions_raw, const float* sigmas, const float* values, int n, int pos_dim, int val_dim,
+                  int* keys, int* entries, int* nr_filled, int* status, int capacity, int* indices, float* weights,
+                  float* distributed, void* stream) {
+    LN_REQUIRE(positions_raw && sigmas && values && keys && entries && nr_filled && status && indices && weights && distributed,
+               "ln_distribute: null pointer");
+    LN_REQUIRE(n >= 0 && capacity > 0 && val_dim >= 1, "ln_distribute: bad size");
+    TableView t{keys, entries, nr_filled, status, capacity};
+    switch (pos_dim) {
+        case 3: return launch_splat_build<3>(positions_raw, sigmas, values, n, val_dim, t, indices, weights, distributed, true, (cudaStream_t)stream);
+        case 5: return launch_splat_build<5>(positions_raw, sigmas, values, n, val_dim, t, indices, weights, distributed, true, (cudaStream_t)stream);
+    }
+    set_error("ln_distribute: unsupported pos_dim %d", pos_dim);
+    return LN_ERR_UNSUPPORTED;
+}
+
+int ln_lookup_simplex(const float* positions_raw, const float* sigmas, int n, int pos_dim, const int* keys,
+                      const int* entries, int capacity, int* indices, float* weights, void* stream) {
+    LN_REQUIRE(positions_raw && sigmas && keys && entries && indices && weights, "ln_lookup_simplex: null pointer");
+    LN_REQUIRE(n >= 0 && capacity > 0, "ln_lookup_simplex: bad size");
+    TableView t{const_cast<int*>(keys), const_cast<int*>(entries), nullptr, nullptr, capacity};
+    switch (pos_dim) {
+        case 3: return launch_splat_build<3>(positions_raw, sigmas, nullptr, n, 0, t, indices, weights, nullptr, false, (cudaStream_t)stream);
+        case 5: return launch_splat_build<5>(positions_raw, sigmas, nullptr, n, 0, t, indices, weights, nullptr, false, (cudaStream_t)stream);
+    }
+    set_error("ln_lookup_simplex: unsupported pos_dim %d", pos_dim);
+    return LN_ERR_UNSUPPORTED;
+}
+
+int ln_splat_accumulate(const float* values, const int* indices, const float* weights, int n, int pos_dim, int val_dim,
+                        float* lattice_values, void* stream) {
+    LN_REQUIRE(values && indices && weights && lattice_values, "ln_splat_accumulate: null pointer");
+    LN_REQUIRE(n >= 0 && pos_dim >= 1 && val_dim >= 1, "ln_splat_accumulate: bad size");
+    if (n == 0) return LN_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int spv = pos_dim + 1;
+    const long long rows = (long long)n * spv;
+    if (val_dim <= 3) {
+        const int grid = cdiv(rows, kBlock);
+        if (val_dim == 1) splat_accumulate_small_kernel<1><<<grid, kBlock, 0, s>>>(values, indices, weights, n, spv, lattice_values);
+        if (val_dim == 2) splat_accumulate_small_kernel<2><<<grid, kBlock, 0, s>>>(values, indices, weights, n, spv, lattice_values);
+        if (val_dim == 3) splat_accumulate_small_kernel<3><<<grid, kBlock, 0, s>>>(values, indices, weights, n, spv, lattice_values);
+    } else if (val_dim % 4 == 0) {
+        splat_accumulate_vec_kernel<4><<<cdiv(rows * (val_dim / 4), kBlock), kBlock, 0, s>>>(values, indices, weights, n, spv, val_dim, lattice_values);
+    } else {
+        splat_accumulate_vec_kernel<1><<<cdiv(rows * val_dim, kBlock), kBlock, 0, s>>>(values, indices, weights, n, spv, val_dim, lattice_values);
+    }
+    count_launch();
+    return check_launch("splat_accumulate");
+}
+
+int ln_coarsen_keys(const int* fine_keys, const int* fine_entries, const int* fine_nr_filled, int fine_capacity,
+                    int* coarse_keys, int* coarse_entries, int* coarse_nr_filled, int* coarse_status, int coarse_capacity,
+                    int pos_dim, int nv_fine_upper, void* stream) {
+    LN_REQUIRE(fine_keys && fine_entries && fine_nr_filled && coarse_keys && coarse_entries && coarse_nr_filled && coarse_status,
+               "ln_coarsen_keys: null pointer");
+    LN_REQUIRE(fine_capacity > 0 && coarse_capacity > 0 && nv_fine_upper >= 0, "ln_coarsen_keys: bad size");
+    if (nv_fine_upper == 0) return LN_OK;
+    ConstTableView fine{fine_keys, fine_entries, fine_capacity};
+    TableView coarse{coarse_keys, coarse_entries, coarse_nr_filled, coarse_status, coarse_capacity};
+    cudaStream_t s = (cudaStream_t)stream;
+    if (pos_dim == 3)
+        coarsen_kernel<3><<<cdiv((long long)nv_fine_upper * 9, kBlock), kBlock, 0, s>>>(fine, fine_nr_filled, coarse, nv_fine_upper);
+    else if (pos_dim == 5)
+        coarsen_kernel<5><<<cdiv((long long)nv_fine_upper * 13, kBlock), kBlock, 0, s>>>(fine, fine_nr_filled, coarse, nv_fine_upper);
+    else {
+        set_error("ln_coarsen_keys: unsupported pos_dim %d", pos_dim);
+        return LN_ERR_UNSUPPORTED;
+    }
+    count_launch();
+    return check_launch("coarsen_keys");
+}
+
+}  // extern "C"

@@ -1,0 +1,514 @@
+// Barycentric gather / scatter kernels: slice, gather, fused slice+classify, and their backward
+// passes.  Reference semantics: LatticeGPU.cuh:2552-2595 (slice), 2886-2929 (gather), 3387-3464
+// (slice_classify), 3540-3623 / 3761-3817 / 3628-3756 (backwards).
+//
+// Layout rule used throughout: lanes run along the channel dimension of one vertex row, so every
+// global access is a contiguous (vectorised where val_dim % 4 == 0) run -- the reference maps one
+// thread to one point and walks channels serially (stride-V across the warp).
+#include "ln_common.cuh"
+
+namespace ln {
+
+constexpr int kBlock = 256;
+constexpr int kMaxSpv = 8;   // pos_dim + 1 <= 8
+
+static inline int lanes_per_point(int vectors_per_row) {
+    int lpp = 1;
+    while (lpp < vectors_per_row && lpp < 32) lpp <<= 1;
+    return lpp;
+}
+static inline int ilog2(int x) {
+    int l = 0;
+    while ((1 << l) < x) l++;
+    return l;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(kBlock)
+slice_fwd_kernel(const float* __restrict__ lattice_values, const int* __restrict__ indices,
+                 const float* __restrict__ weights, int n, int spv, int val_dim, int lpp_log2,
+                 float* __restrict__ out) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p = tid >> lpp_log2;
+    if (p >= n) return;
+    const int g = (int)(tid & ((1 << lpp_log2) - 1));
+    const int lpp = 1 << lpp_log2;
+    const int vpr = val_dim / VEC;
+    int id[kMaxSpv];
+    float w[kMaxSpv];
+#pragma unroll
+    for (int r = 0; r < kMaxSpv; r++) {
+        if (r < spv) {
+            id[r] = __ldg(indices + p * spv + r);
+            w[r] = __ldg(weights + p * spv + r);
+        } else {
+            id[r] = -1;
+            w[r] = 0.f;
+        }
+    }
+    for (int c = g; c < vpr; c += lpp) {
+        float acc[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; k++) acc[k] = 0.0f;
+#pragma unroll
+        for (int r = 0; r < kMaxSpv; r++) {
+            if (r < spv && id[r] >= 0) {   // same FMA chain, in the same order, as LatticeGPU.cuh:2575-2585
+                const float* src = lattice_values + (size_t)id[r] * val_dim + (size_t)c * VEC;
+                if (VEC == 4) {
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(src));
+                    acc[0] = fmaf(x.x, w[r], acc[0]);
+                    acc[1] = fmaf(x.y, w[r], acc[1]);
+                    acc[2] = fmaf(x.z, w[r], acc[2]);
+                    acc[3] = fmaf(x.w, w[r], acc[3]);
+                } else {
+                    acc[0] = fmaf(__ldg(src), w[r], acc[0]);
+                }
+            }
+        }
+        float* dst = out + (size_t)p * val_dim + (size_t)c * VEC;
+        if (VEC == 4)
+            *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        else
+            dst[0] = acc[0];
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kBlock)
+slice_bwd_kernel(const float* __restrict__ grad_out, const int* __restrict__ indices,
+                 const float* __restrict__ weights, int n, int spv, int val_dim, int lpp_log2,
+                 float* __restrict__ grad_values) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p = tid >> lpp_log2;
+    if (p >= n) return;
+    const int g = (int)(tid & ((1 << lpp_log2) - 1));
+    const int lpp = 1 << lpp_log2;
+    const int vpr = val_dim / VEC;
+    for (int c = g; c < vpr; c += lpp) {
+        const float* src = grad_out + (size_t)p * val_dim + (size_t)c * VEC;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (VEC == 4)
+            x = __ldg(reinterpret_cast<const float4*>(src));
+        else
+            x.x = __ldg(src);
+        for (int r = 0; r < spv; r++) {
+            const int id = __ldg(indices + p * spv + r);
+            if (id < 0) continue;
+            const float w = __ldg(weights + p * spv + r);
+            float* dst = grad_values + (size_t)id * val_dim + (size_t)c * VEC;
+            if (VEC == 4)
+                atomicAdd(reinterpret_cast<float4*>(dst), make_float4(x.x * w, x.y * w, x.z * w, x.w * w));
+            else
+                atomicAdd(dst, x.x * w);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gather: one thread per output element; row p = (D+1) chunks of [w*values[idx] (V) | w].
+__global__ void __launch_bounds__(kBlock)
+gather_fwd_kernel(const float* __restrict__ lattice_values, const int* __restrict__ indices,
+                  const float* __restrict__ weights, int n, int spv, int val_dim, float* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunk = val_dim + 1;
+    if (t >= (long long)n * spv * chunk) return;
+    const int j = (int)(t % chunk);
+    const long long pr = t / chunk;
+    const int id = __ldg(indices + pr);
+    float r = 0.0f;
+    if (id >= 0) {
+        const float w = __ldg(weights + pr);
+        r = (j < val_dim) ? __ldg(lattice_values + (size_t)id * val_dim + j) * w : w;
+    }
+    out[t] = r;
+}
+
+__global__ void __launch_bounds__(kBlock)
+gather_bwd_kernel(const float* __restrict__ grad_out, const int* __restrict__ indices,
+                  const float* __restrict__ weights, int n, int spv, int val_dim, float* __restrict__ grad_values) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n * spv * val_dim) return;
+    const int j = (int)(t % val_dim);
+    const long long pr = t / val_dim;
+    const int id = __ldg(indices + pr);
+    if (id < 0) return;
+    const float w = __ldg(weights + pr);
+    // the gradient of the trailing weight column is dropped, as in LatticeGPU.cuh:3796-3803
+    atomicAdd(grad_values + (size_t)id * val_dim + j, __ldg(grad_out + pr * (val_dim + 1) + j) * w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// slice_classify forward: one warp per point, lanes along channels (KV = ceil(V/32) channels per
+// lane), classifier weights staged cooperatively in shared memory (the reference lets thread 0
+// copy them serially and accumulates logits through global read-modify-writes).
+template <int KV>
+__global__ void __launch_bounds__(kBlock)
+slice_classify_fwd_kernel(const float* __restrict__ lattice_values, const int* __restrict__ indices,
+                          const float* __restrict__ weights, const float* __restrict__ delta_weights,
+                          const float* __restrict__ cls_weight, const float* __restrict__ cls_bias, int n, int spv,
+                          int val_dim, int nr_classes, float* __restrict__ logits) {
+    extern __shared__ float smem[];
+    float* w_sh = smem;   // [nr_classes][val_dim]
+    for (int i = threadIdx.x; i < nr_classes * val_dim; i += blockDim.x) w_sh[i] = __ldg(cls_weight + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (long long p = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < n;
+         p += (long long)gridDim.x * warps_per_block) {
+        float s[KV];
+#pragma unroll
+        for (int k = 0; k < KV; k++) s[k] = 0.0f;
+        for (int r = 0; r < spv; r++) {
+            const int id = __ldg(indices + p * spv + r);
+            if (id < 0) continue;
+            const float w = __ldg(weights + p * spv + r) + __ldg(delta_weights + p * spv + r);
+#pragma unroll
+            for (int k = 0; k < KV; k++) {
+                const int v = lane + 32 * k;
+                if (v < val_dim) s[k] = fmaf(__ldg(lattice_values + (size_t)id * val_dim + v), w, s[k]);
+            }
+        }
+        float mine = 0.0f;   // lane c%32 keeps logit c (+32: second round)
+        for (int c = 0; c < nr_classes; c++) {
+            float part = 0.0f;
+#pragma unroll
+            for (int k = 0; k < KV; k++) {
+                const int v = lane + 32 * k;
+                if (v < val_dim) part = fmaf(w_sh[c * val_dim + v], s[k], part);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if ((c & 31) == lane) mine = part + __ldg(cls_bias + c);
+            if ((c & 31) == 31 || c == nr_classes - 1) {
+                const int cc = (c & ~31) + lane;
+                if (cc <= c) logits[p * nr_classes + cc] = mine;
+            }
+        }
+    }
+}
+
+// slice_classify backward.  Persistent blocks walk tiles of kTile points:
+//   phase A (warp per point): s_p = sum_r (w+dw) values[idx_r], t_p = g_p * W, scatter
+//            (w+dw)*t_p into the lattice gradient, grad_dw[p,r] = <values[idx_r], t_p>;
+//            s_p and g_p are parked in shared memory;
+//   phase B (all threads): grad_W += G^T S for the tile as a register-accumulated mini GEMM.
+// grad_W / grad_b reach global memory once per block (the reference issues N*nc*V global atomics
+// onto nc*V addresses, LatticeGPU.cuh:3716-3722).
+constexpr int kTile = 32;
+template <int KV>
+__global__ void __launch_bounds__(kBlock)
+slice_classify_bwd_kernel(const float* __restrict__ grad_logits, const float* __restrict__ lattice_values,
+                          const int* __restrict__ indices, const float* __restrict__ weights,
+                          const float* __restrict__ delta_weights, const float* __restrict__ cls_weight, int n,
+                          int spv, int val_dim, int nr_classes, float* __restrict__ grad_lattice_values,
+                          float* __restrict__ grad_delta_weights, float* __restrict__ grad_cls_weight,
+                          float* __restrict__ grad_cls_bias) {
+    extern __shared__ float smem[];
+    float* w_sh = smem;                                 // [nc][V]
+    float* s_sh = w_sh + nr_classes * val_dim;          // [kTile][V]
+    float* g_sh = s_sh + kTile * val_dim;               // [kTile][nc]
+    for (int i = threadIdx.x; i < nr_classes * val_dim; i += blockDim.x) w_sh[i] = __ldg(cls_weight + i);
+
+    constexpr int kMaxAcc = 24;                         // nc*V <= kMaxAcc*kBlock  (checked on the host)
+    float gw_acc[kMaxAcc];
+#pragma unroll
+    for (int i = 0; i < kMaxAcc; i++) gw_acc[i] = 0.0f;
+    float gb_acc = 0.0f;
+    const int n_out = nr_classes * val_dim;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const int n_tiles = (n + kTile - 1) / kTile;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();   // w_sh ready / previous tile's phase B done
+        const int p0 = tile * kTile;
+        const int tile_n = min(kTile, n - p0);
+        for (int pl = warp; pl < kTile; pl += warps_per_block) {
+            float* s_row = s_sh + pl * val_dim;
+            float* g_row = g_sh + pl * nr_classes;
+            if (pl >= tile_n) {   // pad the tile with zeros so phase B needs no bounds
+                for (int v = lane; v < val_dim; v += 32) s_row[v] = 0.0f;
+                for (int c = lane; c < nr_classes; c += 32) g_row[c] = 0.0f;
+                continue;
+            }
+            const long long p = p0 + pl;
+            for (int c = lane; c < nr_classes; c += 32) g_row[c] = __ldg(grad_logits + p * nr_classes + c);
+            __syncwarp();
+            float t[KV], s[KV];
+#pragma unroll
+            for (int k = 0; k < KV; k++) {
+                t[k] = 0.0f;
+                s[k] = 0.0f;
+            }
+            for (int c = 0; c < nr_classes; c++) {
+                const float g = g_row[c];
+#pragma unroll
+                for (int k = 0; k < KV; k++) {
+                    const int v = lane + 32 * k;
+                    if (v < val_dim) t[k] = fmaf(g, w_sh[c * val_dim + v], t[k]);
+                }
+            }
+            for (int r = 0; r < spv; r++) {
+                const int id = __ldg(indices + p * spv + r);
+                float dot = 0.0f;
+                if (id >= 0) {
+                    const float w = __ldg(weights + p * spv + r) + __ldg(delta_weights + p * spv + r);
+#pragma unroll
+                    for (int k = 0; k < KV; k++) {
+                        const int v = lane + 32 * k;
+                        if (v < val_dim) {
+                            const float x = __ldg(lattice_values + (size_t)id * val_dim + v);
+                            s[k] = fmaf(x, w, s[k]);
+                            dot = fmaf(x, t[k], dot);
+                            atomicAdd(grad_lattice_values + (size_t)id * val_dim + v, t[k] * w);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                if (lane == 0) grad_delta_weights[p * spv + r] += dot;   // (p,r) is owned by this warp
+            }
+#pragma unroll
+            for (int k = 0; k < KV; k++) {
+                const int v = lane + 32 * k;
+                if (v < val_dim) s_row[v] = s[k];
+            }
+        }
+        __syncthreads();
+        // phase B: grad_W[c][v] += sum_p G[p][c] * S[p][v]
+#pragma unroll
+        for (int i = 0; i < kMaxAcc; i++) {
+            const int o = threadIdx.x + i * kBlock;
+            if (o < n_out) {
+                const int c = o / val_dim, v = o - c * val_dim;
+                float acc = gw_acc[i];
+#pragma unroll 8
+                for (int pl = 0; pl < kTile; pl++) acc = fmaf(g_sh[pl * nr_classes + c], s_sh[pl * val_dim + v], acc);
+                gw_acc[i] = acc;
+            }
+        }
+        if (threadIdx.x < nr_classes) {
+            for (int pl = 0; pl < kTile; pl++) gb_acc += g_sh[pl * nr_classes + threadIdx.x];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxAcc; i++) {
+        const int o = threadIdx.x + i * kBlock;
+        if (o < n_out) atomicAdd(grad_cls_weight + o, gw_acc[i]);
+    }
+    if (threadIdx.x < nr_classes) atomicAdd(grad_cls_bias + threadIdx.x, gb_acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// PointNet glue: segmented max (+argmax) and sum/count over the rows that share a vertex.
+__device__ __forceinline__ unsigned int float_to_ordered(float f) {
+    const unsigned int b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(unsigned int o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+__global__ void __launch_bounds__(kBlock)
+scatter_max_pack_kernel(const float* __restrict__ src, const int* __restrict__ index, int m, int c,
+                        unsigned long long* __restrict__ packed) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)m * c) return;
+    const int row = (int)(t / c);
+    const int col = (int)(t - (long long)row * c);
+    const int v = __ldg(index + row);
+    // max over (value, -row): the largest value wins, ties go to the smallest row (deterministic)
+    const unsigned long long key =
+        ((unsigned long long)float_to_ordered(__ldg(src + t)) << 32) | (unsigned long long)(0xffffffffu - (unsigned)row);
+    atomicMax(packed + (size_t)v * c + col, key);
+}
+
+__global__ void __launch_bounds__(kBlock)
+scatter_max_unpack_kernel(const unsigned long long* __restrict__ packed, long long total, int m,
+                          float* __restrict__ out_max, int* __restrict__ out_arg) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const unsigned long long key = packed[t];
+    if (key == 0ull) {   // no row maps to this vertex: torch_scatter yields 0 and arg == m
+        out_max[t] = 0.0f;
+        out_arg[t] = m;
+    } else {
+        out_max[t] = ordered_to_float((unsigned int)(key >> 32));
+        out_arg[t] = (int)(0xffffffffu - (unsigned int)(key & 0xffffffffu));
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+scatter_sum_count_kernel(const float* __restrict__ src, const int* __restrict__ index, int m, int c,
+                         float* __restrict__ out_sum, float* __restrict__ out_count) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)m * c) return;
+    const int row = (int)(t / c);
+    const int col = (int)(t - (long long)row * c);
+    const int v = __ldg(index + row);
+    atomicAdd(out_sum + (size_t)v * c + col, __ldg(src + t));
+    if (col == 0 && out_count != nullptr) atomicAdd(out_count + v, 1.0f);
+}
+
+}  // namespace ln
+
+using namespace ln;
+
+#define LN_SLICE_ARGS_OK(name)                                                                              \
+    LN_REQUIRE(n >= 0 && pos_dim >= 1 && pos_dim + 1 <= kMaxSpv && val_dim >= 1, name ": bad size n=%d pos_dim=%d val_dim=%d", n, pos_dim, val_dim)
+
+extern "C" {
+
+int ln_slice_fwd(const float* lattice_values, const int* indices, const float* weights, int n, int pos_dim,
+                 int val_dim, float* out, void* stream) {
+    LN_REQUIRE(lattice_values && indices && weights && out, "ln_slice_fwd: null pointer");
+    LN_SLICE_ARGS_OK("ln_slice_fwd");
+    if (n == 0) return LN_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int vec = (val_dim % 4 == 0) ? 4 : 1;
+    const int lpp = lanes_per_point(val_dim / vec);
+    const int grid = cdiv((long long)n * lpp, kBlock);
+    if (vec == 4)
+        slice_fwd_kernel<4><<<grid, kBlock, 0, s>>>(lattice_values, indices, weights, n, pos_dim + 1, val_dim, ilog2(lpp), out);
+    else
+        slice_fwd_kernel<1><<<grid, kBlock, 0, s>>>(lattice_values, indices, weights, n, pos_dim + 1, val_dim, ilog2(lpp), out);
+    count_launch();
+    return check_launch("slice_fwd");
+}
+
+int ln_slice_bwd(const float* grad_out, const int* indices, const float* weights, int n, int pos_dim, int val_dim,
+                 float* grad_values, void* stream) {
+    LN_REQUIRE(grad_out && indices && weights && grad_values, "ln_slice_bwd: null pointer");
+    LN_SLICE_ARGS_OK("ln_slice_bwd");
+    if (n == 0) return LN_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int vec = (val_dim % 4 == 0) ? 4 : 1;
+    const int lpp = lanes_per_point(val_dim / vec);
+    const int grid = cdiv((long long)n * lpp, kBlock);
+    if (vec == 4)
+        slice_bwd_kernel<4><<<grid, kBlock, 0, s>>>(grad_out, indices, weights, n, pos_dim + 1, val_dim, ilog2(lpp), grad_values);
+    else
+        slice_bwd_kernel<1><<<grid, kBlock, 0, s>>>(grad_out, indices, weights, n, pos_dim + 1, val_dim, ilog2(lpp), grad_values);
+    count_launch();
+    return check_launch("slice_bwd");
+}
+
+int ln_gather_fwd(const float* lattice_values, const int* indices, const float* weights, int n, int pos_dim,
+                  int val_dim, float* out, void* stream) {
+    LN_REQUIRE(lattice_values && indices && weights && out, "ln_gather_fwd: null pointer");
+    LN_SLICE_ARGS_OK("ln_gather_fwd");
+    if (n == 0) return LN_OK;
+    const long long total = (long long)n * (pos_dim + 1) * (val_dim + 1);
+    gather_fwd_kernel<<<cdiv(total, kBlock), kBlock, 0, (cudaStream_t)stream>>>(lattice_values, indices, weights, n, pos_dim + 1, val_dim, out);
+    count_launch();
+    return check_launch("gather_fwd");
+}
+
+int ln_gather_bwd(const float* grad_out, const int* indices, const float* weights, int n, int pos_dim, int val_dim,
+                  float* grad_values, void* stream) {
+    LN_REQUIRE(grad_out && indices && weights && grad_values, "ln_gather_bwd: null pointer");
+    LN_SLICE_ARGS_OK("ln_gather_bwd");
+    if (n == 0) return LN_OK;
+    const long long total = (long long)n * (pos_dim + 1) * val_dim;
+    gather_bwd_kernel<<<cdiv(total, kBlock), kBlock, 0, (cudaStream_t)stream>>>(grad_out, indices, weights, n, pos_dim + 1, val_dim, grad_values);
+    count_launch();
+    return check_launch("gather_bwd");
+}
+
+int ln_slice_classify_fwd(const float* lattice_values, const int* indices, const float* weights,
+                          const float* delta_weights, const float* cls_weight, const float* cls_bias, int n,
+                          int pos_dim, int val_dim, int nr_classes, float* logits, void* stream) {
+    LN_REQUIRE(lattice_values && indices && weights && delta_weights && cls_weight && cls_bias && logits,
+               "ln_slice_classify_fwd: null pointer");
+    LN_SLICE_ARGS_OK("ln_slice_classify_fwd");
+    LN_REQUIRE(nr_classes >= 1, "ln_slice_classify_fwd: nr_classes must be positive");
+    if (n == 0) return LN_OK;
+    if (val_dim > 256) {
+        set_error("ln_slice_classify_fwd: val_dim %d > 256 not built", val_dim);
+        return LN_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = (size_t)nr_classes * val_dim * sizeof(float);
+    const int grid = min(cdiv(n, kBlock / 32), 148 * 8);
+    const int kv = cdiv(val_dim, 32);
+#define LN_LAUNCH_SCF(KV)                                                                                          \
+    do {                                                                                                           \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(slice_classify_fwd_kernel<KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        slice_classify_fwd_kernel<KV><<<grid, kBlock, smem, s>>>(lattice_values, indices, weights, delta_weights, cls_weight, cls_bias, n, pos_dim + 1, val_dim, nr_classes, logits); \
+    } while (0)
+    if (kv <= 1) LN_LAUNCH_SCF(1);
+    else if (kv <= 2) LN_LAUNCH_SCF(2);
+    else if (kv <= 4) LN_LAUNCH_SCF(4);
+    else LN_LAUNCH_SCF(8);
+#undef LN_LAUNCH_SCF
+    count_launch();
+    return check_launch("slice_classify_fwd");
+}
+
+int ln_slice_classify_bwd(const float* grad_logits, const float* lattice_values, const int* indices,
+                          const float* weights, const float* delta_weights, const float* cls_weight, int n,
+                          int pos_dim, int val_dim, int nr_classes, float* grad_lattice_values,
+                          float* grad_delta_weights, float* grad_cls_weight, float* grad_cls_bias, void* stream) {
+    LN_REQUIRE(grad_logits && lattice_values && indices && weights && delta_weights && cls_weight && grad_lattice_values &&
+                   grad_delta_weights && grad_cls_weight && grad_cls_bias,
+               "ln_slice_classify_bwd: null pointer");
+    LN_SLICE_ARGS_OK("ln_slice_classify_bwd");
+    LN_REQUIRE(nr_classes >= 1, "ln_slice_classify_bwd: nr_classes must be positive");
+    if (n == 0) return LN_OK;
+    if (val_dim > 256 || (long long)nr_classes * val_dim > 24LL * kBlock || nr_classes > kBlock) {
+        set_error("ln_slice_classify_bwd: val_dim %d x nr_classes %d outside the built range (val_dim<=256, product<=6144)", val_dim, nr_classes);
+        return LN_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = ((size_t)nr_classes * val_dim + (size_t)kTile * val_dim + (size_t)kTile * nr_classes) * sizeof(float);
+    const int grid = min(cdiv(n, kTile), 148 * 2);
+    const int kv = cdiv(val_dim, 32);
+#define LN_LAUNCH_SCB(KV)                                                                                          \
+    do {                                                                                                           \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(slice_classify_bwd_kernel<KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        slice_classify_bwd_kernel<KV><<<grid, kBlock, smem, s>>>(grad_logits, lattice_values, indices, weights, delta_weights, cls_weight, n, pos_dim + 1, val_dim, nr_classes, grad_lattice_values, grad_delta_weights, grad_cls_weight, grad_cls_bias); \
+    } while (0)
+    if (kv <= 1) LN_LAUNCH_SCB(1);
+    else if (kv <= 2) LN_LAUNCH_SCB(2);
+    else if (kv <= 4) LN_LAUNCH_SCB(4);
+    else LN_LAUNCH_SCB(8);
+#undef LN_LAUNCH_SCB
+    count_launch();
+    return check_launch("slice_classify_bwd");
+}
+
+int ln_scatter_max(const float* src, const int* index, int m, int c, int nv, float* out_max, int* out_arg,
+                   unsigned long long* workspace, void* stream) {
+    LN_REQUIRE(src && index && out_max && out_arg && workspace, "ln_scatter_max: null pointer");
+    LN_REQUIRE(m >= 0 && c >= 1 && nv >= 0, "ln_scatter_max: bad size");
+    if (nv == 0) return LN_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long total = (long long)nv * c;
+    if (cudaMemsetAsync(workspace, 0, total * sizeof(unsigned long long), s) != cudaSuccess) return check_launch("scatter_max memset");
+    if (m > 0) {
+        scatter_max_pack_kernel<<<cdiv((long long)m * c, kBlock), kBlock, 0, s>>>(src, index, m, c, workspace);
+        count_launch();
+    }
+    scatter_max_unpack_kernel<<<cdiv(total, kBlock), kBlock, 0, s>>>(workspace, total, m, out_max, out_arg);
+    count_launch();
+    return check_launch("scatter_max");
+}
+
+int ln_scatter_sum_count(const float* src, const int* index, int m, int c, int nv, float* out_sum, float* out_count,
+                         void* stream) {
+    LN_REQUIRE(src && index && out_sum, "ln_scatter_sum_count: null pointer");
+    LN_REQUIRE(m >= 0 && c >= 1 && nv >= 0, "ln_scatter_sum_count: bad size");
+    if (nv == 0) return LN_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(out_sum, 0, (size_t)nv * c * sizeof(float), s);
+    if (out_count) cudaMemsetAsync(out_count, 0, (size_t)nv * sizeof(float), s);
+    if (m > 0) {
+        scatter_sum_count_kernel<<<cdiv((long long)m * c, kBlock), kBlock, 0, s>>>(src, index, m, c, out_sum, out_count);
+        count_launch();
+    }
+    return check_launch("scatter_sum_count");
+}
+
+}  // extern "C"

@@ -1,0 +1,651 @@
+"""`Lattice` / `HashTable`: host-side mirror of the reference's pybind classes
+(/root/reference/src/PyBridge.cxx:33-113, /root/reference/src/Lattice.cu, /root/reference/src/HashTable.cu).
+
+Same method names, arguments, return tuples, dtypes and shapes as the reference; every device
+operation goes through the C ABI of include/lattice_b200.h (hand-written sm_100a kernels).  PyTorch
+is used only to own device memory and for the current stream.
+
+What is deliberately different from the reference host code (results are identical):
+  * positions are divided by sigma inside the kernels (no extra launch, Lattice.cu:226);
+  * index / weight tables need no `fill_(-1)` pre-pass (Lattice.cu:214-215): every cell is written;
+  * the vertex count is read back ONCE per lattice structure and shared by all handles that alias
+    that structure (the reference re-syncs on every cloned handle, Lattice.cu:1326-1338 + :97-98);
+  * the 1-hop neighbourhood is looked up once per (query, neighbour, dilation) and cached on the
+    structure; convolutions consume the table directly and never materialise the im2row buffer
+    (Lattice.cu:454-462);
+  * the tensors' device is honoured (the reference hard-codes cuda:0), which scene-parallel
+    multi-GPU training needs;
+  * a full hash table raises instead of hanging (HashTableGPU.cuh:443-484 has no probe limit).
+"""
+import ctypes
+import weakref
+
+import torch
+
+from . import _cabi
+from ._cabi import call, ptr, stream_ptr
+from .params import lattice_settings, parse_cfg
+
+# conv arithmetic: 0 = exact fp32 (CUDA cores), 1 = tcgen05 3xTF32 (fp32-equivalent), 2 = tcgen05 TF32
+CONV_PRECISION = 0
+
+
+def set_conv_precision(mode):
+    global CONV_PRECISION
+    assert mode in (0, 1, 2)
+    CONV_PRECISION = mode
+
+
+def _check(cond, msg):
+    # the reference aborts through loguru CHECK (Lattice.cu:162-181); here it is an exception
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _as_cuda_f32(t, device):
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"expected a float32 tensor, got {t.dtype}")
+    return t.to(device).contiguous()
+
+
+class _Structure:
+    """Key set of one lattice level: the device arrays of HashTableGPU (HashTableGPU.cuh:23-28).
+    Shared by every handle that aliases the same vertices (the reference shares the tensors between
+    clones, Lattice.cu:89-95)."""
+
+    def __init__(self, capacity, pos_dim, device, zero_keys=True):
+        self.capacity = int(capacity)
+        self.pos_dim = int(pos_dim)
+        self.device = device
+        alloc = torch.zeros if zero_keys else torch.empty
+        self.keys = alloc((self.capacity, self.pos_dim), dtype=torch.int32, device=device)
+        self.entries = torch.empty((self.capacity,), dtype=torch.int32, device=device)
+        self.nr_filled = torch.zeros((1,), dtype=torch.int32, device=device)
+        self.status = torch.zeros((2,), dtype=torch.int32, device=device)
+        self.nv = None            # host copy of nr_filled, None = dirty
+        self.max_probe = 0
+        self.neighbour_cache = {}
+        self.clear()
+
+    def clear(self):
+        call("ln_table_clear", ptr(self.entries), ptr(self.nr_filled), ptr(self.status), self.capacity, stream_ptr(self.device))
+        self.mark_dirty()
+
+    def mark_dirty(self):
+        self.nv = None
+        self.neighbour_cache.clear()
+
+    def nr_vertices(self):
+        if self.nv is None:
+            nv = ctypes.c_int(0)
+            probe = ctypes.c_int(0)
+            call("ln_table_status", ptr(self.nr_filled), ptr(self.status), ctypes.byref(nv), ctypes.byref(probe), stream_ptr(self.device))
+            self.nv = int(nv.value)
+            self.max_probe = int(probe.value)
+        return self.nv
+
+    def copy(self):
+        other = _Structure.__new__(_Structure)
+        other.capacity, other.pos_dim, other.device = self.capacity, self.pos_dim, self.device
+        other.keys = self.keys.clone()
+        other.entries = self.entries.clone()
+        other.nr_filled = self.nr_filled.clone()
+        other.status = self.status.clone()
+        other.nv, other.max_probe, other.neighbour_cache = self.nv, self.max_probe, {}
+        return other
+
+
+class HashTable:
+    """Python-visible part of the reference's HashTable (PyBridge.cxx:33-39): `m_keys_tensor`,
+    `m_nr_filled_tensor`; plus the per-handle values tensor."""
+
+    def __init__(self, capacity):
+        self.m_capacity = int(capacity)
+        self.structure = None
+        self.m_values_tensor = None
+
+    @property
+    def m_keys_tensor(self):
+        return None if self.structure is None else self.structure.keys
+
+    @property
+    def m_entries_tensor(self):
+        return None if self.structure is None else self.structure.entries
+
+    @property
+    def m_nr_filled_tensor(self):
+        return None if self.structure is None else self.structure.nr_filled
+
+    def is_initialized(self):
+        return self.structure is not None
+
+    def init(self, pos_dim, val_dim, device):
+        # HashTable::init (HashTable.cu:21-47)
+        self.structure = _Structure(self.m_capacity, pos_dim, device)
+        self.m_values_tensor = torch.zeros((self.m_capacity, val_dim), dtype=torch.float32, device=device)
+
+    def capacity(self):
+        return self.m_capacity
+
+    def pos_dim(self):
+        _check(self.structure is not None, "hash table is not initialised: splat or distribute something first")
+        return self.structure.pos_dim
+
+    def val_dim(self):
+        _check(self.m_values_tensor is not None, "hash table has no values yet")
+        return int(self.m_values_tensor.shape[1])
+
+    def set_values(self, new_values):
+        self.m_values_tensor = new_values.contiguous()   # HashTable.cu:112-115: kept by reference
+
+
+class Lattice:
+    """The user-visible lattice handle (reference: class Lattice, /root/reference/src/Lattice.cu)."""
+
+    m_expected_position_dimensions = -1   # static in the reference too (Lattice.cu:44,143)
+
+    # ---- construction ------------------------------------------------------------------------
+    def __init__(self, capacity=None, sigmas=None, name="", _clone_of=None):
+        self.m_name = name
+        self.m_lvl = 1
+        self.m_positions = None
+        self.m_sigmas = []
+        self.m_sigmas_val_and_extent = []
+        self._sigmas_dev = {}
+        if _clone_of is not None:
+            return
+        _check(capacity is not None and sigmas is not None, "Lattice needs a capacity and sigmas (or use Lattice.create(cfg))")
+        self.m_hash_table = HashTable(int(capacity))
+        self.set_sigmas(list(sigmas))
+
+    @staticmethod
+    def create(config, name=""):
+        """Lattice.create(cfg_path[, name]) (PyBridge.cxx:46-47; Lattice::init_params Lattice.cu:107-132).
+        `config` may also be an already parsed dict, or another Lattice (clone, Lattice.cu:73-101)."""
+        if isinstance(config, Lattice):
+            return config.clone_lattice()
+        cfg = config if isinstance(config, dict) else parse_cfg(config)
+        capacity, sigmas = lattice_settings(cfg)
+        return Lattice(capacity, sigmas, name)
+
+    def clone_lattice(self):
+        # Lattice::Lattice(Lattice* other), Lattice.cu:73-101: shares structure + values, keeps level/sigmas
+        other = Lattice(_clone_of=self)
+        other.m_lvl = self.m_lvl
+        other.m_sigmas = list(self.m_sigmas)
+        other.m_sigmas_val_and_extent = list(self.m_sigmas_val_and_extent)
+        other.m_positions = self.m_positions
+        other.m_hash_table = HashTable(self.m_hash_table.m_capacity)
+        other.m_hash_table.structure = self.m_hash_table.structure
+        other.m_hash_table.m_values_tensor = self.m_hash_table.m_values_tensor
+        return other
+
+    def set_sigmas(self, sigmas_list):
+        # Lattice::set_sigmas, Lattice.cu:134-160
+        self.m_sigmas_val_and_extent = [(float(s), int(n)) for s, n in sigmas_list]
+        self.m_sigmas = [s for s, n in self.m_sigmas_val_and_extent for _ in range(n)]
+        Lattice.m_expected_position_dimensions = len(self.m_sigmas)
+        self._sigmas_dev = {}
+
+    def set_sigma(self, sigma):
+        _check(len(self.m_sigmas_val_and_extent) == 1, "set_sigma assumes a single sigma group")   # Lattice.cu:1379
+        self.m_sigmas = [float(sigma)] * len(self.m_sigmas)
+        self._sigmas_dev = {}
+
+    def increase_sigmas(self, stepsize):
+        self.m_sigmas = [s + float(stepsize) for s in self.m_sigmas]
+        self._sigmas_dev = {}
+
+    # ---- small getters -------------------------------------------------------------------------
+    def name(self):
+        return self.m_name
+
+    def set_name(self, name):
+        self.m_name = name
+
+    def val_dim(self):
+        return self.m_hash_table.val_dim()
+
+    def pos_dim(self):
+        return self.m_hash_table.pos_dim()
+
+    def capacity(self):
+        return self.m_hash_table.capacity()
+
+    def lvl(self):
+        return self.m_lvl
+
+    def positions(self):
+        return self.m_positions
+
+    def set_positions(self, positions_raw):
+        self.m_positions = positions_raw
+
+    def hash_table(self):
+        return self.m_hash_table
+
+    def values(self):
+        return self.m_hash_table.m_values_tensor
+
+    def sigmas_tensor(self):
+        return torch.tensor(self.m_sigmas, dtype=torch.float32)
+
+    def nr_lattice_vertices(self):
+        _check(self.m_hash_table.structure is not None, "lattice has no vertices yet")
+        return self.m_hash_table.structure.nr_vertices()
+
+    def get_filter_extent(self, neighborhood_size):
+        _check(neighborhood_size == 1, "only a 1-hop neighbourhood is implemented")   # Lattice.cu:1349
+        return 2 * (self.pos_dim() + 1) + 1
+
+    @staticmethod
+    def get_expected_filter_extent(neighborhood_size):
+        _check(neighborhood_size == 1, "only a 1-hop neighbourhood is implemented")
+        _check(Lattice.m_expected_position_dimensions > 0, "create a Lattice first: the expected position dimension comes from its sigmas")
+        return 2 * (Lattice.m_expected_position_dimensions + 1) + 1
+
+    def set_values(self, new_values):
+        # Lattice::set_values, Lattice.cu:1394-1398
+        self.m_hash_table.set_values(new_values)
+        _check(new_values.shape[0] == self.nr_lattice_vertices(),
+               f"set_values: {new_values.shape[0]} rows but the lattice has {self.nr_lattice_vertices()} vertices")
+
+    # ---- helpers ---------------------------------------------------------------------------------
+    def _device_of(self, t):
+        if t is not None and t.is_cuda:
+            return t.device
+        st = self.m_hash_table.structure
+        return st.device if st is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def _sigmas_on(self, device):
+        key = str(device)
+        if key not in self._sigmas_dev:
+            self._sigmas_dev[key] = torch.tensor(self.m_sigmas, dtype=torch.float32, device=device)
+        return self._sigmas_dev[key]
+
+    def _check_positions(self, positions_raw):
+        # Lattice::check_positions, Lattice.cu:162-170
+        _check(positions_raw.dtype == torch.float32, "positions should be of type float")
+        _check(positions_raw.dim() == 2, f"positions should have dim 2, got sizes {tuple(positions_raw.shape)}")
+        _check(len(self.m_sigmas) == positions_raw.shape[1],
+               f"one sigma per position dimension is needed: {len(self.m_sigmas)} sigmas, pos_dim {positions_raw.shape[1]}")
+        _check(positions_raw.is_contiguous(), "positions_raw is not contiguous, call .contiguous() on it")
+        _check(positions_raw.shape[1] == Lattice.m_expected_position_dimensions,
+               f"pos dim {positions_raw.shape[1]} differs from the expected {Lattice.m_expected_position_dimensions}")
+
+    def _check_values(self, values):
+        _check(values.dtype == torch.float32, "values should be of type float")
+        _check(values.dim() == 2, f"values should have dim 2, got sizes {tuple(values.shape)}")
+        _check(values.is_contiguous(), "values is not contiguous, call .contiguous() on it")
+
+    def _structure(self):
+        st = self.m_hash_table.structure
+        _check(st is not None, "lattice has no vertices yet")
+        return st
+
+    def _neighbour_table(self, lattice_neighbours, dilation):
+        """int32 [nv_query x F] vertex ids of `lattice_neighbours` around each vertex of self."""
+        q, n = self._structure(), lattice_neighbours._structure()
+        _check(abs(self.m_lvl - lattice_neighbours.m_lvl) <= 1,
+               f"query lvl {self.m_lvl} and neighbour lvl {lattice_neighbours.m_lvl} may differ by one at most")   # Lattice.cu:442
+        key = (id(n), int(dilation), self.m_lvl - lattice_neighbours.m_lvl)
+        hit = q.neighbour_cache.get(key)
+        if hit is not None and hit[0]() is n:   # weak reference: no cycles between lattice levels
+            return hit[1]
+        nv = q.nr_vertices()
+        _check(nv != 0, "why does this lattice have zero vertices?")   # Lattice.cu:443
+        n.nr_vertices()   # surfaces a table overflow of the neighbour lattice before it is read
+        F = 2 * (q.pos_dim + 1) + 1
+        table = torch.empty((nv, F), dtype=torch.int32, device=q.device)
+        call("ln_neighbour_table", ptr(q.keys), nv, q.pos_dim, ptr(n.keys), ptr(n.entries), n.capacity,
+             self.m_lvl - lattice_neighbours.m_lvl, int(dilation), ptr(table), stream_ptr(q.device))
+        q.neighbour_cache[key] = (weakref.ref(n), table)
+        return table
+
+    # ---- splat / distribute -----------------------------------------------------------------------
+    def begin_splat(self, reset_hashmap=True):
+        # Lattice::begin_splat, Lattice.cu:185-193 (HashTable::clear / clear_only_values)
+        ht = self.m_hash_table
+        if ht.is_initialized():
+            if ht.m_values_tensor is not None:
+                if ht.m_values_tensor.shape[0] != ht.m_capacity:
+                    ht.m_values_tensor = torch.zeros((ht.m_capacity, ht.m_values_tensor.shape[1]), dtype=torch.float32, device=ht.structure.device)
+                else:
+                    ht.m_values_tensor.zero_()
+            if reset_hashmap:
+                ht.structure.clear()
+
+    def splat_standalone(self, positions_raw, values):
+        """-> (splatting_indices i32 [N(d+1)], splatting_weights f32 [N(d+1)]); values() is [capacity x V]."""
+        _check(positions_raw.shape[0] == values.shape[0], "positions and values need the same number of rows")
+        self._check_positions(positions_raw)
+        self._check_values(values)
+        device = self._device_of(positions_raw)
+        n, d = positions_raw.shape
+        v = values.shape[1]
+        self.m_positions = positions_raw
+        ht = self.m_hash_table
+        if not ht.is_initialized():
+            ht.init(d, v, device)
+        st = ht.structure
+        pos = _as_cuda_f32(positions_raw, st.device)
+        val = _as_cuda_f32(values, st.device)
+        if ht.m_values_tensor is None or tuple(ht.m_values_tensor.shape) != (ht.m_capacity, v):
+            ht.m_values_tensor = torch.zeros((ht.m_capacity, v), dtype=torch.float32, device=st.device)
+        idx = torch.empty((n * (d + 1),), dtype=torch.int32, device=st.device)
+        w = torch.empty((n * (d + 1),), dtype=torch.float32, device=st.device)
+        s = stream_ptr(st.device)
+        if n > 0:
+            call("ln_splat_build", ptr(pos), ptr(self._sigmas_on(st.device)), n, d, ptr(st.keys), ptr(st.entries),
+                 ptr(st.nr_filled), ptr(st.status), st.capacity, ptr(idx), ptr(w), s)
+            call("ln_splat_accumulate", ptr(val), ptr(idx), ptr(w), n, d, v, ptr(ht.m_values_tensor), s)
+        st.mark_dirty()
+        return idx, w
+
+    def just_create_verts(self, positions_raw, return_indices_and_weights):
+        self._check_positions(positions_raw)
+        device = self._device_of(positions_raw)
+        n, d = positions_raw.shape
+        ht = self.m_hash_table
+        if not ht.is_initialized():
+            ht.init(d, 1, device)
+        st = ht.structure
+        pos = _as_cuda_f32(positions_raw, st.device)
+        idx = w = None
+        if return_indices_and_weights:
+            idx = torch.empty((n * (d + 1),), dtype=torch.int32, device=st.device)
+            w = torch.empty((n * (d + 1),), dtype=torch.float32, device=st.device)
+        if n > 0:
+            call("ln_splat_build", ptr(pos), ptr(self._sigmas_on(st.device)), n, d, ptr(st.keys), ptr(st.entries),
+                 ptr(st.nr_filled), ptr(st.status), st.capacity, ptr(idx), ptr(w), stream_ptr(st.device))
+        st.mark_dirty()
+        return idx, w
+
+    def distribute(self, positions_raw, values, reset_hashmap=True):
+        """-> (distributed_lattice, distributed [N(d+1) x (d+V+1)], indices, weights)  (Lattice.cu:351-410)."""
+        _check(positions_raw.shape[0] == values.shape[0], "positions and values need the same number of rows")
+        self._check_positions(positions_raw)
+        self._check_values(values)
+        device = self._device_of(positions_raw)
+        n, d = positions_raw.shape
+        v = values.shape[1]
+        self.m_positions = positions_raw
+        ht = self.m_hash_table
+        if not ht.is_initialized():
+            ht.init(d, v, device)
+        parent = ht.structure
+        dev = parent.device
+        pos = _as_cuda_f32(positions_raw, dev)
+        val = _as_cuda_f32(values, dev)
+        new = self.clone_lattice()
+        new.m_name = "distributed_lattice"
+        # the reference clones the parent's table and clears it (Lattice.cu:377-390); a fresh table is the same thing
+        new.m_hash_table.structure = _Structure(parent.capacity, d, dev) if reset_hashmap else parent.copy()
+        if ht.m_values_tensor is not None and ht.m_values_tensor.shape[1] == v:
+            new.m_hash_table.m_values_tensor = torch.zeros_like(ht.m_values_tensor)
+        else:
+            new.m_hash_table.m_values_tensor = torch.zeros((ht.m_capacity, v), dtype=torch.float32, device=dev)
+        st = new.m_hash_table.structure
+        distributed = torch.empty((n * (d + 1), d + v + 1), dtype=torch.float32, device=dev)
+        idx = torch.empty((n * (d + 1),), dtype=torch.int32, device=dev)
+        w = torch.empty((n * (d + 1),), dtype=torch.float32, device=dev)
+        if n > 0:
+            call("ln_distribute", ptr(pos), ptr(self._sigmas_on(dev)), ptr(val), n, d, v, ptr(st.keys), ptr(st.entries),
+                 ptr(st.nr_filled), ptr(st.status), st.capacity, ptr(idx), ptr(w), ptr(distributed), stream_ptr(dev))
+        st.mark_dirty()
+        return new, distributed, idx, w
+
+    def expand(self, positions_raw, point_multiplier, noise_stddev, expand_values):
+        # Lattice::expand, Lattice.cu:292-348
+        self._check_positions(positions_raw)
+        device = self._device_of(positions_raw)
+        d = positions_raw.shape[1]
+        ht = self.m_hash_table
+        if not ht.is_initialized():
+            ht.init(d, 1, device)
+        st0 = ht.structure
+        pos = _as_cuda_f32(positions_raw, st0.device)
+        expanded_pos = pos.repeat(point_multiplier, 1)
+        expanded_pos = expanded_pos + torch.randn_like(expanded_pos) * noise_stddev
+        new = self.clone_lattice()
+        new.m_name = "expanded_lattice"
+        new.m_hash_table.structure = st0.copy()
+        new.m_hash_table.m_values_tensor = torch.zeros((1, self.val_dim()), dtype=torch.float32, device=st0.device)
+        new.just_create_verts(expanded_pos.contiguous(), False)
+        if expand_values:
+            diff = new.nr_lattice_vertices() - self.nr_lattice_vertices()
+            _check(diff >= 0, "expanding a lattice can only add vertices")
+            new.set_values(torch.nn.functional.pad(self.values(), (0, 0, 0, diff)))
+        return new
+
+    # ---- coarse levels ---------------------------------------------------------------------------
+    def _new_coarse_handle(self):
+        st = self._structure()
+        coarse = self.clone_lattice()
+        coarse.m_name = "coarse_lattice"
+        coarse.m_lvl = self.m_lvl + 1
+        coarse.m_sigmas = [s * 2.0 for s in self.m_sigmas]   # Lattice.cu:678-682
+        coarse.m_sigmas_val_and_extent = [(s * 2.0, n) for s, n in self.m_sigmas_val_and_extent]
+        coarse._sigmas_dev = {}
+        coarse.m_hash_table = HashTable(st.capacity)
+        coarse.m_hash_table.structure = _Structure(st.capacity, st.pos_dim, st.device)
+        coarse.m_hash_table.m_values_tensor = torch.zeros((1, self.val_dim()), dtype=torch.float32, device=st.device)
+        return coarse
+
+    def create_coarse_verts(self):
+        # Lattice::create_coarse_verts, Lattice.cu:670-703 (coarsen<d> kernel)
+        st = self._structure()
+        nv = st.nr_vertices()
+        coarse = self._new_coarse_handle()
+        cst = coarse.m_hash_table.structure
+        call("ln_coarsen_keys", ptr(st.keys), ptr(st.entries), ptr(st.nr_filled), st.capacity, ptr(cst.keys),
+             ptr(cst.entries), ptr(cst.nr_filled), ptr(cst.status), cst.capacity, st.pos_dim, nv, stream_ptr(st.device))
+        cst.mark_dirty()
+        coarse.m_hash_table.m_values_tensor = torch.zeros((coarse.nr_lattice_vertices(), self.val_dim()), dtype=torch.float32, device=st.device)
+        return coarse
+
+    def create_coarse_verts_naive(self, positions_raw):
+        # Lattice::create_coarse_verts_naive, Lattice.cu:706-740: splat the raw points at 2*sigma
+        self._check_positions(positions_raw)
+        coarse = self._new_coarse_handle()
+        coarse.just_create_verts(positions_raw, False)
+        return coarse
+
+    # ---- convolution -----------------------------------------------------------------------------
+    def convolve_im2row_standalone(self, filter_bank, dilation, lattice_neighbours=None, flip_neighbours=False, bias=None):
+        """values_new[nv_self x nr_filters] = im2row(lattice_neighbours) . filter_bank, as one implicit-GEMM
+        kernel (Lattice.cu:424-474).  Returns a new handle sharing this lattice's structure."""
+        nbrs = self if lattice_neighbours is None else lattice_neighbours
+        _check(filter_bank is not None and filter_bank.dim() == 2, "filter bank should be 2-D: (filter_extent*val_dim) x nr_filters")
+        st = self._structure()
+        vn = nbrs.val_dim()
+        nr_filters = int(filter_bank.shape[1])
+        F = int(filter_bank.shape[0]) // vn
+        _check(F == self.get_filter_extent(1) and F * vn == filter_bank.shape[0],
+               f"filter extent should be {self.get_filter_extent(1)} but the filter bank has {filter_bank.shape[0]} rows for val_dim {vn}")
+        table = self._neighbour_table(nbrs, dilation)
+        nv = st.nr_vertices()
+        vals = nbrs.values()
+        _check(vals.shape[0] >= nbrs.nr_lattice_vertices(), "neighbour lattice values have fewer rows than vertices")
+        fb = _as_cuda_f32(filter_bank, st.device)
+        out = torch.empty((nv, nr_filters), dtype=torch.float32, device=st.device)
+        call("ln_conv_fwd", ptr(vals.contiguous()), ptr(table), ptr(fb), ptr(bias), nv, F, vn, nr_filters,
+             1 if flip_neighbours else 0, CONV_PRECISION, ptr(out), stream_ptr(st.device))
+        new = self.clone_lattice()
+        new.m_name = "convolved_lattice"
+        new.m_hash_table.set_values(out)
+        return new
+
+    def conv_weight_grad(self, lattice_neighbours, grad_values, filter_extent, dilation):
+        """grad_filter = im2row(lattice_neighbours)^T . grad_values without the rowified buffer
+        (lattice_funcs.py:298-302).  Extension of the reference API used by the autograd Functions."""
+        nbrs = self if lattice_neighbours is None else lattice_neighbours
+        st = self._structure()
+        table = self._neighbour_table(nbrs, dilation)
+        nv = st.nr_vertices()
+        vn = nbrs.val_dim()
+        g = _as_cuda_f32(grad_values, st.device)
+        _check(g.shape[0] == nv, "grad_values rows must match the query lattice")
+        grad_filter = torch.empty((filter_extent * vn, g.shape[1]), dtype=torch.float32, device=st.device)
+        call("ln_conv_wgrad", ptr(nbrs.values().contiguous()), ptr(table), ptr(g), nv, filter_extent, vn,
+             int(g.shape[1]), ptr(grad_filter), stream_ptr(st.device))
+        return grad_filter
+
+    @staticmethod
+    def filter_for_data_grad(filter_bank, filter_extent, val_dim):
+        """[F*val_dim x nr_filters] -> [F*nr_filters x val_dim] (lattice_funcs.py:304-311) in one kernel."""
+        fb = filter_bank.contiguous()
+        nr_filters = int(fb.shape[1])
+        out = torch.empty((filter_extent * nr_filters, val_dim), dtype=torch.float32, device=fb.device)
+        call("ln_filter_for_dgrad", ptr(fb), filter_extent, val_dim, nr_filters, ptr(out), stream_ptr(fb.device))
+        return out
+
+    def im2row(self, lattice_neighbours, filter_extent, dilation, flip_neighbours):
+        nbrs = self if lattice_neighbours is None else lattice_neighbours
+        _check(filter_extent == self.get_filter_extent(1), f"filter extent should be {self.get_filter_extent(1)}")
+        st = self._structure()
+        table = self._neighbour_table(nbrs, dilation)
+        nv, vn = st.nr_vertices(), nbrs.val_dim()
+        out = torch.empty((nv, filter_extent * vn), dtype=torch.float32, device=st.device)
+        call("ln_im2row", ptr(nbrs.values().contiguous()), ptr(table), nv, filter_extent, vn, 1 if flip_neighbours else 0,
+             ptr(out), stream_ptr(st.device))
+        return out
+
+    def im2rowindices(self, lattice_neighbours, filter_extent, dilation, flip_neighbours):
+        nbrs = self if lattice_neighbours is None else lattice_neighbours
+        _check(filter_extent == self.get_filter_extent(1), f"filter extent should be {self.get_filter_extent(1)}")
+        st = self._structure()
+        table = self._neighbour_table(nbrs, dilation)
+        nv, vn = st.nr_vertices(), nbrs.val_dim()
+        out = torch.empty((nv, filter_extent * vn), dtype=torch.int32, device=st.device)
+        call("ln_im2rowindices", ptr(table), nv, filter_extent, vn, 1 if flip_neighbours else 0, ptr(out), stream_ptr(st.device))
+        return out
+
+    def row2im(self, lattice_rowified, dilation, filter_extent, nr_filters, lattice_neighbours=None):
+        # Lattice::row2im, Lattice.cu:646-667: replaces this handle's values
+        nbrs = self if lattice_neighbours is None else lattice_neighbours
+        _check(lattice_rowified.is_contiguous(), "lattice rowified is not contiguous, call .contiguous() on it")
+        _check(lattice_rowified.shape[1] // filter_extent == self.val_dim(), "each row of the rowified lattice should be val_dim*filter_extent long")
+        st = self._structure()
+        table = self._neighbour_table(nbrs, dilation)
+        nv, v = st.nr_vertices(), self.val_dim()
+        out = torch.empty((nv, v), dtype=torch.float32, device=st.device)
+        call("ln_row2im", ptr(lattice_rowified), ptr(table), nv, filter_extent, v, ptr(out), stream_ptr(st.device))
+        self.m_hash_table.m_values_tensor = out
+        return out
+
+    # ---- slice family ------------------------------------------------------------------------------
+    def _slice_prep(self, positions_raw, idx, w):
+        self._check_positions(positions_raw)
+        _check(self.val_dim() > 0, "splat something first so that there are values to slice")
+        n, d = positions_raw.shape
+        _check(d == self.pos_dim(), "position dimension differs from the one the lattice was created with")
+        if idx is not None:
+            _check(idx.numel() == n * (d + 1) and w.numel() == n * (d + 1),
+                   f"indices / weights should have {n * (d + 1)} elements, got {tuple(idx.shape)} and {tuple(w.shape)}")   # Lattice.cu:771-773
+            idx, w = idx.contiguous(), w.contiguous()
+        return n, d, idx, w
+
+    def slice_standalone_with_precomputation(self, positions_raw, splatting_indices, splatting_weights):
+        n, d, idx, w = self._slice_prep(positions_raw, splatting_indices, splatting_weights)
+        vals = self.values().contiguous()
+        out = torch.empty((n, self.val_dim()), dtype=torch.float32, device=vals.device)
+        call("ln_slice_fwd", ptr(vals), ptr(idx), ptr(w), n, d, self.val_dim(), ptr(out), stream_ptr(vals.device))
+        return out
+
+    def slice_standalone_no_precomputation(self, positions_raw):
+        n, d, _, _ = self._slice_prep(positions_raw, None, None)
+        st = self._structure()
+        pos = _as_cuda_f32(positions_raw, st.device)
+        idx = torch.empty((n * (d + 1),), dtype=torch.int32, device=st.device)
+        w = torch.empty((n * (d + 1),), dtype=torch.float32, device=st.device)
+        call("ln_lookup_simplex", ptr(pos), ptr(self._sigmas_on(st.device)), n, d, ptr(st.keys), ptr(st.entries),
+             st.capacity, ptr(idx), ptr(w), stream_ptr(st.device))
+        return self.slice_standalone_with_precomputation(positions_raw, idx, w), idx, w
+
+    def gather_standalone_with_precomputation(self, positions_raw, splatting_indices, splatting_weights):
+        n, d, idx, w = self._slice_prep(positions_raw, splatting_indices, splatting_weights)
+        vals = self.values().contiguous()
+        v = self.val_dim()
+        out = torch.empty((n, (d + 1) * (v + 1)), dtype=torch.float32, device=vals.device)
+        call("ln_gather_fwd", ptr(vals), ptr(idx), ptr(w), n, d, v, ptr(out), stream_ptr(vals.device))
+        return out
+
+    def gather_standalone_no_precomputation(self, positions_raw):
+        # the reference's kernel for this is ill-formed (LatticeGPU.cuh:2875); composing lookup + gather gives
+        # what it evidently intends
+        n, d, _, _ = self._slice_prep(positions_raw, None, None)
+        st = self._structure()
+        pos = _as_cuda_f32(positions_raw, st.device)
+        idx = torch.empty((n * (d + 1),), dtype=torch.int32, device=st.device)
+        w = torch.empty((n * (d + 1),), dtype=torch.float32, device=st.device)
+        call("ln_lookup_simplex", ptr(pos), ptr(self._sigmas_on(st.device)), n, d, ptr(st.keys), ptr(st.entries),
+             st.capacity, ptr(idx), ptr(w), stream_ptr(st.device))
+        return self.gather_standalone_with_precomputation(positions_raw, idx, w), idx, w
+
+    def slice_classify_with_precomputation(self, positions_raw, delta_weights, linear_clasify_weight, linear_clasify_bias,
+                                           nr_classes, splatting_indices, splatting_weights):
+        n, d, idx, w = self._slice_prep(positions_raw, splatting_indices, splatting_weights)
+        vals = self.values().contiguous()
+        dev = vals.device
+        dw = _as_cuda_f32(delta_weights, dev)
+        cw = _as_cuda_f32(linear_clasify_weight, dev)
+        cb = _as_cuda_f32(linear_clasify_bias, dev)
+        _check(tuple(cw.shape) == (nr_classes, self.val_dim()), "classifier weight should be nr_classes x val_dim")
+        out = torch.empty((n, nr_classes), dtype=torch.float32, device=dev)
+        call("ln_slice_classify_fwd", ptr(vals), ptr(idx), ptr(w), ptr(dw), ptr(cw), ptr(cb), n, d, self.val_dim(),
+             int(nr_classes), ptr(out), stream_ptr(dev))
+        return out
+
+    def slice_classify_no_precomputation(self, positions_raw, delta_weights, linear_clasify_weight, linear_clasify_bias, nr_classes):
+        n, d, _, _ = self._slice_prep(positions_raw, None, None)
+        st = self._structure()
+        pos = _as_cuda_f32(positions_raw, st.device)
+        idx = torch.empty((n * (d + 1),), dtype=torch.int32, device=st.device)
+        w = torch.empty((n * (d + 1),), dtype=torch.float32, device=st.device)
+        call("ln_lookup_simplex", ptr(pos), ptr(self._sigmas_on(st.device)), n, d, ptr(st.keys), ptr(st.entries),
+             st.capacity, ptr(idx), ptr(w), stream_ptr(st.device))
+        logits = self.slice_classify_with_precomputation(positions_raw, delta_weights, linear_clasify_weight,
+                                                         linear_clasify_bias, nr_classes, idx, w)
+        return logits, idx, w
+
+    def slice_backwards_standalone_with_precomputation(self, *args, **kwargs):
+        # the reference's wrapper targets a kernel that is commented out (LatticeGPU.cuh:3467-3536)
+        raise RuntimeError("slice_backwards_standalone_with_precomputation has no kernel in the reference either; "
+                           "use slice_backwards_standalone_with_precomputation_no_homogeneous")
+
+    def slice_backwards_standalone_with_precomputation_no_homogeneous(self, positions_raw, grad_sliced_values,
+                                                                      splatting_indices, splatting_weights):
+        # Lattice.cu:1067-1088: the handle's values become the gradient w.r.t. the lattice values
+        n, d, idx, w = self._slice_prep(positions_raw, splatting_indices, splatting_weights)
+        _check(grad_sliced_values.dim() == 2 and grad_sliced_values.is_contiguous(), "grad_sliced_values must be 2-D and contiguous")
+        st = self._structure()
+        v = int(grad_sliced_values.shape[1])
+        grad = torch.zeros((st.nr_vertices(), v), dtype=torch.float32, device=st.device)
+        call("ln_slice_bwd", ptr(grad_sliced_values), ptr(idx), ptr(w), n, d, v, ptr(grad), stream_ptr(st.device))
+        self.m_hash_table.m_values_tensor = grad
+
+    def gather_backwards_standalone_with_precomputation(self, positions_raw, grad_sliced_values, splatting_indices, splatting_weights):
+        # Lattice.cu:1117-1142
+        n, d, idx, w = self._slice_prep(positions_raw, splatting_indices, splatting_weights)
+        _check(grad_sliced_values.dim() == 2 and grad_sliced_values.is_contiguous(), "grad_sliced_values must be 2-D and contiguous")
+        st = self._structure()
+        v = int(grad_sliced_values.shape[1]) // (d + 1) - 1
+        grad = torch.zeros((st.nr_vertices(), v), dtype=torch.float32, device=st.device)
+        call("ln_gather_bwd", ptr(grad_sliced_values), ptr(idx), ptr(w), n, d, v, ptr(grad), stream_ptr(st.device))
+        self.m_hash_table.m_values_tensor = grad
+
+    def slice_classify_backwards_with_precomputation(self, grad_class_logits, positions_raw, initial_values, delta_weights,
+                                                     linear_clasify_weight, linear_clasify_bias, nr_classes,
+                                                     grad_lattice_values, grad_delta_weights, grad_linear_clasify_weight,
+                                                     grad_linear_clasify_bias, splatting_indices, splatting_weights):
+        # Lattice.cu:1091-1115: accumulates into the four caller-allocated (zeroed) gradients
+        n, d, idx, w = self._slice_prep(positions_raw, splatting_indices, splatting_weights)
+        _check(grad_class_logits.dim() == 2 and grad_class_logits.is_contiguous(), "grad_class_logits must be 2-D and contiguous")
+        vals = initial_values.contiguous()
+        dev = vals.device
+        for t in (grad_lattice_values, grad_delta_weights, grad_linear_clasify_weight, grad_linear_clasify_bias):
+            _check(t.is_contiguous() and t.is_cuda, "gradient buffers must be contiguous CUDA tensors")
+        call("ln_slice_classify_bwd", ptr(grad_class_logits), ptr(vals), ptr(idx), ptr(w), ptr(delta_weights.contiguous()),
+             ptr(linear_clasify_weight.contiguous()), n, d, int(vals.shape[1]), int(nr_classes), ptr(grad_lattice_values),
+             ptr(grad_delta_weights), ptr(grad_linear_clasify_weight), ptr(grad_linear_clasify_bias), stream_ptr(dev))

@@ -1,0 +1,50 @@
+"""Losses of the reference's training step: NLL on the log-softmax plus
+the Lovasz-softmax surrogate of the mean IoU (Berman et al. 2018), which
+/root/reference/latticenet_py/ln_train.py:156-158 combines 50/50.  Plain PyTorch: not part of the
+lattice hot path, present so the benchmark times the same step the reference runs."""
+import torch
+
+
+def lovasz_grad(gt_sorted):
+    """Gradient of the Lovasz extension of the Jaccard loss w.r.t. sorted errors."""
+    gts = gt_sorted.sum()
+    intersection = gts - gt_sorted.cumsum(0)
+    union = gts + (1.0 - gt_sorted).cumsum(0)
+    jaccard = 1.0 - intersection / union
+    if gt_sorted.numel() > 1:
+        jaccard[1:] = jaccard[1:] - jaccard[:-1]
+    return jaccard
+
+
+def lovasz_softmax(probas, labels, ignore_index=None):
+    """probas [P, C] (class probabilities), labels [P] (int64).  Mean over the classes present."""
+    if ignore_index is not None:
+        keep = labels != ignore_index
+        probas, labels = probas[keep], labels[keep]
+    if probas.numel() == 0:
+        return probas.sum() * 0.0
+    losses = []
+    for c in range(probas.shape[1]):
+        fg = (labels == c).float()
+        if fg.sum() == 0:
+            continue
+        errors = (fg - probas[:, c]).abs()
+        errors_sorted, perm = torch.sort(errors, 0, descending=True)
+        losses.append(torch.dot(errors_sorted, lovasz_grad(fg[perm])))
+    return torch.stack(losses).mean()
+
+
+class LovaszSoftmax(torch.nn.Module):
+    def __init__(self, ignore_index=None):
+        super().__init__()
+        self.ignore_index = ignore_index
+
+    def forward(self, logsoftmax, labels):
+        return lovasz_softmax(logsoftmax.exp(), labels, self.ignore_index)
+
+
+def segmentation_loss(logsoftmax, labels, ignore_index=-100):
+    """0.5 * Lovasz-softmax + 0.5 * NLL, as in ln_train.py:156-158."""
+    nll = torch.nn.functional.nll_loss(logsoftmax, labels, ignore_index=ignore_index)
+    lov = lovasz_softmax(logsoftmax.exp(), labels, ignore_index if ignore_index >= 0 else None)
+    return 0.5 * lov + 0.5 * nll

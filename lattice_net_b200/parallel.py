@@ -1,0 +1,93 @@
+"""Scene-level data parallelism.  The reference is single-process /
+single-GPU; each point cloud builds its own lattice, so the only natural shard is the scene.  One
+process per GPU; the lattice is never split; the only exchange per step is ONE all-reduce of all
+weight / bias gradients over NCCL (NVLink 5 / NVSwitch), done in place on a flat fp32 bucket that the
+parameters' `.grad` tensors alias (no pack / unpack copies).
+
+The model creates parameters lazily during its first forward (lattice_modules.py creates PointNet /
+deltaW / classifier layers on first use), so the bucket is laid out after a warm-up forward --
+the same reason the reference creates its optimizer late (ln_train.py:163-165).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend=None):
+    """Initialise torch.distributed from the torchrun environment (no-op for a single process).
+    Returns (rank, world_size, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local_rank
+
+
+def scenes_for_rank(nr_scenes, rank, world):
+    """Rank r takes scenes r, r+W, r+2W, ..."""
+    return list(range(rank, nr_scenes, world))
+
+
+class GradBucket:
+    """All parameter gradients of a model as views into one flat fp32 buffer."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params, "no trainable parameters (run a warm-up forward first: they are created lazily)"
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+        self.nbytes = total * 4
+
+    def zero(self):
+        self.flat.zero_()
+
+    def reattach(self):
+        """optimizer.zero_grad(set_to_none=True) or autograd may replace .grad; re-alias and keep values."""
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            view = self.flat[off:off + n].view_as(p)
+            if p.grad is None:
+                view.zero_()
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
+            off += n
+
+    def allreduce_mean(self, world):
+        """One collective for the whole model; averages over ranks."""
+        if world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.mul_(1.0 / world)
+
+
+def broadcast_parameters(model, src=0):
+    """Make every rank start from rank `src`'s (lazily created) parameters, in one flat broadcast."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    params = [p for p in model.parameters()]
+    flat = torch.cat([p.detach().reshape(-1) for p in params])
+    dist.broadcast(flat, src)
+    off = 0
+    with torch.no_grad():
+        for p in params:
+            n = p.numel()
+            p.copy_(flat[off:off + n].view_as(p))
+            off += n

@@ -1,0 +1,366 @@
+"""Parity tests proper: the CUDA path, called through the C ABI via the `Lattice` handle, against
+  (1) the reference's own kernels run live on the same GPU (oracle/ref_cuda.py), and
+  (2) the CPU oracle (oracle/lattice_oracle.py) / the committed golden vectors.
+Integers (keys, vertex counts, index tables, neighbour tables) must be bit-exact after the canonical
+key sort; weights are expected bit-equal; accumulated values within the stated fp32 tolerances.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, lattice_oracle as lo
+from tests.util import assert_close, bits_equal, canonical, max_rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_VALUES = 1e-4   # north_star: max rel-err <= 1e-4 on values (atomic / accumulation order differs)
+TOL_GRADS = 1e-3    # and <= 1e-3 on gradients
+
+
+def _lattice(spec):
+    from lattice_net_b200 import Lattice
+    d = len(spec["sigmas"])
+    return Lattice(spec["capacity"], [(s, 1) for s in spec["sigmas"]])
+
+
+def _ref():
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    return ref_cuda
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module", params=list(cases.CASES))
+def built(request):
+    """Build the same lattice with our kernels, the reference kernels and the CPU oracle."""
+    name = request.param
+    spec = cases.CASES[name]
+    pos_np = spec["make"]()
+    pos = cuda(pos_np)
+    n, d = pos_np.shape
+    vals_np = cases.randn((n, 3), 10)
+    ours = _lattice(spec)
+    ours.begin_splat()
+    idx, w = ours.splat_standalone(pos, cuda(vals_np))
+    nv = ours.nr_lattice_vertices()
+    keys = ours.hash_table().m_keys_tensor[:nv].cpu().numpy()
+    ks, o2n, n2o = canonical(keys)
+    ref_mod = _ref()
+    ref = ref_mod.RefLattice(spec["capacity"], spec["sigmas"])
+    ridx, rw = ref.splat(pos, cuda(vals_np))
+    rnv = ref.nv()
+    rks, ro2n, rn2o = canonical(ref.table.keys[:rnv].cpu().numpy())
+    cpu = lo.build_lattice(pos_np, spec["sigmas"])
+    return dict(name=name, spec=spec, pos_np=pos_np, pos=pos, n=n, d=d, vals_np=vals_np, ours=ours, idx=idx, w=w, nv=nv,
+                ks=ks, o2n=o2n, n2o=n2o, ref=ref, ridx=ridx, rw=rw, rnv=rnv, rks=rks, ro2n=ro2n, rn2o=rn2o, cpu=cpu)
+
+
+def test_structure_bit_exact(built):
+    b = built
+    assert b["nv"] == b["rnv"] == b["cpu"]["nv"]
+    assert np.array_equal(b["ks"], b["rks"]), "key set differs from the reference kernels"
+    assert np.array_equal(b["ks"], b["cpu"]["keys"]), "key set differs from the CPU oracle"
+    ours_idx = lo.relabel(b["idx"].cpu().numpy(), b["o2n"])
+    ref_idx = lo.relabel(b["ridx"].cpu().numpy(), b["ro2n"])
+    assert np.array_equal(ours_idx, ref_idx), f"{(ours_idx != ref_idx).sum()} splatting indices differ from the reference"
+    assert np.array_equal(ours_idx, b["cpu"]["indices"])
+    assert bits_equal(b["w"].cpu().numpy(), b["rw"].cpu().numpy()) == 0, "barycentric weights are not bit-equal to the reference"
+    assert bits_equal(b["w"].cpu().numpy(), b["cpu"]["weights"]) == 0, "barycentric weights are not bit-equal to the CPU oracle"
+    # compact ids: a permutation of 0..nv-1, every key exactly once
+    assert len(np.unique(b["ks"], axis=0)) == b["nv"]
+
+
+def test_splat_values(built):
+    b = built
+    ours = b["ours"].values()
+    assert tuple(ours.shape) == (b["spec"]["capacity"], 3)           # [capacity x V], like the reference
+    ours_np = ours[:b["nv"]].cpu().numpy()[b["n2o"]]
+    ref_np = b["ref"].values[:b["nv"]].cpu().numpy()[b["rn2o"]]
+    assert_close(ours_np, ref_np, TOL_VALUES, "splat values vs reference kernels")
+    assert_close(ours_np, lo.splat_accumulate(b["vals_np"], b["cpu"]["indices"], b["cpu"]["weights"], b["nv"]), TOL_VALUES, "splat values vs oracle")
+    assert float(ours[b["nv"]:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("V", [1, 4, 8, 32, 64, 3])
+def test_splat_accumulate_widths(built, V):
+    b = built
+    from lattice_net_b200._cabi import call, ptr, stream_ptr
+    vals = cases.randn((b["n"], V), 100 + V)
+    out = torch.zeros((b["nv"], V), device="cuda")
+    call("ln_splat_accumulate", ptr(cuda(vals)), ptr(b["idx"]), ptr(b["w"]), b["n"], b["d"], V, ptr(out), stream_ptr())
+    exp = lo.splat_accumulate(vals, b["idx"].cpu().numpy(), b["w"].cpu().numpy(), b["nv"])
+    assert_close(out.cpu().numpy(), exp, TOL_VALUES, f"splat accumulate V={V}")
+
+
+def test_distribute(built):
+    b = built
+    spec, pos = b["spec"], b["pos"]
+    dv = cases.randn((b["n"], 1), 11)
+    ours = _lattice(spec)
+    ours.begin_splat()
+    dl, distributed, idx, w = ours.distribute(pos, cuda(dv))
+    ref = _ref().RefLattice(spec["capacity"], spec["sigmas"])
+    rdist, ridx, rw = ref.distribute(pos, cuda(dv))
+    nv = dl.nr_lattice_vertices()
+    assert nv == ref.nv() == b["nv"]
+    ks, o2n, _ = canonical(dl.hash_table().m_keys_tensor[:nv].cpu().numpy())
+    rks, ro2n, _ = canonical(ref.table.keys[:nv].cpu().numpy())
+    assert np.array_equal(ks, rks)
+    assert np.array_equal(lo.relabel(idx.cpu().numpy(), o2n), lo.relabel(ridx.cpu().numpy(), ro2n))
+    assert bits_equal(w.cpu().numpy(), rw.cpu().numpy()) == 0
+    assert bits_equal(distributed.cpu().numpy(), rdist.cpu().numpy()) == 0, "distributed rows are not bit-equal"
+    assert ours.nr_lattice_vertices() == 0          # the parent lattice stays empty (Lattice.cu:377-390)
+
+
+@pytest.mark.parametrize("V", [1, 8, 32])
+def test_slice_fwd_bwd(built, V):
+    b = built
+    lv = cases.randn((b["nv"], V), 20 + V)                       # canonical order
+    ours, ref = b["ours"].clone_lattice(), b["ref"]
+    ours.set_values(cuda(lv[b["o2n"]]))
+    sliced = ours.slice_standalone_with_precomputation(b["pos"], b["idx"], b["w"])
+    rsliced = ref.slice_with_precomputation(b["pos"], cuda(lv[b["ro2n"]]), b["ridx"], b["rw"])
+    assert bits_equal(sliced.cpu().numpy(), rsliced.cpu().numpy()) == 0, "slice forward is not bit-equal (same FMA chain expected)"
+    assert_close(sliced.cpu().numpy(), lo.slice_fwd(lv, b["cpu"]["indices"], b["cpu"]["weights"], b["n"]), 1e-6, "slice vs oracle")
+    g = cases.randn((b["n"], V), 30 + V)
+    ours.slice_backwards_standalone_with_precomputation_no_homogeneous(b["pos"], cuda(g), b["idx"], b["w"])
+    grad = ours.values().cpu().numpy()[b["n2o"]]
+    rgrad = ref.slice_backwards(cuda(g), b["ridx"], b["rw"]).cpu().numpy()[b["rn2o"]]
+    assert_close(grad, rgrad, TOL_GRADS, "slice backward vs reference kernels")
+    assert_close(grad, lo.slice_bwd(g, b["cpu"]["indices"], b["cpu"]["weights"], b["nv"]), TOL_GRADS, "slice backward vs oracle")
+
+
+def test_slice_no_precomputation(built):
+    b = built
+    lv = cases.randn((b["nv"], 8), 28)
+    ours, ref = b["ours"].clone_lattice(), b["ref"]
+    ours.set_values(cuda(lv[b["o2n"]]))
+    for shift in (0.0, 0.013):      # shifted positions: some simplex vertices are missing -> -1 entries
+        pos = cuda((b["pos_np"] + np.float32(shift)).astype(np.float32))
+        s, i, w = ours.slice_standalone_no_precomputation(pos)
+        rs, ri, rw = ref.slice_no_precomputation(pos, cuda(lv[b["ro2n"]]))
+        assert np.array_equal(lo.relabel(i.cpu().numpy(), b["o2n"]), lo.relabel(ri.cpu().numpy(), b["ro2n"]))
+        assert bits_equal(w.cpu().numpy(), rw.cpu().numpy()) == 0
+        assert bits_equal(s.cpu().numpy(), rs.cpu().numpy()) == 0
+        if shift:
+            assert int((i < 0).sum()) > 0
+
+
+def test_gather_fwd_bwd(built):
+    b = built
+    V = 8
+    lv = cases.randn((b["nv"], V), 28)
+    ours, ref = b["ours"].clone_lattice(), b["ref"]
+    ours.set_values(cuda(lv[b["o2n"]]))
+    g = ours.gather_standalone_with_precomputation(b["pos"], b["idx"], b["w"])
+    rg = ref.gather_with_precomputation(b["pos"], cuda(lv[b["ro2n"]]), b["ridx"], b["rw"])
+    assert bits_equal(g.cpu().numpy(), rg.cpu().numpy()) == 0
+    assert_close(g.cpu().numpy(), lo.gather_fwd(lv, b["cpu"]["indices"], b["cpu"]["weights"], b["n"]), 1e-6, "gather vs oracle")
+    gg = cases.randn((b["n"], (b["d"] + 1) * (V + 1)), 40)
+    ours.gather_backwards_standalone_with_precomputation(b["pos"], cuda(gg), b["idx"], b["w"])
+    grad = ours.values().cpu().numpy()[b["n2o"]]
+    rgrad = ref.gather_backwards(cuda(gg), b["ridx"], b["rw"]).cpu().numpy()[b["rn2o"]]
+    assert_close(grad, rgrad, TOL_GRADS, "gather backward vs reference kernels")
+    assert_close(grad, lo.gather_bwd(gg, b["cpu"]["indices"], b["cpu"]["weights"], b["nv"], V), TOL_GRADS, "gather backward vs oracle")
+
+
+@pytest.mark.parametrize("V,nc", [(32, 7), (128, 20), (8, 4)])
+def test_slice_classify(built, V, nc):
+    b = built
+    if b["d"] != 3:
+        pytest.skip("reference slice_classify instantiations are built for pos_dim 3")
+    n, d = b["n"], b["d"]
+    lv = cases.randn((b["nv"], V), 20 + V)
+    dw = (cases.randn((n, d + 1), 50) * 0.05).astype(np.float32)
+    cw = (cases.randn((nc, V), 51) * 0.2).astype(np.float32)
+    cb = cases.randn((nc,), 52)
+    gl = cases.randn((n, nc), 53)
+    ours, ref = b["ours"].clone_lattice(), b["ref"]
+    lv_ours = cuda(lv[b["o2n"]])
+    ours.set_values(lv_ours)
+    logits = ours.slice_classify_with_precomputation(b["pos"], cuda(dw), cuda(cw), cuda(cb), nc, b["idx"], b["w"])
+    rlogits = ref.slice_classify_with_precomputation(b["pos"], cuda(lv[b["ro2n"]]), cuda(dw), cuda(cw), cuda(cb), b["ridx"], b["rw"])
+    exp, _ = lo.slice_classify_fwd(lv, b["cpu"]["indices"], b["cpu"]["weights"], dw, cw, cb, n)
+    assert_close(logits.cpu().numpy(), rlogits.cpu().numpy(), TOL_VALUES, "slice_classify logits vs reference kernels")
+    assert_close(logits.cpu().numpy(), exp, TOL_VALUES, "slice_classify logits vs oracle")
+    g_lv, g_dw, g_w, g_b = [torch.zeros_like(t) for t in (lv_ours, cuda(dw), cuda(cw), cuda(cb))]
+    ours.slice_classify_backwards_with_precomputation(cuda(gl), b["pos"], lv_ours, cuda(dw), cuda(cw), cuda(cb), nc,
+                                                      g_lv, g_dw, g_w, g_b, b["idx"], b["w"])
+    r = ref.slice_classify_backwards(cuda(gl), cuda(lv[b["ro2n"]]), cuda(dw), cuda(cw), cuda(cb), b["ridx"], b["rw"])
+    e = lo.slice_classify_bwd(gl, lv, b["cpu"]["indices"], b["cpu"]["weights"], dw, cw, n)
+    got = [g_lv.cpu().numpy()[b["n2o"]], g_dw.cpu().numpy(), g_w.cpu().numpy(), g_b.cpu().numpy()]
+    refs = [r[0].cpu().numpy()[b["rn2o"]], r[1].cpu().numpy(), r[2].cpu().numpy(), r[3].cpu().numpy()]
+    for name, a, rr, ee in zip(("grad_values", "grad_delta_w", "grad_W", "grad_b"), got, refs, e):
+        assert_close(a, ee, TOL_GRADS, f"slice_classify {name} vs oracle")
+        assert_close(a, rr, TOL_GRADS, f"slice_classify {name} vs reference kernels")
+
+
+def _rowidx(lat_q, lat_n, dil, flip, o2n_n, n2o_q, F):
+    r = lat_q.im2rowindices(lat_n, F, dil, flip).cpu().numpy().reshape(-1, F, lat_n.val_dim())[:, :, 0]
+    return lo.relabel(r, o2n_n).astype(np.int32)[n2o_q]
+
+
+def _ref_rowidx(ref_q, ref_n, dil, flip, o2n_n, n2o_q, F):
+    r = ref_q.im2rowindices(ref_n, 1, dil, flip).cpu().numpy().reshape(-1, F)
+    return lo.relabel(r, o2n_n).astype(np.int32)[n2o_q]
+
+
+def test_neighbour_tables_same_level(built):
+    b = built
+    F = 2 * (b["d"] + 1) + 1
+    ours = b["ours"].clone_lattice()
+    ours.set_values(torch.zeros((b["nv"], 1), device="cuda"))
+    for dil in (1, 2):
+        exp = lo.neighbour_table(b["ks"], b["ks"], 0, dil)
+        for flip in (False, True):
+            got = _rowidx(ours, ours, dil, flip, b["o2n"], b["n2o"], F)
+            ref = _ref_rowidx(b["ref"], b["ref"], dil, flip, b["ro2n"], b["rn2o"], F)
+            assert np.array_equal(got, ref), f"im2rowindices dil={dil} flip={flip} differs from the reference kernels"
+            assert np.array_equal(got, lo.im2rowindices(exp, 1, flip).reshape(-1, F)), "differs from the oracle"
+
+
+def test_coarse_levels(built):
+    b = built
+    F = 2 * (b["d"] + 1) + 1
+    ours = b["ours"].clone_lattice()
+    ours.set_values(torch.zeros((b["nv"], 1), device="cuda"))
+    coarse = ours.create_coarse_verts_naive(b["pos"])
+    rcoarse = b["ref"].create_coarse_verts_naive(b["pos"])
+    nvc = coarse.nr_lattice_vertices()
+    assert nvc == rcoarse.nv()
+    cks, co2n, cn2o = canonical(coarse.hash_table().m_keys_tensor[:nvc].cpu().numpy())
+    rcks, rco2n, rcn2o = canonical(rcoarse.table.keys[:nvc].cpu().numpy())
+    assert np.array_equal(cks, rcks)
+    assert coarse.lvl() == 2 and coarse.m_sigmas == [s * 2.0 for s in ours.m_sigmas]
+    coarse.set_values(torch.zeros((nvc, 1), device="cuda"))
+    # coarse <- fine  (coarsen forward) and fine <- coarse (finefy forward / coarsen backward)
+    got = _rowidx(coarse, ours, 1, False, b["o2n"], cn2o, F)
+    ref = _ref_rowidx(rcoarse, b["ref"], 1, False, b["ro2n"], rcn2o, F)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(got, lo.im2rowindices(lo.neighbour_table(cks, b["ks"], 1, 1), 1).reshape(-1, F))
+    for flip in (False, True):
+        got = _rowidx(ours, coarse, 1, flip, co2n, b["n2o"], F)
+        ref = _ref_rowidx(b["ref"], rcoarse, 1, flip, rco2n, b["rn2o"], F)
+        assert np.array_equal(got, ref)
+        assert np.array_equal(got, lo.im2rowindices(lo.neighbour_table(b["ks"], cks, -1, 1), 1, flip).reshape(-1, F))
+    # coarsen<d> kernel (create_coarse_verts)
+    kc = ours.create_coarse_verts()
+    rkc = b["ref"].create_coarse_verts()
+    kk, _, _ = canonical(kc.hash_table().m_keys_tensor[:kc.nr_lattice_vertices()].cpu().numpy())
+    rkk, _, _ = canonical(rkc.table.keys[:rkc.nv()].cpu().numpy())
+    assert np.array_equal(kk, rkk)
+    assert np.array_equal(kk, lo.coarsen_keys(b["ks"]))
+
+
+@pytest.mark.parametrize("Cin,Cout", [(8, 16), (32, 32), (3, 5), (64, 128)])
+def test_conv_fwd_wgrad_dgrad(built, Cin, Cout):
+    b = built
+    F = 2 * (b["d"] + 1) + 1
+    lv = cases.randn((b["nv"], Cin), 70 + Cin)
+    fb = (cases.randn((F * Cin, Cout), 60) * 0.1).astype(np.float32)
+    ours = b["ours"].clone_lattice()
+    ours.set_values(cuda(lv[b["o2n"]]))
+    out = ours.convolve_im2row_standalone(cuda(fb), 1, ours, False)
+    got = out.values().cpu().numpy()[b["n2o"]]
+    table = lo.neighbour_table(b["ks"], b["ks"], 0, 1)
+    exp = lo.conv_fwd(lv, table, fb)
+    assert_close(got, exp, TOL_VALUES, "conv forward vs oracle")
+    ref = b["ref"]
+    if ref.k.has(f"im2row<{b['d']},{Cin}>"):
+        rout = ref.convolve(cuda(fb), ref, cuda(lv[b["ro2n"]]), 1, False).cpu().numpy()[b["rn2o"]]
+        assert_close(got, rout, TOL_VALUES, "conv forward vs reference im2row+mm")
+        rows = ours.im2row(ours, F, 1, False).cpu().numpy()[b["n2o"]]
+        rrows = ref.im2row(ref, cuda(lv[b["ro2n"]]), 1, False).cpu().numpy()[b["rn2o"]]
+        assert bits_equal(rows, rrows) == 0, "im2row differs from the reference"
+    # weight gradient and data gradient
+    g = cases.randn((b["nv"], Cout), 80 + Cout)
+    gw = ours.conv_weight_grad(ours, cuda(g[b["o2n"]]), F, 1).cpu().numpy()
+    assert_close(gw, lo.conv_wgrad(lv, table, g), TOL_GRADS, "conv weight gradient vs oracle")
+    from lattice_net_b200 import Lattice
+    fbw = Lattice.filter_for_data_grad(cuda(fb), F, Cin)
+    assert np.array_equal(fbw.cpu().numpy(), lo.filter_for_dgrad(fb, F, Cin, Cout))
+    q = ours.clone_lattice()
+    q.set_values(cuda(g[b["o2n"]]))
+    dg = ours.convolve_im2row_standalone(fbw, 1, q, True).values().cpu().numpy()[b["n2o"]]
+    assert_close(dg, lo.conv_fwd(g, table, lo.filter_for_dgrad(fb, F, Cin, Cout), flip=True), TOL_GRADS, "conv data gradient vs oracle")
+    # data gradient must be the adjoint of the forward: <conv(x), g> == <x, dgrad(g)>
+    lhs = float((exp.astype(np.float64) * g).sum())
+    rhs = float((lv.astype(np.float64) * dg).sum())
+    assert abs(lhs - rhs) <= 1e-3 * max(abs(lhs), 1.0)
+
+
+def test_row2im(built):
+    b = built
+    F = 2 * (b["d"] + 1) + 1
+    V = 8
+    lv = cases.randn((b["nv"], V), 28)
+    ours, ref = b["ours"].clone_lattice(), b["ref"]
+    ours.set_values(cuda(lv[b["o2n"]]))
+    rows = ours.im2row(ours, F, 1, False)
+    back = ours.row2im(rows, 1, F, 16, ours).cpu().numpy()[b["n2o"]]
+    rrows = ref.im2row(ref, cuda(lv[b["ro2n"]]), 1, False)
+    rback = ref.row2im(rrows, ref, V, 1).cpu().numpy()[b["rn2o"]]
+    assert_close(back, rback, 1e-6, "row2im vs reference kernels")
+    table = lo.neighbour_table(b["ks"], b["ks"], 0, 1)
+    assert_close(back, lo.row2im(lo.im2row(lv, table), table, V), 1e-6, "row2im vs oracle")
+
+
+def test_table_overflow_is_reported():
+    """The reference spins forever when the table is full (HashTableGPU.cuh:443-484); we must raise."""
+    from lattice_net_b200 import Lattice
+    from lattice_net_b200._cabi import LatticeBackendError
+    lat = Lattice(64, [(0.01, 3)])
+    pos = cuda(cases.box_surface(2048, 3))
+    lat.begin_splat()
+    lat.splat_standalone(pos, torch.zeros((2048, 1), device="cuda"))
+    with pytest.raises(LatticeBackendError, match="full"):
+        lat.nr_lattice_vertices()
+
+
+def test_empty_and_tiny_inputs():
+    from lattice_net_b200 import Lattice
+    lat = Lattice(1000, [(0.05, 3)])
+    lat.begin_splat()
+    idx, w = lat.splat_standalone(torch.zeros((0, 3), device="cuda"), torch.zeros((0, 2), device="cuda"))
+    assert idx.numel() == 0 and lat.nr_lattice_vertices() == 0
+    lat.begin_splat()
+    idx, w = lat.splat_standalone(torch.tensor([[0.01, 0.02, 0.03]], device="cuda"), torch.ones((1, 2), device="cuda"))
+    assert lat.nr_lattice_vertices() == 4 and abs(float(w.sum()) - 1.0) < 1e-6
+    assert abs(float(lat.values()[:4].sum()) - 2.0) < 1e-5
+
+
+def test_golden_vectors_match_cuda_path(golden_dir):
+    """Committed reference outputs (made by oracle/make_golden.py from the reference kernels)."""
+    from lattice_net_b200 import Lattice
+    found = 0
+    for name, spec in cases.CASES.items():
+        path = os.path.join(golden_dir, f"{name}.npz")
+        if not os.path.isfile(path):
+            continue
+        found += 1
+        g = np.load(path)
+        lat = Lattice(int(g["capacity"]), [(float(s), 1) for s in g["sigmas"]])
+        lat.begin_splat()
+        idx, w = lat.splat_standalone(cuda(g["positions"]), cuda(g["splat_in"]))
+        nv = lat.nr_lattice_vertices()
+        assert nv == int(g["nv"])
+        ks, o2n, n2o = canonical(lat.hash_table().m_keys_tensor[:nv].cpu().numpy())
+        assert np.array_equal(ks, g["keys"])
+        assert np.array_equal(lo.relabel(idx.cpu().numpy(), o2n), g["indices"])
+        assert bits_equal(w.cpu().numpy(), g["weights"]) == 0
+        assert_close(lat.values()[:nv].cpu().numpy()[n2o], g["splat_values"], TOL_VALUES, f"{name}: splat values vs golden")
+        lat2 = lat.clone_lattice()
+        lat2.set_values(cuda(g["lv8"][o2n]))
+        F = 2 * (g["positions"].shape[1] + 1) + 1
+        conv = lat2.convolve_im2row_standalone(cuda(g["conv_filter"]), 1, lat2, False).values().cpu().numpy()[n2o]
+        assert_close(conv, g["conv8_16"], TOL_VALUES, f"{name}: conv vs golden")
+        s = lat2.slice_standalone_with_precomputation(cuda(g["positions"]), idx, w)
+        assert bits_equal(s.cpu().numpy(), g["slice8"]) == 0
+    if found == 0:
+        pytest.skip("no golden vectors committed yet")

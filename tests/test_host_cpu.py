@@ -1,0 +1,116 @@
+"""CPU-only tests of the host logic: cfg reader, parameter structs, C-ABI library symbols."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CFG = '''
+core: { loguru_verbosity: 3  hidpi: false }
+train: { dataset_name: "shapenet" // comment
+    lr: 0.001
+    weight_decay: 3e-4
+    save_checkpoint: false
+    checkpoint_path: ""
+}
+model: {
+    positions_mode: "xyz"
+    values_mode: "none"
+    pointnet_layers: [16,32,64]
+    pointnet_start_nr_channels: 32
+    nr_downsamples: 3
+    nr_blocks_down_stage: [6,6,8]
+    nr_blocks_bottleneck: 8
+    nr_blocks_up_stage: [2,2,2]
+    nr_levels_down_with_normal_resnet: 3
+    nr_levels_up_with_normal_resnet: 3
+    compression_factor: 1.0
+    dropout_last_layer: 0.0
+}
+lattice_gpu: {
+    hash_table_capacity: 60000 //good for shapenet
+    nr_sigmas: 2
+    // sigma_0: "0.06 3"
+    sigma_0: "0.05 3"
+    sigma_1: "0.1 2"
+}
+'''
+
+
+def test_cfg_parser_and_params():
+    from lattice_net_b200 import params
+    cfg = params.parse_cfg_text(CFG)
+    assert params.lattice_settings(cfg) == (60000, [(0.05, 3), (0.1, 2)])
+    mp = params.ModelParams.create(cfg)
+    assert mp.pointnet_channels_per_layer() == [16, 32, 64]      # old key spelling accepted
+    assert mp.nr_blocks_down_stage() == [6, 6, 8] and mp.nr_blocks_bottleneck() == 8
+    tp = params.TrainParams.create(cfg)
+    assert tp.lr() == 0.001 and tp.weight_decay() == 3e-4 and tp.dataset_name() == "shapenet" and tp.save_checkpoint() is False
+    assert params.EvalParams.create(cfg).do_write_predictions() is False
+    with pytest.raises(ValueError):
+        params.parse_cfg_text("a: { b: 1 ")
+    with pytest.raises(FileNotFoundError):
+        params.parse_cfg("does_not_exist.cfg")
+
+
+def test_default_model_params_are_the_shapenet_architecture():
+    from lattice_net_b200 import ModelParams
+    mp = ModelParams()
+    assert mp.pointnet_start_nr_channels() == 32 and mp.nr_downsamples() == 3
+    assert mp.nr_blocks_down_stage() == [3, 3, 3] and mp.nr_blocks_up_stage() == [2, 2, 2]
+
+
+def test_lattice_handle_host_logic():
+    from lattice_net_b200 import Lattice
+    lat = Lattice(1000, [(0.05, 3)], name="l")
+    assert Lattice.get_expected_filter_extent(1) == 9 and lat.name() == "l" and lat.capacity() == 1000
+    assert lat.m_sigmas == [0.05, 0.05, 0.05]
+    lat.increase_sigmas(0.01)
+    assert abs(lat.m_sigmas[0] - 0.06) < 1e-9
+    lat.set_sigma(0.1)
+    assert lat.m_sigmas == [0.1] * 3
+    with pytest.raises(RuntimeError):
+        lat.nr_lattice_vertices()            # nothing splatted yet
+    with pytest.raises(RuntimeError):
+        Lattice.get_expected_filter_extent(2)
+    lat5 = Lattice(10, [(0.1, 3), (0.2, 2)])
+    assert Lattice.get_expected_filter_extent(1) == 13 and len(lat5.m_sigmas) == 5
+    clone = lat5.clone_lattice()
+    assert clone.m_sigmas == lat5.m_sigmas and clone.lvl() == 1 and clone.hash_table().structure is lat5.hash_table().structure
+    Lattice(1000, [(0.05, 3)])               # restore the static expected pos_dim for other tests
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    """include/lattice_b200.h is the contract: every declared ln_* function must be exported."""
+    from lattice_net_b200 import _cabi, build
+    if not os.path.isfile(_cabi.LIB_PATH):
+        build.build()
+    with open(os.path.join(ROOT, "include", "lattice_b200.h")) as f:
+        header = f.read()
+    declared = sorted(set(re.findall(r"\b(ln_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in the header but not exported"
+    assert sorted(_cabi.EXPORTED_SYMBOLS) == declared, "ctypes signature table and header disagree"
+    _cabi.load()
+    assert _cabi.version().endswith("sm_100a")
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from lattice_net_b200 import _cabi
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_cabi.LatticeBackendError, match="no CPU or PyTorch fallback"):
+        _cabi.load()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "lattice_net_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            with open(os.path.join(pkg, fn)) as f:
+                src = f.read()
+            assert "oracle" not in src.replace("# oracle", ""), f"{fn} mentions the oracle"
