@@ -127,11 +127,15 @@ int ln_row2im(const float* rowified, const int* neighbours, int nv, int filter_e
  *   out[q, co] = sum_slot sum_ci nbr_values[neighbours[q, slot'], ci] * filter[slot*c_in + ci, co] (+ bias[co])
  * slot' = slot^1 for slot < F-1 when flip != 0 (the data-gradient convolution of
  * /root/reference/latticenet_py/lattice/lattice_funcs.py:307-313), else slot.
- * precision: 0 = exact fp32 FMA (SIMT), 1 = tcgen05 3xTF32 (fp32-equivalent), 2 = tcgen05 1xTF32.
- * bias may be NULL. */
+ * precision: 0 = exact fp32 FMA on the CUDA cores; 1 = tcgen05 tensor cores, 3xTF32 split (fp32-equivalent,
+ * ~1e-6 relative); 2 = tcgen05 single-pass TF32 (~1e-3 relative).  The tensor-core path needs
+ * c_in % 32 == 0 and c_out <= 256; other shapes run the fp32 kernel whatever `precision` says.
+ * workspace: device scratch of ln_conv_workspace_bytes() bytes for precision 1/2 (re-laid-out filter),
+ * may be NULL for precision 0.  bias may be NULL. */
 int ln_conv_fwd(const float* nbr_values, const int* neighbours, const float* filter, const float* bias,
                 int nv_query, int filter_extent, int c_in, int c_out, int flip, int precision,
-                float* out, void* stream);
+                float* workspace, float* out, void* stream);
+long long ln_conv_workspace_bytes(int filter_extent, int c_in, int c_out, int precision);
 
 /* Weight gradient, replaces `lattice_rowified.transpose(0,1).mm(grad)` (lattice_funcs.py:302,378,443):
  *   grad_filter[slot*c_in + ci, co] = sum_q nbr_values[neighbours[q, slot], ci] * grad_out[q, co]

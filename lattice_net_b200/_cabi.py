@@ -27,7 +27,7 @@ _SIGNATURES = {
     "ln_im2row": [_P, _P, _I, _I, _I, _I, _P, _P],
     "ln_im2rowindices": [_P, _I, _I, _I, _I, _P, _P],
     "ln_row2im": [_P, _P, _I, _I, _I, _P, _P],
-    "ln_conv_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "ln_conv_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "ln_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "ln_filter_for_dgrad": [_P, _I, _I, _I, _P, _P],
     "ln_slice_fwd": [_P, _P, _P, _I, _I, _I, _P, _P],
@@ -43,6 +43,7 @@ _SPECIAL = {
     "ln_version": (ctypes.c_char_p, []),
     "ln_last_error": (ctypes.c_char_p, []),
     "ln_launch_count": (ctypes.c_longlong, []),
+    "ln_conv_workspace_bytes": (ctypes.c_longlong, [_I, _I, _I, _I]),
     "ln_reset_launch_count": (None, []),
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + list(_SPECIAL))

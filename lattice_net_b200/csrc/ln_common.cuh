@@ -124,15 +124,21 @@ __device__ __forceinline__ int table_find(const ConstTableView& t, const int* ke
 }
 
 // ---------------------------------------------------------------------------------------------
-// Permutohedral geometry.  The reference compiles with --use_fast_math (jitify_helper.cuh:29);
-// NVRTC 12.9 lowers kernel_splat/distribute/slice_no_precomputation (LatticeGPU.cuh:718-806) to
-// the exact operation sequence reproduced here (see DESIGN.md "bit-exact keys"):
-//   scale_i = rsqrt.approx.ftz((i+1)(i+2)) * fl((D+1)*sqrt(2/3))
-//   cf = p*scale;  e_i = fma(cf, -i, sm) for i >= 3;  e_2 = sm - fma(p, scale, cf);  e_1 = sm - cf
-__device__ __forceinline__ float rsqrt_approx(float x) {
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
+// Permutohedral geometry.  The reference compiles its kernels with NVRTC --use_fast_math
+// (jitify_helper.cuh:29) and the PTX is then lowered by ptxas / the driver JIT.  What actually runs
+// (SASS of kernel_splat / distribute / slice_no_precomputation, identical in all of them; see
+// DESIGN.md "bit-exact keys") for LatticeGPU.cuh:718-741 is
+//     scale_i  : a CONSTANT -- ptxas folds rsqrt.approx.ftz((i+1)(i+2)) with the correctly rounded
+//                1/sqrt and multiplies by fl((D+1)*sqrtf(2/3)); it is not the hardware MUFU.RSQ result
+//     cf = fl(p*scale);  e_i = fma(cf, -i, sm)            for i >= 3
+//                        e_2 = sm - fma(p, scale, cf)
+//     e_1 = fma(p_0, -scale_0, sm), e_0 = fma(p_0, scale_0, sm)   (mul+add contracted by ptxas)
+// and everything after it is plain fp32 (fp64 for the two (D+1)-divisions when D != 3).
+template <int D>
+__device__ __forceinline__ float elevate_scale(int i) {   // scale applied to position coordinate i
+    static_assert(D == 3 || D == 5, "pos_dim must be 3 or 5");
+    if (D == 3) return __int_as_float(i == 0 ? 0x4013cd3a : i == 1 ? 0x3faaaaab : 0x3f715bef);
+    return __int_as_float(i == 0 ? 0x405db3d8 : i == 1 ? 0x40000001 : i == 2 ? 0x3fb504f3 : i == 3 ? 0x3f8c378c : 0x3f64f92e);
 }
 
 template <int D>
@@ -142,13 +148,6 @@ struct Simplex {
     float bary[D + 2];
 };
 
-template <int D>
-__device__ __forceinline__ float inv_std_dev() {
-    static_assert(D == 3 || D == 5, "pos_dim must be 3 or 5");
-    // fl((D+1) * sqrtf(2.0f/3)) as constant-folded by NVRTC: 0f405105EC (D=3), 0f409CC471 (D=5)
-    return __int_as_float(D == 3 ? 0x405105EC : 0x409CC471);
-}
-
 // p: position already divided by sigma
 template <int D>
 __device__ __forceinline__ void compute_simplex(const float* p, Simplex<D>& s) {
@@ -156,17 +155,16 @@ __device__ __forceinline__ void compute_simplex(const float* p, Simplex<D>& s) {
     float sm = 0.0f;
 #pragma unroll
     for (int i = D; i > 0; i--) {
-        const float scale = __fmul_rn(rsqrt_approx((float)((i + 1) * i)), inv_std_dev<D>());
-        const float cf = __fmul_rn(p[i - 1], scale);
-        if (i >= 3)
-            e[i] = __fmaf_rn(cf, -(float)i, sm);
-        else if (i == 2)
-            e[i] = __fsub_rn(sm, __fmaf_rn(p[i - 1], scale, cf));
-        else
-            e[i] = __fsub_rn(sm, cf);
-        sm = __fadd_rn(sm, cf);
+        const float scale = elevate_scale<D>(i - 1);
+        if (i == 1) {
+            e[1] = __fmaf_rn(p[0], -scale, sm);
+            e[0] = __fmaf_rn(p[0], scale, sm);
+        } else {
+            const float cf = __fmul_rn(p[i - 1], scale);
+            e[i] = (i >= 3) ? __fmaf_rn(cf, -(float)i, sm) : __fsub_rn(sm, __fmaf_rn(p[i - 1], scale, cf));
+            sm = __fadd_rn(sm, cf);
+        }
     }
-    e[0] = sm;
 
     // nearest remainder-0 point (LatticeGPU.cuh:746-758)
     int sum = 0;

@@ -9,8 +9,11 @@
 
 namespace ln {
 
+// ln_conv_tc.cu
 int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
-                int F, int c_in, int c_out, int flip, int precision, float* out, cudaStream_t s);   // ln_conv_tc.cu
+                int F, int c_in, int c_out, int flip, int precision, float* workspace, float* out, cudaStream_t s);
+size_t conv_tc_workspace_bytes(int F, int c_in, int c_out);
+bool conv_tc_supported(int F, int c_in, int c_out);
 
 constexpr int kThreads = 256;
 constexpr int BM = 64, BN = 64, BK = 16;
@@ -178,14 +181,22 @@ using namespace ln;
 
 extern "C" {
 
+long long ln_conv_workspace_bytes(int filter_extent, int c_in, int c_out, int precision) {
+    if (precision == 0 || !conv_tc_supported(filter_extent, c_in, c_out)) return 0;
+    return (long long)conv_tc_workspace_bytes(filter_extent, c_in, c_out);
+}
+
 int ln_conv_fwd(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
-                int filter_extent, int c_in, int c_out, int flip, int precision, float* out, void* stream) {
+                int filter_extent, int c_in, int c_out, int flip, int precision, float* workspace, float* out, void* stream) {
     LN_REQUIRE(nbr_values && neighbours && filter && out, "ln_conv_fwd: null pointer");
     LN_REQUIRE(nv_query >= 0 && filter_extent >= 3 && (filter_extent & 1) && c_in >= 1 && c_out >= 1, "ln_conv_fwd: bad size");
     LN_REQUIRE(precision >= 0 && precision <= 2, "ln_conv_fwd: precision must be 0 (fp32), 1 (3xTF32) or 2 (TF32)");
     if (nv_query == 0) return LN_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    if (precision != 0) return conv_fwd_tc(nbr_values, neighbours, filter, bias, nv_query, filter_extent, c_in, c_out, flip, precision, out, s);
+    if (precision != 0 && conv_tc_supported(filter_extent, c_in, c_out)) {
+        LN_REQUIRE(workspace != nullptr, "ln_conv_fwd: precision %d needs a workspace of ln_conv_workspace_bytes() bytes", precision);
+        return conv_fwd_tc(nbr_values, neighbours, filter, bias, nv_query, filter_extent, c_in, c_out, flip, precision, workspace, out, s);
+    }
     dim3 grid(cdiv(nv_query, BM), cdiv(c_out, BN));
     conv_fwd_simt_kernel<<<grid, kThreads, 0, s>>>(nbr_values, neighbours, filter, bias, nv_query, filter_extent, c_in, c_out, flip, out);
     count_launch();

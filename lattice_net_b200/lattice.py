@@ -469,8 +469,10 @@ class Lattice:
         _check(vals.shape[0] >= nbrs.nr_lattice_vertices(), "neighbour lattice values have fewer rows than vertices")
         fb = _as_cuda_f32(filter_bank, st.device)
         out = torch.empty((nv, nr_filters), dtype=torch.float32, device=st.device)
+        ws_bytes = int(_cabi.load().ln_conv_workspace_bytes(F, vn, nr_filters, CONV_PRECISION))
+        workspace = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=st.device) if ws_bytes else None
         call("ln_conv_fwd", ptr(vals.contiguous()), ptr(table), ptr(fb), ptr(bias), nv, F, vn, nr_filters,
-             1 if flip_neighbours else 0, CONV_PRECISION, ptr(out), stream_ptr(st.device))
+             1 if flip_neighbours else 0, CONV_PRECISION, ptr(workspace), ptr(out), stream_ptr(st.device))
         new = self.clone_lattice()
         new.m_name = "convolved_lattice"
         new.m_hash_table.set_values(out)

@@ -12,7 +12,6 @@ import sys
 import torch
 from torch.autograd import Function
 
-from .lattice import Lattice
 from .lattice_wrapper import LatticeWrapper
 
 
@@ -24,7 +23,7 @@ def _conv_backward(query, neighbours, neighbour_values, filter_bank, grad_out, d
     grad_out = grad_out.contiguous()
     neighbours.set_values(neighbour_values)
     grad_filter = query.conv_weight_grad(neighbours, grad_out, filter_extent, dilation)
-    filter_bw = Lattice.filter_for_data_grad(filter_bank, filter_extent, val_dim)
+    filter_bw = query.filter_for_data_grad(filter_bank, filter_extent, val_dim)
     query.set_values(grad_out)
     grad_lattice = neighbours.convolve_im2row_standalone(filter_bw, dilation, query, True)
     return grad_lattice.values(), grad_filter

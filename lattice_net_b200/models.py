@@ -84,6 +84,7 @@ class LNN(torch.nn.Module):
     def forward(self, ls, positions, values):
         with torch.no_grad():
             ls, distributed, indices, weights = self.distribute(ls, positions, values)
+        self.last_level1_lattice = ls          # kept for inspection / tests (vertex numbering of this pass)
         lv, ls = self.point_net(ls, distributed, indices)
 
         fine_structures, fine_values = [], []

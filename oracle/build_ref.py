@@ -31,6 +31,7 @@ POS_DIMS = (3, 5)
 # (kernel, template-arg tuples).  V / nc lists cover the test + bench configurations.
 VALS_SMALL = (1, 3, 4, 8)
 VALS_ALL = (1, 3, 4, 8, 16, 32, 64, 128)
+VALS_CONV = (1, 3, 4, 8, 16, 32, 64, 96, 128, 192, 256)   # channel widths met by the LatticeNet architectures
 CLASSIFY = ((32, 7), (64, 16), (128, 7), (128, 20), (8, 4))
 
 
@@ -39,10 +40,11 @@ def name_expressions():
     for d in POS_DIMS:
         names.append(f"kernel_splat<{d},1>")
         names.append(f"coarsen<{d}>")
-        for v in VALS_ALL:
-            names.append(f"splatCacheNaive<{d},{v}>")
+        for v in (VALS_CONV if d == 3 else VALS_ALL):
             names.append(f"im2row<{d},{v}>")
             names.append(f"row2im<{d},{v}>")
+        for v in VALS_ALL:
+            names.append(f"splatCacheNaive<{d},{v}>")
             names.append(f"slice_with_precomputation<{d},{v}>")
             names.append(f"slice_no_precomputation<{d},{v}>")
             names.append(f"slice_backwards_with_precomputation_no_homogeneous<{d},{v}>")

