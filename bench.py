@@ -192,6 +192,8 @@ def run_ours(args):
     torch.cuda.set_device(device)
     torch.manual_seed(0)
 
+    from lattice_net_b200 import set_conv_precision
+    set_conv_precision(args.conv_precision)
     lattice, model = build_training(device)
     clouds = [synthetic_cloud(1000 * rank + i) for i in range(POOL)]
     dev_clouds = [(torch.from_numpy(p).to(device), torch.zeros((NR_POINTS, 1), device=device), torch.from_numpy(l).to(device)) for p, l in clouds]
@@ -201,7 +203,7 @@ def run_ours(args):
     with torch.no_grad():
         model(lattice, *dev_clouds[0][:2])
     broadcast_parameters(model, 0)
-    optimizer = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=3e-4, amsgrad=True)
+    optimizer = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=3e-4, amsgrad=True, fused=True)
     bucket = GradBucket(model.parameters())
     flush_buf = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=device)
 
@@ -246,7 +248,7 @@ def run_ours(args):
                    "nr_points": NR_POINTS, "nr_classes": NR_CLASSES, "sigma": SIGMA, "hash_table_capacity": CAPACITY,
                    "parallelism": f"scene-parallel dp{world}, one flat NCCL all-reduce of {bucket.nbytes} grad bytes/step",
                    "l2": f"flushed between steps by a {L2_FLUSH_BYTES >> 20} MiB write (inside the timed region)",
-                   "conv_precision": "fp32 FMA (exact)"},
+                   "conv_precision": {0: "fp32 FMA on CUDA cores", 1: "tcgen05 3xTF32 split, fp32 accumulate (fp32-equivalent)", 2: "tcgen05 TF32"}[args.conv_precision]},
         "e2e": {"value": scans / (ms_e2e * 1e-3), "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
@@ -281,6 +283,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--conv-precision", type=int, default=1, choices=[0, 1, 2],
+                    help="0 fp32 CUDA cores, 1 tcgen05 3xTF32 (fp32-equivalent, default), 2 tcgen05 TF32")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -1,0 +1,205 @@
+#!/usr/bin/env python
+"""Operator micro-benchmarks (BASELINE.json configs[4]: the splat / slice / conv sweep).
+
+For every op: CUDA-event time of our kernel, achieved algorithmic HBM GB/s (bytes of SURVEY.md
+section 8d) or TFLOP/s, the fraction of the measured peak (MEASURED_PEAKS.json), and -- where the
+reference's own kernel is available (oracle/_ref) -- the reference kernel's time on the same inputs.
+Inputs are sized well above the 126 MB L2 or the L2 is flushed between iterations.
+
+    python bench_ops.py [--n 1000000] [--quick] > ops.jsonl
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p["bf16_tflops"]), "measured"
+    except Exception:
+        return 6650.0, 1590.0, "fallback"
+
+
+HBM, TF, PEAK_SRC = peaks()
+_flush = None
+
+
+def timeit(fn, reps=10, warm=3, flush=True):
+    global _flush
+    if _flush is None:
+        _flush = torch.empty((256 << 20) // 4, dtype=torch.float32, device="cuda")
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for i in range(reps):
+        if flush:
+            _flush.fill_(float(i))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    return float(np.median(ts))
+
+
+def emit(op, cfg, sec, nbytes=None, flops=None, ref_sec=None, extra=None):
+    rec = {"op": op, **cfg, "us": sec * 1e6}
+    if nbytes is not None:
+        rec.update(algo_GB=nbytes / 1e9, GBps=nbytes / sec / 1e9, hbm_frac=nbytes / sec / 1e9 / HBM)
+    if flops is not None:
+        rec.update(TFLOPs=flops / sec / 1e12, tensor_frac=flops / sec / 1e12 / TF)
+    if ref_sec is not None:
+        rec.update(ref_us=ref_sec * 1e6, speedup_vs_ref_kernel=ref_sec / sec)
+    if extra:
+        rec.update(extra)
+    rec["peak_source"] = PEAK_SRC
+    print(json.dumps(rec), flush=True)
+
+
+def uniform_cloud(n, d, seed, target_ratio=0.5):
+    """n points uniform in a cube sized so that nv ~ target_ratio * n * ... (nv ~ N/2)."""
+    rng = np.random.RandomState(seed)
+    pos = rng.rand(n, d).astype(np.float32)
+    return pos
+
+
+def run(n, d, vals, quick):
+    from lattice_net_b200 import Lattice, lattice as lm
+    from lattice_net_b200._cabi import call, ptr, stream_ptr
+    from oracle import ref_cuda
+    have_ref = ref_cuda.available()
+    dev = torch.device("cuda", 0)
+    # sigma so that nv ~ n/2: vertices ~ (d+1)! * volume/sigma^d density; tune by a coarse search
+    pos = torch.from_numpy(uniform_cloud(n, d, 0)).to(dev)
+    cap = int(4 * n)
+    sigma = (1.0 / n) ** (1.0 / d) * (2.2 if d == 3 else 1.6)
+    for _ in range(6):
+        lat = Lattice(cap, [(sigma, d)])
+        lat.begin_splat()
+        idx, w = lat.just_create_verts(pos, True)
+        nv = lat.nr_lattice_vertices()
+        if nv > 0.65 * n:
+            sigma *= 1.25
+        elif nv < 0.35 * n:
+            sigma *= 0.85
+        else:
+            break
+    cfg0 = {"n": n, "pos_dim": d, "nv": nv, "capacity": cap, "sigma": round(sigma, 5)}
+    st = lat.hash_table().structure
+    sig = lat._sigmas_on(dev)
+
+    def build():
+        st.clear()
+        call("ln_splat_build", ptr(pos), ptr(sig), n, d, ptr(st.keys), ptr(st.entries), ptr(st.nr_filled), ptr(st.status), st.capacity, ptr(idx), ptr(w), stream_ptr(dev))
+
+    ref = None
+    ref_sec = None
+    if have_ref:
+        ref = ref_cuda.RefLattice(cap, [sigma] * d)
+        ref.table = ref_cuda.RefTable(cap, d)
+
+        def ref_build():
+            ref.table.entries.fill_(-1)
+            ref.table.nr_filled.fill_(0)
+            return ref.build(pos)
+        ref_sec = timeit(ref_build, reps=5)
+        ridx, rw = ref_build()
+    sec = timeit(build, reps=5)
+    st.mark_dirty()
+    nv = lat.nr_lattice_vertices()
+    emit("splat_build(+table clear)", cfg0, sec, nbytes=4 * n * d + 8 * n * (d + 1) + 4 * nv * d, ref_sec=ref_sec,
+         extra={"points_per_s": n / sec, "max_probe": st.max_probe})
+
+    for V in vals:
+        cfg = dict(cfg0, val_dim=V)
+        x = torch.randn((n, V), device=dev)
+        lv = torch.zeros((nv, V), device=dev)
+
+        def acc():
+            call("ln_splat_accumulate", ptr(x), ptr(idx), ptr(w), n, d, V, ptr(lv), stream_ptr(dev))
+        rs = None
+        if ref is not None and ref.k.has(f"splatCacheNaive<{d},{V}>"):
+            rvals = torch.zeros((cap, V), device=dev)
+            import ctypes
+            rs = timeit(lambda: ref.k.launch(f"splatCacheNaive<{d},{V}>", n, [ctypes.c_int(n), ref_cuda._p(x), ref_cuda._p(ridx), ref_cuda._p(rw), ref.table.struct(rvals)]), reps=5)
+            del rvals
+        emit("splat_accumulate", cfg, timeit(acc, reps=5), nbytes=4 * n * V + 8 * n * (d + 1) + 4 * nv * V, ref_sec=rs)
+
+        lat2 = lat.clone_lattice()
+        lvr = torch.randn((nv, V), device=dev)
+        lat2.set_values(lvr)
+        out = torch.empty((n, V), device=dev)
+
+        def sl():
+            call("ln_slice_fwd", ptr(lvr), ptr(idx), ptr(w), n, d, V, ptr(out), stream_ptr(dev))
+        rs = None
+        if ref is not None and ref.k.has(f"slice_with_precomputation<{d},{V}>"):
+            rs = timeit(lambda: ref.slice_with_precomputation(pos, lvr, ridx, rw), reps=5)
+        emit("slice_fwd", cfg, timeit(sl, reps=5), nbytes=8 * n * (d + 1) + 4 * nv * V + 4 * n * V, ref_sec=rs,
+             extra={"gather_GB": 4 * n * (d + 1) * V / 1e9})
+        g = torch.randn((n, V), device=dev)
+        gl = torch.zeros((nv, V), device=dev)
+
+        def slb():
+            call("ln_slice_bwd", ptr(g), ptr(idx), ptr(w), n, d, V, ptr(gl), stream_ptr(dev))
+        rs = None
+        if ref is not None and ref.k.has(f"slice_backwards_with_precomputation_no_homogeneous<{d},{V}>"):
+            rs = timeit(lambda: ref.slice_backwards(g, ridx, rw), reps=5)
+        emit("slice_bwd", cfg, timeit(slb, reps=5), nbytes=8 * n * (d + 1) + 4 * nv * V + 4 * n * V, ref_sec=rs)
+        del x, lv, out, g, gl
+
+        if V >= 32 and not (quick and V > 64):
+            F = 2 * (d + 1) + 1
+            fb = torch.randn((F * V, V), device=dev) * 0.05
+            lat2._neighbour_table(lat2, 1)
+            flops = 2.0 * nv * F * V * V
+            cbytes = 4.0 * (nv * V + nv * F + F * V * V + nv * V)
+            for prec, name in ((0, "conv_fwd fp32 SIMT"), (1, "conv_fwd tcgen05 3xTF32"), (2, "conv_fwd tcgen05 TF32")):
+                lm.set_conv_precision(prec)
+                try:
+                    s = timeit(lambda: lat2.convolve_im2row_standalone(fb, 1, lat2, False), reps=5)
+                    emit(name, dict(cfg, c_out=V), s, nbytes=cbytes, flops=flops)
+                finally:
+                    lm.set_conv_precision(0)
+            if ref is not None and ref.k.has(f"im2row<{d},{V}>"):
+                rs = timeit(lambda: ref.convolve(fb, ref, lvr, 1, False), reps=3)
+                emit("conv_fwd reference (im2row kernel + fp32 mm)", dict(cfg, c_out=V), rs, nbytes=cbytes, flops=flops)
+            gout = torch.randn((nv, V), device=dev)
+            emit("conv_wgrad fp32 SIMT", dict(cfg, c_out=V), timeit(lambda: lat2.conv_weight_grad(lat2, gout, F, 1), reps=5), flops=flops)
+            del fb, gout
+        del lat2, lvr
+    # neighbour table
+    lat3 = lat.clone_lattice()
+    lat3.set_values(torch.zeros((nv, 1), device=dev))
+    F = 2 * (d + 1) + 1
+
+    def nt():
+        st.neighbour_cache.clear()
+        lat3._neighbour_table(lat3, 1)
+    emit("neighbour_table", cfg0, timeit(nt, reps=5), nbytes=4 * nv * d + 4 * nv * F + 4 * nv * (d + 1))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, nargs="*", default=[100000, 1000000])
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    for n in args.n:
+        run(n, 3, [8, 32, 64] if args.quick else [1, 8, 32, 64, 128], args.quick)
+    if not args.quick:
+        run(args.n[-1] // 2, 5, [8, 32], True)
+
+
+if __name__ == "__main__":
+    main()

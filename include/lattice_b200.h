@@ -127,13 +127,16 @@ int ln_row2im(const float* rowified, const int* neighbours, int nv, int filter_e
  *   out[q, co] = sum_slot sum_ci nbr_values[neighbours[q, slot'], ci] * filter[slot*c_in + ci, co] (+ bias[co])
  * slot' = slot^1 for slot < F-1 when flip != 0 (the data-gradient convolution of
  * /root/reference/latticenet_py/lattice/lattice_funcs.py:307-313), else slot.
+ * transposed_filter != 0: `filter` is the FORWARD bank [F*c_out x c_in] of the convolution whose data
+ * gradient is being computed, read as filter_bw[(slot*c_in + ci), co] = filter[(slot*c_out + co), ci]
+ * -- the transpose/view/contiguous re-layout of lattice_funcs.py:304-311 without materialising it.
  * precision: 0 = exact fp32 FMA on the CUDA cores; 1 = tcgen05 tensor cores, 3xTF32 split (fp32-equivalent,
  * ~1e-6 relative); 2 = tcgen05 single-pass TF32 (~1e-3 relative).  The tensor-core path needs
  * c_in % 32 == 0 and c_out <= 256; other shapes run the fp32 kernel whatever `precision` says.
  * workspace: device scratch of ln_conv_workspace_bytes() bytes for precision 1/2 (re-laid-out filter),
  * may be NULL for precision 0.  bias may be NULL. */
 int ln_conv_fwd(const float* nbr_values, const int* neighbours, const float* filter, const float* bias,
-                int nv_query, int filter_extent, int c_in, int c_out, int flip, int precision,
+                int nv_query, int filter_extent, int c_in, int c_out, int flip, int transposed_filter, int precision,
                 float* workspace, float* out, void* stream);
 long long ln_conv_workspace_bytes(int filter_extent, int c_in, int c_out, int precision);
 
@@ -143,6 +146,17 @@ long long ln_conv_workspace_bytes(int filter_extent, int c_in, int c_out, int pr
 int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* grad_out,
                   int nv_query, int filter_extent, int c_in, int c_out,
                   float* grad_filter, void* stream);
+
+/* Whole backward pass of one lattice convolution out = conv(query <- neighbours) in one call
+ * (/root/reference/latticenet_py/lattice/lattice_funcs.py:294-313, 373-388, 438-454):
+ *   grad_nbr_values [nv_nbr x c_in] = flipped convolution of grad_out [nv_query x c_out] at the neighbour
+ *                                     lattice's vertices (neighbours_bwd [nv_nbr x F] = table neighbour -> query),
+ *                                     forward filter bank read transposed;            NULL = not wanted
+ *   grad_filter [F*c_in x c_out]    = im2row(nbr_values)^T . grad_out                 NULL = not wanted
+ * precision / workspace as in ln_conv_fwd (workspace size: ln_conv_workspace_bytes(F, c_out, c_in, precision)). */
+int ln_conv_bwd(const float* nbr_values, const int* neighbours_fwd, const float* grad_out, const int* neighbours_bwd,
+                const float* filter, int nv_query, int nv_nbr, int filter_extent, int c_in, int c_out, int precision,
+                float* workspace, float* grad_nbr_values, float* grad_filter, void* stream);
 
 /* filter_bw[(slot*c_out + co), ci] = filter[(slot*c_in + ci), co]: the re-layout done with
  * transpose/view/contiguous in lattice_funcs.py:304-311. */
@@ -187,6 +201,17 @@ int ln_scatter_max(const float* src, const int* index, int m, int c, int nv,
 /* out_sum[v,c] = sum, out_count[v] = number of rows (float) */
 int ln_scatter_sum_count(const float* src, const int* index, int m, int c, int nv,
                          float* out_sum, float* out_count, void* stream);
+
+/* ---- normalisation between lattice convolutions -----------------------
+ * GroupNorm (+ optional fused ReLU) on vertex-major lattice values x [nv x c]: statistics per group over
+ * (c/groups channels) x (all nv vertices), biased variance -- torch.nn.GroupNorm(groups, c) applied to the
+ * [1, c, nv] view the reference builds with unsqueeze/transpose
+ * (/root/reference/latticenet_py/lattice/lattice_modules.py:585-614).  stats [groups x 2] = (mean, rstd). */
+int ln_group_norm_fwd(const float* x, const float* gamma, const float* beta, int nv, int c, int groups, float eps,
+                      int relu, float* y, float* stats, void* stream);
+/* y = forward output (needed for the ReLU mask when relu != 0).  dgamma/dbeta [c] are overwritten. */
+int ln_group_norm_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* stats,
+                      int nv, int c, int groups, int relu, float* dx, float* dgamma, float* dbeta, void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,8 +27,9 @@ _SIGNATURES = {
     "ln_im2row": [_P, _P, _I, _I, _I, _I, _P, _P],
     "ln_im2rowindices": [_P, _I, _I, _I, _I, _P, _P],
     "ln_row2im": [_P, _P, _I, _I, _I, _P, _P],
-    "ln_conv_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "ln_conv_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "ln_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "ln_conv_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "ln_filter_for_dgrad": [_P, _I, _I, _I, _P, _P],
     "ln_slice_fwd": [_P, _P, _P, _I, _I, _I, _P, _P],
     "ln_slice_bwd": [_P, _P, _P, _I, _I, _I, _P, _P],
@@ -38,6 +39,8 @@ _SIGNATURES = {
     "ln_slice_classify_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "ln_scatter_max": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "ln_scatter_sum_count": [_P, _P, _I, _I, _I, _P, _P, _P],
+    "ln_group_norm_fwd": [_P, _P, _P, _I, _I, _I, ctypes.c_float, _I, _P, _P, _P],
+    "ln_group_norm_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P],
 }
 _SPECIAL = {
     "ln_version": (ctypes.c_char_p, []),
@@ -81,20 +84,38 @@ def ptr(t):
     """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
     if t is None:
         return None
-    assert t.is_cuda and t.is_contiguous(), "lattice kernels need contiguous CUDA tensors"
+    if not (t.is_cuda and t.is_contiguous()):
+        raise LatticeBackendError("lattice kernels need contiguous CUDA tensors")
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on `device` (hot path: avoids building a Stream object)."""
+    if _raw_stream is not None:
+        if device is None:
+            idx = torch.cuda.current_device()
+        else:
+            idx = device.index if isinstance(device, torch.device) else int(device)
+            if idx is None:
+                idx = torch.cuda.current_device()
+        return _raw_stream(idx)
     return torch.cuda.current_stream(device).cuda_stream
+
+
+_fn_cache = {}
 
 
 def call(name, *args):
     """Call an int-returning entry point; raise with the library's message on failure."""
-    lib = load()
-    rc = getattr(lib, name)(*args)
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(load(), name)
+    rc = fn(*args)
     if rc != LN_OK:
-        msg = lib.ln_last_error().decode(errors="replace")
+        msg = load().ln_last_error().decode(errors="replace")
         raise LatticeBackendError(f"{name} failed (code {rc}): {msg}")
     return rc
 

@@ -11,7 +11,8 @@ namespace ln {
 
 // ln_conv_tc.cu
 int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
-                int F, int c_in, int c_out, int flip, int precision, float* workspace, float* out, cudaStream_t s);
+                int F, int c_in, int c_out, int flip, int precision, int transposed, float* workspace, float* out,
+                float* also_zero, long long also_zero_n, cudaStream_t s);
 size_t conv_tc_workspace_bytes(int F, int c_in, int c_out);
 bool conv_tc_supported(int F, int c_in, int c_out);
 
@@ -22,7 +23,7 @@ constexpr int BM = 64, BN = 64, BK = 16;
 __global__ void __launch_bounds__(kThreads)
 conv_fwd_simt_kernel(const float* __restrict__ values, const int* __restrict__ neighbours,
                      const float* __restrict__ filter, const float* __restrict__ bias, int nv_query, int F, int c_in,
-                     int c_out, int flip, float* __restrict__ out) {
+                     int c_out, int flip, int transposed, float* __restrict__ out) {
     __shared__ float a_sh[BK][BM + 4];
     __shared__ float b_sh[BK][BN + 4];
     __shared__ int nbr_sh[BM];
@@ -65,7 +66,11 @@ conv_fwd_simt_kernel(const float* __restrict__ values, const int* __restrict__ n
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const int n = n0 + b_col + k;
-                    b_sh[b_row][b_col + k] = (c < c_in && n < c_out) ? __ldg(filter + ((size_t)slot * c_in + c) * c_out + n) : 0.0f;
+                    float wv = 0.0f;
+                    if (c < c_in && n < c_out)
+                        wv = transposed ? __ldg(filter + ((size_t)slot * c_out + n) * c_in + c)      // forward bank read as its own transpose
+                                        : __ldg(filter + ((size_t)slot * c_in + c) * c_out + n);
+                    b_sh[b_row][b_col + k] = wv;
                 }
             }
             __syncthreads();
@@ -187,7 +192,8 @@ long long ln_conv_workspace_bytes(int filter_extent, int c_in, int c_out, int pr
 }
 
 int ln_conv_fwd(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
-                int filter_extent, int c_in, int c_out, int flip, int precision, float* workspace, float* out, void* stream) {
+                int filter_extent, int c_in, int c_out, int flip, int transposed_filter, int precision, float* workspace,
+                float* out, void* stream) {
     LN_REQUIRE(nbr_values && neighbours && filter && out, "ln_conv_fwd: null pointer");
     LN_REQUIRE(nv_query >= 0 && filter_extent >= 3 && (filter_extent & 1) && c_in >= 1 && c_out >= 1, "ln_conv_fwd: bad size");
     LN_REQUIRE(precision >= 0 && precision <= 2, "ln_conv_fwd: precision must be 0 (fp32), 1 (3xTF32) or 2 (TF32)");
@@ -195,21 +201,18 @@ int ln_conv_fwd(const float* nbr_values, const int* neighbours, const float* fil
     cudaStream_t s = (cudaStream_t)stream;
     if (precision != 0 && conv_tc_supported(filter_extent, c_in, c_out)) {
         LN_REQUIRE(workspace != nullptr, "ln_conv_fwd: precision %d needs a workspace of ln_conv_workspace_bytes() bytes", precision);
-        return conv_fwd_tc(nbr_values, neighbours, filter, bias, nv_query, filter_extent, c_in, c_out, flip, precision, workspace, out, s);
+        return conv_fwd_tc(nbr_values, neighbours, filter, bias, nv_query, filter_extent, c_in, c_out, flip, precision, transposed_filter, workspace, out, nullptr, 0, s);
     }
     dim3 grid(cdiv(nv_query, BM), cdiv(c_out, BN));
-    conv_fwd_simt_kernel<<<grid, kThreads, 0, s>>>(nbr_values, neighbours, filter, bias, nv_query, filter_extent, c_in, c_out, flip, out);
+    conv_fwd_simt_kernel<<<grid, kThreads, 0, s>>>(nbr_values, neighbours, filter, bias, nv_query, filter_extent, c_in, c_out, flip, transposed_filter, out);
     count_launch();
     return check_launch("conv_fwd_simt");
 }
 
-int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query,
-                  int filter_extent, int c_in, int c_out, float* grad_filter, void* stream) {
-    LN_REQUIRE(nbr_values && neighbours && grad_out && grad_filter, "ln_conv_wgrad: null pointer");
-    LN_REQUIRE(nv_query >= 0 && filter_extent >= 3 && c_in >= 1 && c_out >= 1, "ln_conv_wgrad: bad size");
-    cudaStream_t s = (cudaStream_t)stream;
+static int conv_wgrad_launch(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query,
+                             int filter_extent, int c_in, int c_out, float* grad_filter, bool already_zero, cudaStream_t s) {
     const size_t bytes = (size_t)filter_extent * c_in * c_out * sizeof(float);
-    if (cudaMemsetAsync(grad_filter, 0, bytes, s) != cudaSuccess) return check_launch("conv_wgrad memset");
+    if (!already_zero && cudaMemsetAsync(grad_filter, 0, bytes, s) != cudaSuccess) return check_launch("conv_wgrad memset");
     if (nv_query == 0) return LN_OK;
     const int ci_tiles = cdiv(c_in, BM), co_tiles = cdiv(c_out, BN);
     // enough q-chunks to fill the machine (~4 waves of 148 SMs), at least 256 rows each
@@ -221,6 +224,44 @@ int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* g
     conv_wgrad_simt_kernel<<<grid, kThreads, 0, s>>>(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, q_chunk, co_tiles, grad_filter);
     count_launch();
     return check_launch("conv_wgrad_simt");
+}
+
+int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query,
+                  int filter_extent, int c_in, int c_out, float* grad_filter, void* stream) {
+    LN_REQUIRE(nbr_values && neighbours && grad_out && grad_filter, "ln_conv_wgrad: null pointer");
+    LN_REQUIRE(nv_query >= 0 && filter_extent >= 3 && c_in >= 1 && c_out >= 1, "ln_conv_wgrad: bad size");
+    return conv_wgrad_launch(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, grad_filter, false, (cudaStream_t)stream);
+}
+
+int ln_conv_bwd(const float* nbr_values, const int* neighbours_fwd, const float* grad_out, const int* neighbours_bwd,
+                const float* filter, int nv_query, int nv_nbr, int filter_extent, int c_in, int c_out, int precision,
+                float* workspace, float* grad_nbr_values, float* grad_filter, void* stream) {
+    LN_REQUIRE(nbr_values && neighbours_fwd && grad_out && filter, "ln_conv_bwd: null pointer");
+    LN_REQUIRE(nv_query >= 0 && nv_nbr >= 0 && filter_extent >= 3 && c_in >= 1 && c_out >= 1, "ln_conv_bwd: bad size");
+    LN_REQUIRE(grad_nbr_values == nullptr || neighbours_bwd != nullptr, "ln_conv_bwd: the data gradient needs the reverse neighbour table");
+    cudaStream_t s = (cudaStream_t)stream;
+    bool filter_zeroed = false;
+    const long long nfilt = (long long)filter_extent * c_in * c_out;
+    if (grad_nbr_values && nv_nbr > 0) {
+        // data gradient = flipped convolution of grad_out, evaluated at the neighbour lattice's vertices, with the
+        // forward bank read transposed (c_in <-> c_out)
+        if (precision != 0 && conv_tc_supported(filter_extent, c_out, c_in)) {
+            LN_REQUIRE(workspace != nullptr, "ln_conv_bwd: precision %d needs a workspace", precision);
+            const int rc = conv_fwd_tc(grad_out, neighbours_bwd, filter, nullptr, nv_nbr, filter_extent, c_out, c_in, 1, precision, 1,
+                                       workspace, grad_nbr_values, grad_filter, grad_filter ? nfilt : 0, s);
+            if (rc != LN_OK) return rc;
+            filter_zeroed = grad_filter != nullptr;
+        } else {
+            dim3 grid(cdiv(nv_nbr, BM), cdiv(c_in, BN));
+            conv_fwd_simt_kernel<<<grid, kThreads, 0, s>>>(grad_out, neighbours_bwd, filter, nullptr, nv_nbr, filter_extent, c_out, c_in, 1, 1, grad_nbr_values);
+            count_launch();
+            const int rc = check_launch("conv_dgrad_simt");
+            if (rc != LN_OK) return rc;
+        }
+    }
+    if (grad_filter)
+        return conv_wgrad_launch(nbr_values, neighbours_fwd, grad_out, nv_query, filter_extent, c_in, c_out, grad_filter, filter_zeroed, s);
+    return LN_OK;
 }
 
 int ln_filter_for_dgrad(const float* filter, int filter_extent, int c_in, int c_out, float* filter_bw, void* stream) {

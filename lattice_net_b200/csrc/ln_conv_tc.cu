@@ -122,9 +122,15 @@ __device__ __forceinline__ float to_tf32(float x) {   // round-to-nearest TF32, 
 // B^T (n-major rows, 32 k-values each) already in the 128B-swizzled order the UMMA descriptor expects:
 // 16-byte chunk j of row n sits at chunk position j ^ (n % 8).  hi = tf32(W), lo = tf32(W - hi).
 __global__ void __launch_bounds__(256)
-filter_prep_kernel(const float* __restrict__ filter, int k_total, int c_out, int n_pad, int split,
-                   float* __restrict__ b_hi, float* __restrict__ b_lo) {
+filter_prep_kernel(const float* __restrict__ filter, int k_total, int c_in, int c_out, int n_pad, int split,
+                   int transposed, float* __restrict__ b_hi, float* __restrict__ b_lo,
+                   float* __restrict__ zero_a, long long n_a, float* __restrict__ zero_b, long long n_b) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // buffers that later kernels accumulate into with atomics (split-K output, weight gradient) are
+    // cleared here instead of by separate memset launches
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = t; i < n_a; i += stride) zero_a[i] = 0.0f;
+    for (long long i = t; i < n_b; i += stride) zero_b[i] = 0.0f;
     const long long total = (long long)(k_total / kBlockK) * n_pad * kBlockK;
     if (t >= total) return;
     const int kk = (int)(t % kBlockK);
@@ -132,7 +138,17 @@ filter_prep_kernel(const float* __restrict__ filter, int k_total, int c_out, int
     const int n = (int)(rest % n_pad);
     const int kb = (int)(rest / n_pad);
     const int k = kb * kBlockK + kk;
-    const float w = (n < c_out) ? __ldg(filter + (size_t)k * c_out + n) : 0.0f;
+    // transposed: `filter` is the forward bank [F*c_out x c_in] of the convolution whose data gradient this is
+    // (element (slot, k, n) lives at [(slot*c_out + n), k]), lattice_funcs.py:304-311 without the copy
+    float w = 0.0f;
+    if (n < c_out) {
+        if (transposed) {
+            const int slot = k / c_in, ci = k - slot * c_in;
+            w = __ldg(filter + ((size_t)slot * c_out + n) * c_in + ci);
+        } else {
+            w = __ldg(filter + (size_t)k * c_out + n);
+        }
+    }
     const int chunk = kk >> 2, within = kk & 3;
     const size_t dst = ((size_t)kb * n_pad + n) * kBlockK + (size_t)((chunk ^ (n & 7)) << 2) + within;
     const float hi = to_tf32(w);
@@ -145,7 +161,7 @@ template <int kSplit>   // 1: 3xTF32, 0: single pass
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_fwd_tc_kernel(const float* __restrict__ values, const int* __restrict__ neighbours,
                    const float* __restrict__ b_hi, const float* __restrict__ b_lo, const float* __restrict__ bias,
-                   int nv_query, int F, int c_in, int c_out, int n_pad, int flip, int stages,
+                   int nv_query, int F, int c_in, int c_out, int n_pad, int flip, int stages, int kb_per_split,
                    float* __restrict__ out) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages] x { A_hi, (A_lo), B_hi, (B_lo) } tiles (all multiples of 1024 B), then indices, barriers
@@ -191,15 +207,21 @@ conv_fwd_tc_kernel(const float* __restrict__ values, const int* __restrict__ nei
     const uint32_t tmem_base = *tmem_slot;
 
     const int cpb = c_in / kBlockK;          // K blocks per slot
-    const int num_kb = F * cpb;
+    // split-K: blockIdx.y owns K blocks [kb_begin, kb_end); partial tiles are reduced with fp32 atomics
+    // into the pre-zeroed output (small lattices: a 1000-vertex level is only 8 M tiles)
+    const int kb_begin = blockIdx.y * kb_per_split;
+    const int kb_end = min(F * cpb, kb_begin + kb_per_split);
+    const int num_kb = kb_end - kb_begin;
+    const bool split_k = gridDim.y > 1;
 
     if (warp < 4) {
         // ================= producers =================
         const int chunk = tid & 7;
         const int row0 = tid >> 3;           // rows row0 + 16*i
-        for (int kb = 0; kb < num_kb; kb++) {
-            const int s = kb % stages;
-            const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+        for (int it = 0; it < num_kb; it++) {
+            const int kb = kb_begin + it;
+            const int s = it % stages;
+            const uint32_t ph = (uint32_t)(it / stages) & 1u;
             mbar_wait(empty_bar(s), ph ^ 1u);
             if (tid == 0) {
                 mbar_arrive_expect_tx(full_bar(s), (kSplit ? 2u : 1u) * b_tile_bytes);
@@ -240,7 +262,11 @@ conv_fwd_tc_kernel(const float* __restrict__ values, const int* __restrict__ nei
         for (int n0 = 0; n0 < n_pad; n0 += 16) {
             float acc[16];
             tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, acc);
-            if (q < nv_query) {
+            if (q < nv_query && split_k) {
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if (n0 + j < c_out) atomicAdd(orow + n0 + j, acc[j] + ((bias && blockIdx.y == 0) ? __ldg(bias + n0 + j) : 0.0f));
+            } else if (q < nv_query) {
                 if (n0 + 16 <= c_out && (c_out & 3) == 0) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
@@ -263,7 +289,7 @@ conv_fwd_tc_kernel(const float* __restrict__ values, const int* __restrict__ nei
         // ================= MMA issuer (warp 4, one lane) =================
         if ((tid & 31) == 0) {
             const uint32_t idesc = umma_idesc_tf32(kTileM, n_pad);
-            for (int kb = 0; kb < num_kb; kb++) {
+            for (int kb = 0; kb < num_kb; kb++) {   // kb counts this CTA's K blocks from 0
                 const int s = kb % stages;
                 const uint32_t ph = (uint32_t)(kb / stages) & 1u;
                 mbar_wait(full_bar(s), ph);
@@ -304,15 +330,24 @@ size_t conv_tc_workspace_bytes(int F, int c_in, int c_out) {
 bool conv_tc_supported(int F, int c_in, int c_out) { return c_in % kBlockK == 0 && c_out >= 1 && c_out <= 256 && F >= 3; }
 
 int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
-                int F, int c_in, int c_out, int flip, int precision, float* workspace, float* out, cudaStream_t s) {
+                int F, int c_in, int c_out, int flip, int precision, int transposed, float* workspace, float* out,
+                float* also_zero, long long also_zero_n, cudaStream_t s) {
     const int n_pad = (c_out + 15) / 16 * 16;
     const int k_total = F * c_in;
     const int split = precision == 1 ? 1 : 0;
     float* b_hi = workspace;
     float* b_lo = workspace + (size_t)k_total * n_pad;
+    const int num_kb = F * (c_in / kBlockK);
+    // enough CTAs for the machine: split K when there are few M tiles (148 SMs, one CTA each)
+    const int m_tiles = cdiv(nv_query, kTileM);
+    int splits = 1;
+    if (m_tiles < 148) splits = max(1, min(num_kb, 148 / m_tiles));
+    const int kb_per_split = cdiv(num_kb, splits);
+    splits = cdiv(num_kb, kb_per_split);
     {
         const long long total = (long long)k_total * n_pad;
-        filter_prep_kernel<<<cdiv(total, 256), 256, 0, s>>>(filter, k_total, c_out, n_pad, split, b_hi, b_lo);
+        filter_prep_kernel<<<cdiv(total, 256), 256, 0, s>>>(filter, k_total, c_in, c_out, n_pad, split, transposed, b_hi, b_lo,
+                                                            out, splits > 1 ? (long long)nv_query * c_out : 0, also_zero, also_zero_n);
         count_launch();
     }
     const size_t b_tile = (size_t)n_pad * kRowBytes;
@@ -320,23 +355,22 @@ int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* fil
     const size_t fixed = (size_t)kTileM * F * sizeof(int) + 16 + (2 * 8 + 1) * 8 + 16 + 1024;
     int stages = (int)((227 * 1024 - fixed) / stage_bytes);
     stages = min(stages, 8);
-    const int num_kb = F * (c_in / kBlockK);
-    stages = min(stages, num_kb);
-    if (stages < 2 && num_kb >= 2) {
+    stages = min(stages, kb_per_split);
+    if (stages < 2 && kb_per_split >= 2) {
         set_error("ln_conv_fwd: tensor-core tile does not fit shared memory (c_out=%d)", c_out);
         return LN_ERR_UNSUPPORTED;
     }
     const size_t smem = (size_t)stages * stage_bytes + fixed;
-    const int grid = cdiv(nv_query, kTileM);
+    const dim3 grid(m_tiles, splits);
     cudaError_t err;
     if (split) {
         err = cudaFuncSetAttribute(conv_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err == cudaSuccess)
-            conv_fwd_tc_kernel<1><<<grid, kTcThreads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias, nv_query, F, c_in, c_out, n_pad, flip, stages, out);
+            conv_fwd_tc_kernel<1><<<grid, kTcThreads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias, nv_query, F, c_in, c_out, n_pad, flip, stages, kb_per_split, out);
     } else {
         err = cudaFuncSetAttribute(conv_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err == cudaSuccess)
-            conv_fwd_tc_kernel<0><<<grid, kTcThreads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias, nv_query, F, c_in, c_out, n_pad, flip, stages, out);
+            conv_fwd_tc_kernel<0><<<grid, kTcThreads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias, nv_query, F, c_in, c_out, n_pad, flip, stages, kb_per_split, out);
     }
     if (err != cudaSuccess) {
         set_error("conv_fwd_tc: %s", cudaGetErrorString(err));

@@ -36,6 +36,22 @@ def set_conv_precision(mode):
     CONV_PRECISION = mode
 
 
+_workspaces = {}
+
+
+def _workspace(nbytes, device):
+    """Grow-only scratch per device for the re-laid-out filter of the tensor-core convolution.  Kernels on
+    one stream run in order, so consecutive convolutions can share it."""
+    if nbytes <= 0:
+        return None
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr(device))
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() * 4 < nbytes:
+        ws = torch.empty((max(nbytes // 4, 1 << 20),), dtype=torch.float32, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
 def _check(cond, msg):
     # the reference aborts through loguru CHECK (Lattice.cu:162-181); here it is an exception
     if not cond:
@@ -142,6 +158,8 @@ class HashTable:
 class Lattice:
     """The user-visible lattice handle (reference: class Lattice, /root/reference/src/Lattice.cu)."""
 
+    SUPPORTS_TRANSPOSED_FILTER = True     # convolve_im2row_standalone(..., transposed_filter=True)
+
     m_expected_position_dimensions = -1   # static in the reference too (Lattice.cu:44,143)
 
     # ---- construction ------------------------------------------------------------------------
@@ -245,10 +263,13 @@ class Lattice:
         return 2 * (Lattice.m_expected_position_dimensions + 1) + 1
 
     def set_values(self, new_values):
-        # Lattice::set_values, Lattice.cu:1394-1398
-        self.m_hash_table.set_values(new_values)
-        _check(new_values.shape[0] == self.nr_lattice_vertices(),
-               f"set_values: {new_values.shape[0]} rows but the lattice has {self.nr_lattice_vertices()} vertices")
+        # Lattice::set_values, Lattice.cu:1394-1398 (kept by reference; row count must equal the vertex count)
+        ht = self.m_hash_table
+        ht.m_values_tensor = new_values if new_values.is_contiguous() else new_values.contiguous()
+        st = ht.structure
+        nv = st.nv if (st is not None and st.nv is not None) else self.nr_lattice_vertices()
+        if new_values.shape[0] != nv:
+            raise RuntimeError(f"set_values: {new_values.shape[0]} rows but the lattice has {nv} vertices")
 
     # ---- helpers ---------------------------------------------------------------------------------
     def _device_of(self, t):
@@ -452,31 +473,71 @@ class Lattice:
         return coarse
 
     # ---- convolution -----------------------------------------------------------------------------
-    def convolve_im2row_standalone(self, filter_bank, dilation, lattice_neighbours=None, flip_neighbours=False, bias=None):
+    def convolve_im2row_standalone(self, filter_bank, dilation, lattice_neighbours=None, flip_neighbours=False, bias=None,
+                                   transposed_filter=False):
         """values_new[nv_self x nr_filters] = im2row(lattice_neighbours) . filter_bank, as one implicit-GEMM
-        kernel (Lattice.cu:424-474).  Returns a new handle sharing this lattice's structure."""
+        kernel (Lattice.cu:424-474).  Returns a new handle sharing this lattice's structure.
+        transposed_filter (extension): filter_bank is the forward bank [F*nr_filters x val_dim] of the convolution
+        whose data gradient this call computes; it is read transposed in place (lattice_funcs.py:304-311)."""
         nbrs = self if lattice_neighbours is None else lattice_neighbours
         _check(filter_bank is not None and filter_bank.dim() == 2, "filter bank should be 2-D: (filter_extent*val_dim) x nr_filters")
         st = self._structure()
         vn = nbrs.val_dim()
-        nr_filters = int(filter_bank.shape[1])
-        F = int(filter_bank.shape[0]) // vn
-        _check(F == self.get_filter_extent(1) and F * vn == filter_bank.shape[0],
-               f"filter extent should be {self.get_filter_extent(1)} but the filter bank has {filter_bank.shape[0]} rows for val_dim {vn}")
+        if transposed_filter:
+            F = self.get_filter_extent(1)
+            nr_filters = int(filter_bank.shape[0]) // F     # input width of the forward conv = output width here
+            _check(nr_filters * F == filter_bank.shape[0] and int(filter_bank.shape[1]) == vn,
+                   f"transposed filter bank should be [{F}*c x {vn}], got {tuple(filter_bank.shape)}")
+        else:
+            nr_filters = int(filter_bank.shape[1])
+            F = int(filter_bank.shape[0]) // vn
+            _check(F == self.get_filter_extent(1) and F * vn == filter_bank.shape[0],
+                   f"filter extent should be {self.get_filter_extent(1)} but the filter bank has {filter_bank.shape[0]} rows for val_dim {vn}")
         table = self._neighbour_table(nbrs, dilation)
         nv = st.nr_vertices()
         vals = nbrs.values()
         _check(vals.shape[0] >= nbrs.nr_lattice_vertices(), "neighbour lattice values have fewer rows than vertices")
         fb = _as_cuda_f32(filter_bank, st.device)
         out = torch.empty((nv, nr_filters), dtype=torch.float32, device=st.device)
-        ws_bytes = int(_cabi.load().ln_conv_workspace_bytes(F, vn, nr_filters, CONV_PRECISION))
-        workspace = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=st.device) if ws_bytes else None
+        workspace = _workspace(self._conv_ws_bytes(F, vn, nr_filters), st.device)
         call("ln_conv_fwd", ptr(vals.contiguous()), ptr(table), ptr(fb), ptr(bias), nv, F, vn, nr_filters,
-             1 if flip_neighbours else 0, CONV_PRECISION, ptr(workspace), ptr(out), stream_ptr(st.device))
+             1 if flip_neighbours else 0, 1 if transposed_filter else 0, CONV_PRECISION, ptr(workspace), ptr(out),
+             stream_ptr(st.device))
         new = self.clone_lattice()
         new.m_name = "convolved_lattice"
         new.m_hash_table.set_values(out)
         return new
+
+    @staticmethod
+    def _conv_ws_bytes(F, c_in, c_out):
+        if CONV_PRECISION == 0 or c_in % 32 != 0 or c_out > 256:
+            return 0
+        return 2 * F * c_in * ((c_out + 15) // 16 * 16) * 4      # == ln_conv_workspace_bytes()
+
+    def conv_backward(self, lattice_neighbours, grad_values, filter_bank, dilation, need_input_grad=True):
+        """Backward of `out = self.convolve_im2row_standalone(filter_bank, dilation, lattice_neighbours)`:
+        returns (grad w.r.t. lattice_neighbours.values(), grad w.r.t. filter_bank) from one C call
+        (lattice_funcs.py:294-313 / 373-388 / 438-454 do it with two im2row buffers and three GEMMs)."""
+        nbrs = self if lattice_neighbours is None else lattice_neighbours
+        st, nst = self._structure(), nbrs._structure()
+        table_fwd = self._neighbour_table(nbrs, dilation)
+        nv_q, nv_n = st.nr_vertices(), nst.nr_vertices()
+        vn = nbrs.val_dim()
+        g = _as_cuda_f32(grad_values, st.device)
+        _check(g.shape[0] == nv_q, "grad_values rows must match the query lattice")
+        c_out = int(g.shape[1])
+        F = self.get_filter_extent(1)
+        fb = _as_cuda_f32(filter_bank, st.device)
+        _check(tuple(fb.shape) == (F * vn, c_out), f"filter bank should be [{F * vn} x {c_out}], got {tuple(fb.shape)}")
+        grad_filter = torch.empty((F * vn, c_out), dtype=torch.float32, device=st.device)
+        grad_in = table_bwd = None
+        if need_input_grad:
+            table_bwd = nbrs._neighbour_table(self, dilation)
+            grad_in = torch.empty((nv_n, vn), dtype=torch.float32, device=st.device)
+        workspace = _workspace(self._conv_ws_bytes(F, c_out, vn), st.device)
+        call("ln_conv_bwd", ptr(nbrs.values().contiguous()), ptr(table_fwd), ptr(g), ptr(table_bwd), ptr(fb), nv_q, nv_n, F, vn,
+             c_out, CONV_PRECISION, ptr(workspace), ptr(grad_in), ptr(grad_filter), stream_ptr(st.device))
+        return grad_in, grad_filter
 
     def conv_weight_grad(self, lattice_neighbours, grad_values, filter_extent, dilation):
         """grad_filter = im2row(lattice_neighbours)^T . grad_values without the rowified buffer

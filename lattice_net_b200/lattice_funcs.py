@@ -22,10 +22,18 @@ def _conv_backward(query, neighbours, neighbour_values, filter_bank, grad_out, d
     filter_extent = int(filter_bank.shape[0] // val_dim)
     grad_out = grad_out.contiguous()
     neighbours.set_values(neighbour_values)
+    if hasattr(query, "conv_backward"):     # both gradients from one call into the CUDA library
+        grad_values, grad_filter = query.conv_backward(neighbours, grad_out, filter_bank, dilation)
+        query.set_values(grad_out)          # the reference leaves the query handle holding the incoming gradient
+        return grad_values, grad_filter
     grad_filter = query.conv_weight_grad(neighbours, grad_out, filter_extent, dilation)
-    filter_bw = query.filter_for_data_grad(filter_bank, filter_extent, val_dim)
     query.set_values(grad_out)
-    grad_lattice = neighbours.convolve_im2row_standalone(filter_bw, dilation, query, True)
+    if getattr(neighbours, "SUPPORTS_TRANSPOSED_FILTER", False):
+        # the kernel reads the forward bank transposed in place: no re-laid-out copy of the filter
+        grad_lattice = neighbours.convolve_im2row_standalone(filter_bank, dilation, query, True, transposed_filter=True)
+    else:
+        filter_bw = query.filter_for_data_grad(filter_bank, filter_extent, val_dim)
+        grad_lattice = neighbours.convolve_im2row_standalone(filter_bw, dilation, query, True)
     return grad_lattice.values(), grad_filter
 
 

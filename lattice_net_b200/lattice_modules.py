@@ -68,6 +68,37 @@ def scatter_sum_count(src, index, nv):
     return out, cnt
 
 
+class _GroupNormReLU(torch.autograd.Function):
+    """GroupNorm (+ReLU) on vertex-major values [nv x C] in one kernel each way (ln_group_norm_fwd/bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, relu):
+        x = x.contiguous()
+        nv, c = x.shape
+        y = torch.empty_like(x)
+        stats = torch.empty((groups, 2), dtype=torch.float32, device=x.device)
+        call("ln_group_norm_fwd", ptr(x), ptr(gamma.contiguous()), ptr(beta.contiguous()), nv, c, groups, float(eps),
+             1 if relu else 0, ptr(y), ptr(stats), stream_ptr(x.device))
+        ctx.save_for_backward(x, y, gamma, stats)
+        ctx.groups, ctx.relu = groups, relu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, stats = ctx.saved_tensors
+        nv, c = x.shape
+        dx = torch.empty_like(x)
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(gamma)
+        call("ln_group_norm_bwd", ptr(dy.contiguous()), ptr(x), ptr(y), ptr(gamma.contiguous()), ptr(stats), nv, c, ctx.groups,
+             1 if ctx.relu else 0, ptr(dx), ptr(dgamma), ptr(dbeta), stream_ptr(x.device))
+        return dx, dgamma, dbeta, None, None, None
+
+
+# one CTA per group: meant for the lattice sizes where launch count, not bandwidth, is the cost
+FUSED_NORM_MAX_ELEMS_PER_GROUP = 1 << 17
+
+
 # --------------------------------------------------------------------------------------------------
 # weight normalisation with a per-output gain and a whole-tensor norm: what the reference's
 # weight_norm_wrapper(cls, g_dim, v_dim=None) computes (latticenet_py/utils/utils.py:72-158)
@@ -330,14 +361,25 @@ class GroupNormLatticeModule(torch.nn.Module):
         nr_groups = 32 if nr_params % 32 == 0 else int(nr_params / 2)   # lattice_modules.py:587-590
         self.gn = torch.nn.GroupNorm(nr_groups, nr_params).to(device or _default_device())
 
-    def forward(self, lattice_values, lattice_py, do_set_values=True):
+    def forward(self, lattice_values, lattice_py, do_set_values=True, relu=False):
         if lattice_values.dim() != 2:
             sys.exit("lattice should be 2 dimensional, nr_vertices x val_dim")
         # statistics run over (channels of a group) x (all vertices): vertices are the "length" axis
-        lv = self.gn(lattice_values.t().unsqueeze(0)).squeeze(0).t()
+        gn = self.gn
+        nv, c = lattice_values.shape
+        if lattice_values.is_cuda and nv * (c // gn.num_groups) <= FUSED_NORM_MAX_ELEMS_PER_GROUP:
+            lv = _GroupNormReLU.apply(lattice_values, gn.weight, gn.bias, gn.num_groups, gn.eps, relu)
+        else:
+            lv = gn(lattice_values.t().unsqueeze(0)).squeeze(0).t()
+            if relu:
+                lv = torch.relu(lv)
         if do_set_values:
             lattice_py.set_values(lv)
         return lv, lattice_py
+
+    def forward_relu(self, lattice_values, lattice_py):
+        """GroupNorm followed by ReLU as one fused op (the GN -> ReLU -> conv pattern of every block)."""
+        return self.forward(lattice_values, lattice_py, True, relu=True)
 
 
 class PointNetModule(torch.nn.Module):
@@ -447,8 +489,8 @@ class GnRelu1x1(torch.nn.Module):
 
     def forward(self, lv, ls):
         ls.set_values(lv)
-        lv, ls = self.norm(lv, ls)
-        lv = self.linear(self.relu(lv))
+        lv, ls = self.norm.forward_relu(lv, ls)
+        lv = self.linear(lv)
         ls.set_values(lv)
         return lv, ls
 
@@ -496,11 +538,10 @@ class GnReluConv(torch.nn.Module):
 
     def forward(self, lv, ls):
         ls.set_values(lv)
-        lv, ls = self.norm(lv, ls)
-        lv = self.relu(lv)
+        lv, ls = self.norm.forward_relu(lv, ls)
         if self.drop is not None:
             lv = self.drop(lv)
-        ls.set_values(lv)
+            ls.set_values(lv)
         lv_1, ls_1 = self.conv(lv, ls)
         ls_1.set_values(lv_1)
         return lv_1, ls_1
@@ -553,9 +594,7 @@ class GnReluCoarsen(torch.nn.Module):
 
     def forward(self, lv, ls, concat_connection=None):
         ls.set_values(lv)
-        lv, ls = self.norm(lv, ls)
-        lv = self.relu(lv)
-        ls.set_values(lv)
+        lv, ls = self.norm.forward_relu(lv, ls)
         lv_1, ls_1 = self.coarse(lv, ls)
         ls_1.set_values(lv_1)
         if concat_connection is not None:
@@ -589,9 +628,7 @@ class GnReluFinefy(torch.nn.Module):
 
     def forward(self, lv_coarse, ls_coarse, ls_fine):
         ls_coarse.set_values(lv_coarse)
-        lv_coarse, ls_coarse = self.norm(lv_coarse, ls_coarse)
-        lv_coarse = self.relu(lv_coarse)
-        ls_coarse.set_values(lv_coarse)
+        lv_coarse, ls_coarse = self.norm.forward_relu(lv_coarse, ls_coarse)
         lv_1, ls_1 = self.fine(lv_coarse, ls_coarse, ls_fine)
         ls_1.set_values(lv_1)
         return lv_1, ls_1

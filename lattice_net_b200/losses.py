@@ -17,12 +17,30 @@ def lovasz_grad(gt_sorted):
 
 
 def lovasz_softmax(probas, labels, ignore_index=None):
-    """probas [P, C] (class probabilities), labels [P] (int64).  Mean over the classes present."""
+    """probas [P, C] (class probabilities), labels [P] (int64).  Mean over the classes present.
+    All classes are handled by one batched sort / cumsum (the textbook version loops over classes)."""
     if ignore_index is not None:
         keep = labels != ignore_index
         probas, labels = probas[keep], labels[keep]
     if probas.numel() == 0:
         return probas.sum() * 0.0
+    nr_classes = probas.shape[1]
+    # class-major [C, P] so that the sort and the scans run along the contiguous dimension
+    fg = torch.nn.functional.one_hot(labels, nr_classes).to(probas.dtype).t().contiguous()
+    present = (fg.sum(1) > 0).to(probas.dtype)
+    errors_sorted, perm = torch.sort((fg - probas.t()).abs(), dim=1, descending=True)
+    fg_sorted = fg.gather(1, perm)
+    gts = fg_sorted.sum(1, keepdim=True)
+    intersection = gts - fg_sorted.cumsum(1)
+    union = gts + (1.0 - fg_sorted).cumsum(1)
+    jaccard = 1.0 - intersection / union
+    grad = torch.cat([jaccard[:, :1], jaccard[:, 1:] - jaccard[:, :-1]], 1)       # Lovasz extension gradient
+    per_class = (errors_sorted * grad).sum(1)
+    return (per_class * present).sum() / present.sum().clamp(min=1.0)
+
+
+def lovasz_softmax_loop(probas, labels):
+    """Per-class loop formulation (reference: latticenet_py/lattice/lovasz_loss.py:41-72), kept for tests."""
     losses = []
     for c in range(probas.shape[1]):
         fg = (labels == c).float()

@@ -39,7 +39,12 @@ def scenes_for_rank(nr_scenes, rank, world):
 
 
 class GradBucket:
-    """All parameter gradients of a model as views into one flat fp32 buffer."""
+    """All parameter gradients of a model in one flat fp32 buffer, for a single all-reduce per step.
+
+    Gradients are produced by autograd as separate tensors (`.grad` is reset to None before each backward,
+    so autograd hands its buffers over without an accumulation kernel per parameter); `pack()` gathers them
+    into the flat buffer with one multi-tensor copy and re-points every `.grad` at its slice, so the
+    optimizer reads the reduced values without an unpack pass."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
@@ -47,33 +52,30 @@ class GradBucket:
         dev = self.params[0].device
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.views = []
         off = 0
         for p in self.params:
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
+            self.views.append(self.flat[off:off + n].view_as(p))
             off += n
         self.nbytes = total * 4
 
     def zero(self):
-        self.flat.zero_()
-
-    def reattach(self):
-        """optimizer.zero_grad(set_to_none=True) or autograd may replace .grad; re-alias and keep values."""
-        off = 0
+        """Call before backward."""
         for p in self.params:
-            n = p.numel()
-            view = self.flat[off:off + n].view_as(p)
-            if p.grad is None:
-                view.zero_()
-                p.grad = view
-            elif p.grad.data_ptr() != view.data_ptr():
-                view.copy_(p.grad)
-                p.grad = view
-            off += n
+            p.grad = None
+
+    def pack(self):
+        """Call after backward: flat <- all grads (one fused copy), .grad <- views of flat."""
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+        torch._foreach_copy_(self.views, grads)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def allreduce_mean(self, world):
-        """One collective for the whole model; averages over ranks."""
+        """One collective for the whole model; averages over ranks.  Single process: nothing to do."""
         if world > 1:
+            self.pack()
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.mul_(1.0 / world)
 

@@ -263,6 +263,7 @@ def run(args, cloud_fn, cfg):
     lm.scatter_max = lambda src, index, nv: _torch_scatter_max(src, index, nv)
     lm.scatter_sum_count = _torch_scatter_sum_count
     lm.ConvLatticeIm2RowModule.forward = _ref_conv_module_forward
+    lm.FUSED_NORM_MAX_ELEMS_PER_GROUP = 0      # torch GroupNorm + ReLU, as in the reference
     _L.m_expected_position_dimensions = 3            # static pos-dim the module constructors read
     model = LNN(cfg["nr_classes"], ModelParams(), device=dev)
     pool = 16

@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from oracle import cases, lattice_oracle as lo
-from tests.util import assert_close, bits_equal, canonical, max_rel_err
+from tests.util import agg, assert_close, bits_equal, canonical, max_rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -63,7 +63,9 @@ def built(request):
 
 def test_structure_bit_exact(built):
     b = built
-    assert b["nv"] == b["rnv"] == b["cpu"]["nv"]
+    assert b["nv"] == b["cpu"]["nv"] == len(b["rks"])
+    if b["rnv"] != len(b["rks"]):
+        print(f"note: the reference kernel stored {b['rnv'] - len(b['rks'])} duplicate vertices in this run")
     assert np.array_equal(b["ks"], b["rks"]), "key set differs from the reference kernels"
     assert np.array_equal(b["ks"], b["cpu"]["keys"]), "key set differs from the CPU oracle"
     ours_idx = lo.relabel(b["idx"].cpu().numpy(), b["o2n"])
@@ -81,7 +83,7 @@ def test_splat_values(built):
     ours = b["ours"].values()
     assert tuple(ours.shape) == (b["spec"]["capacity"], 3)           # [capacity x V], like the reference
     ours_np = ours[:b["nv"]].cpu().numpy()[b["n2o"]]
-    ref_np = b["ref"].values[:b["nv"]].cpu().numpy()[b["rn2o"]]
+    ref_np = agg(b["ref"].values[:b["nv"]].cpu().numpy(), b["ro2n"])
     assert_close(ours_np, ref_np, TOL_VALUES, "splat values vs reference kernels")
     assert_close(ours_np, lo.splat_accumulate(b["vals_np"], b["cpu"]["indices"], b["cpu"]["weights"], b["nv"]), TOL_VALUES, "splat values vs oracle")
     assert float(ours[b["nv"]:].abs().max()) == 0.0
@@ -108,9 +110,9 @@ def test_distribute(built):
     ref = _ref().RefLattice(spec["capacity"], spec["sigmas"])
     rdist, ridx, rw = ref.distribute(pos, cuda(dv))
     nv = dl.nr_lattice_vertices()
-    assert nv == ref.nv() == b["nv"]
+    assert nv == b["nv"]
     ks, o2n, _ = canonical(dl.hash_table().m_keys_tensor[:nv].cpu().numpy())
-    rks, ro2n, _ = canonical(ref.table.keys[:nv].cpu().numpy())
+    rks, ro2n, _ = canonical(ref.table.keys[:ref.nv()].cpu().numpy())
     assert np.array_equal(ks, rks)
     assert np.array_equal(lo.relabel(idx.cpu().numpy(), o2n), lo.relabel(ridx.cpu().numpy(), ro2n))
     assert bits_equal(w.cpu().numpy(), rw.cpu().numpy()) == 0
@@ -131,7 +133,7 @@ def test_slice_fwd_bwd(built, V):
     g = cases.randn((b["n"], V), 30 + V)
     ours.slice_backwards_standalone_with_precomputation_no_homogeneous(b["pos"], cuda(g), b["idx"], b["w"])
     grad = ours.values().cpu().numpy()[b["n2o"]]
-    rgrad = ref.slice_backwards(cuda(g), b["ridx"], b["rw"]).cpu().numpy()[b["rn2o"]]
+    rgrad = agg(ref.slice_backwards(cuda(g), b["ridx"], b["rw"]).cpu().numpy(), b["ro2n"])
     assert_close(grad, rgrad, TOL_GRADS, "slice backward vs reference kernels")
     assert_close(grad, lo.slice_bwd(g, b["cpu"]["indices"], b["cpu"]["weights"], b["nv"]), TOL_GRADS, "slice backward vs oracle")
 
@@ -165,7 +167,7 @@ def test_gather_fwd_bwd(built):
     gg = cases.randn((b["n"], (b["d"] + 1) * (V + 1)), 40)
     ours.gather_backwards_standalone_with_precomputation(b["pos"], cuda(gg), b["idx"], b["w"])
     grad = ours.values().cpu().numpy()[b["n2o"]]
-    rgrad = ref.gather_backwards(cuda(gg), b["ridx"], b["rw"]).cpu().numpy()[b["rn2o"]]
+    rgrad = agg(ref.gather_backwards(cuda(gg), b["ridx"], b["rw"]).cpu().numpy(), b["ro2n"])
     assert_close(grad, rgrad, TOL_GRADS, "gather backward vs reference kernels")
     assert_close(grad, lo.gather_bwd(gg, b["cpu"]["indices"], b["cpu"]["weights"], b["nv"], V), TOL_GRADS, "gather backward vs oracle")
 
@@ -195,7 +197,7 @@ def test_slice_classify(built, V, nc):
     r = ref.slice_classify_backwards(cuda(gl), cuda(lv[b["ro2n"]]), cuda(dw), cuda(cw), cuda(cb), b["ridx"], b["rw"])
     e = lo.slice_classify_bwd(gl, lv, b["cpu"]["indices"], b["cpu"]["weights"], dw, cw, n)
     got = [g_lv.cpu().numpy()[b["n2o"]], g_dw.cpu().numpy(), g_w.cpu().numpy(), g_b.cpu().numpy()]
-    refs = [r[0].cpu().numpy()[b["rn2o"]], r[1].cpu().numpy(), r[2].cpu().numpy(), r[3].cpu().numpy()]
+    refs = [agg(r[0].cpu().numpy(), b["ro2n"]), r[1].cpu().numpy(), r[2].cpu().numpy(), r[3].cpu().numpy()]
     for name, a, rr, ee in zip(("grad_values", "grad_delta_w", "grad_W", "grad_b"), got, refs, e):
         assert_close(a, ee, TOL_GRADS, f"slice_classify {name} vs oracle")
         assert_close(a, rr, TOL_GRADS, f"slice_classify {name} vs reference kernels")
@@ -247,10 +249,9 @@ def test_coarse_levels(built):
     coarse = ours.create_coarse_verts_naive(b["pos"])
     rcoarse = b["ref"].create_coarse_verts_naive(b["pos"])
     nvc = coarse.nr_lattice_vertices()
-    assert nvc == rcoarse.nv()
     cks, co2n, cn2o = canonical(coarse.hash_table().m_keys_tensor[:nvc].cpu().numpy())
-    rcks, rco2n, rcn2o = canonical(rcoarse.table.keys[:nvc].cpu().numpy())
-    assert np.array_equal(cks, rcks)
+    rcks, rco2n, rcn2o = canonical(rcoarse.table.keys[:rcoarse.nv()].cpu().numpy())
+    assert np.array_equal(cks, rcks) and nvc == len(rcks)      # (the reference may hold duplicates of some keys)
     assert coarse.lvl() == 2 and coarse.m_sigmas == [s * 2.0 for s in ours.m_sigmas]
     coarse.set_values(torch.zeros((nvc, 1), device="cuda"))
     # coarse <- fine  (coarsen forward) and fine <- coarse (finefy forward / coarsen backward)
@@ -289,10 +290,10 @@ def test_conv_fwd_wgrad_dgrad(built, Cin, Cout):
     assert_close(got, exp, TOL_VALUES, "conv forward vs oracle")
     ref = b["ref"]
     if ref.k.has(f"im2row<{b['d']},{Cin}>"):
-        rout = ref.convolve(cuda(fb), ref, cuda(lv[b["ro2n"]]), 1, False).cpu().numpy()[b["rn2o"]]
+        rout = agg(ref.convolve(cuda(fb), ref, cuda(lv[b["ro2n"]]), 1, False).cpu().numpy(), b["ro2n"])
         assert_close(got, rout, TOL_VALUES, "conv forward vs reference im2row+mm")
         rows = ours.im2row(ours, F, 1, False).cpu().numpy()[b["n2o"]]
-        rrows = ref.im2row(ref, cuda(lv[b["ro2n"]]), 1, False).cpu().numpy()[b["rn2o"]]
+        rrows = agg(ref.im2row(ref, cuda(lv[b["ro2n"]]), 1, False).cpu().numpy(), b["ro2n"])
         assert bits_equal(rows, rrows) == 0, "im2row differs from the reference"
     # weight gradient and data gradient
     g = cases.randn((b["nv"], Cout), 80 + Cout)
@@ -321,7 +322,7 @@ def test_row2im(built):
     rows = ours.im2row(ours, F, 1, False)
     back = ours.row2im(rows, 1, F, 16, ours).cpu().numpy()[b["n2o"]]
     rrows = ref.im2row(ref, cuda(lv[b["ro2n"]]), 1, False)
-    rback = ref.row2im(rrows, ref, V, 1).cpu().numpy()[b["rn2o"]]
+    rback = agg(ref.row2im(rrows, ref, V, 1).cpu().numpy(), b["ro2n"])
     assert_close(back, rback, 1e-6, "row2im vs reference kernels")
     table = lo.neighbour_table(b["ks"], b["ks"], 0, 1)
     assert_close(back, lo.row2im(lo.im2row(lv, table), table, V), 1e-6, "row2im vs oracle")
@@ -464,3 +465,50 @@ def test_conv_tensor_core_cross_level(built):
     finally:
         lattice_mod.set_conv_precision(0)
     assert_close(got, lo.conv_fwd(lv, up, fb), 2e-5, "tensor-core coarsen conv")
+
+
+@pytest.mark.parametrize("nv,C", [(983, 32), (1231, 128), (77, 192), (25, 256), (300, 8), (5000, 96)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_fused_group_norm(nv, C, relu):
+    """ln_group_norm_fwd/bwd vs torch.nn.GroupNorm on the [1, C, nv] view the reference uses."""
+    from lattice_net_b200.lattice_modules import _GroupNormReLU
+    torch.manual_seed(nv + C)
+    groups = 32 if C % 32 == 0 else C // 2
+    x = torch.randn((nv, C), device="cuda") * 2 + 0.5
+    gamma = torch.randn(C, device="cuda")
+    beta = torch.randn(C, device="cuda")
+    g = torch.randn((nv, C), device="cuda")
+    xs = [x.clone().requires_grad_(True) for _ in range(2)]
+    ps = [(gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)) for _ in range(2)]
+    y0 = torch.nn.functional.group_norm(xs[0].t().unsqueeze(0), groups, ps[0][0], ps[0][1], 1e-5).squeeze(0).t()
+    if relu:
+        y0 = torch.relu(y0)
+    y1 = _GroupNormReLU.apply(xs[1], ps[1][0], ps[1][1], groups, 1e-5, relu)
+    assert_close(y1.detach().cpu().numpy(), y0.detach().cpu().numpy(), 1e-5, "fused group norm forward")
+    y0.backward(g)
+    y1.backward(g)
+    assert_close(xs[1].grad.cpu().numpy(), xs[0].grad.cpu().numpy(), 1e-4, "fused group norm dx")
+    assert_close(ps[1][0].grad.cpu().numpy(), ps[0][0].grad.cpu().numpy(), 1e-4, "fused group norm dgamma")
+    assert_close(ps[1][1].grad.cpu().numpy(), ps[0][1].grad.cpu().numpy(), 1e-4, "fused group norm dbeta")
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_conv_transposed_filter_equals_relayout(built, precision):
+    """dgrad with the forward bank read transposed in place == dgrad with the re-laid-out copy."""
+    from lattice_net_b200 import Lattice, lattice as lattice_mod
+    b = built
+    F = 2 * (b["d"] + 1) + 1
+    Cin, Cout = 32, 64
+    fb = (cases.randn((F * Cin, Cout), 64) * 0.1).astype(np.float32)
+    g = cases.randn((b["nv"], Cout), 85)
+    lat = b["ours"].clone_lattice()
+    lat.set_values(cuda(g))
+    try:
+        lattice_mod.set_conv_precision(precision)
+        a = lat.convolve_im2row_standalone(cuda(fb), 1, lat, True, transposed_filter=True).values()
+        fbw = Lattice.filter_for_data_grad(cuda(fb), F, Cin)
+        c = lat.convolve_im2row_standalone(fbw, 1, lat, True).values()
+    finally:
+        lattice_mod.set_conv_precision(0)
+    assert tuple(a.shape) == (b["nv"], Cin)
+    assert_close(a.cpu().numpy(), c.cpu().numpy(), 1e-6, "transposed-filter dgrad")

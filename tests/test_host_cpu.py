@@ -114,3 +114,18 @@ def test_product_never_imports_the_oracle():
             with open(os.path.join(pkg, fn)) as f:
                 src = f.read()
             assert "oracle" not in src.replace("# oracle", ""), f"{fn} mentions the oracle"
+
+
+def test_batched_lovasz_equals_per_class_loop():
+    import torch
+    from lattice_net_b200.losses import lovasz_softmax, lovasz_softmax_loop, segmentation_loss
+    torch.manual_seed(0)
+    logits = torch.randn(500, 7, requires_grad=True)
+    labels = torch.randint(0, 5, (500,))            # classes 5 and 6 absent
+    p = torch.softmax(logits, 1)
+    a, b = lovasz_softmax(p, labels), lovasz_softmax_loop(p, labels)
+    assert torch.allclose(a, b, atol=1e-6)
+    ga, = torch.autograd.grad(a, logits, retain_graph=True)
+    gb, = torch.autograd.grad(b, logits)
+    assert torch.allclose(ga, gb, atol=1e-6)
+    assert torch.isfinite(segmentation_loss(torch.log_softmax(logits, 1), labels))

@@ -25,7 +25,7 @@ def _worker(rank, world, port, out):
     x = torch.full((5, 4), float(rank + 1))
     bucket.zero()
     model(x).sum().backward()
-    local = bucket.flat.clone()
+    local = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
     bucket.allreduce_mean(world)
     gathered = [torch.zeros_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
@@ -54,13 +54,14 @@ def test_scene_sharding_is_a_partition():
         assert seen == list(range(37))
 
 
-def test_bucket_reattach_after_zero_grad():
+def test_bucket_pack_aliases_grads():
     model = torch.nn.Linear(3, 2)
     bucket = GradBucket(model.parameters())
+    bucket.zero()
+    assert all(p.grad is None for p in model.parameters())
     model(torch.ones(1, 3)).sum().backward()
-    before = bucket.flat.clone()
-    for p in model.parameters():
-        p.grad = p.grad.clone()                  # something replaced the aliases
-    bucket.reattach()
-    assert torch.equal(bucket.flat, before)
-    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in model.parameters())
+    expect = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    bucket.pack()
+    assert torch.equal(bucket.flat, expect)
+    lo, hi = bucket.flat.data_ptr(), bucket.flat.data_ptr() + bucket.nbytes
+    assert all(lo <= p.grad.data_ptr() < hi for p in model.parameters())

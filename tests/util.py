@@ -5,9 +5,20 @@ from oracle import lattice_oracle as lo
 
 
 def canonical(keys_np):
-    """keys [nv,d] (GPU insertion order) -> (sorted keys, old_to_new, new_to_old)."""
-    ks, o2n = lo.canonical_order(keys_np)
-    return ks, o2n, np.argsort(o2n)
+    """keys [nv,d] (GPU insertion order) -> (sorted UNIQUE keys, old_to_new, new_to_old).
+    The reference's insert can, rarely, store the same key twice (its key compare reads through a
+    non-coherent L1, HashTableGPU.cuh:457-463); duplicates map onto one canonical id and new_to_old
+    names the first occurrence."""
+    ks, first, inv = np.unique(np.asarray(keys_np), axis=0, return_index=True, return_inverse=True)
+    return ks, inv.reshape(-1).astype(np.int64), first.astype(np.int64)
+
+
+def agg(rows, old_to_new):
+    """Per-vertex rows in GPU order -> canonical order, summing rows of duplicated vertices."""
+    rows = np.asarray(rows)
+    out = np.zeros((int(old_to_new.max()) + 1,) + rows.shape[1:], rows.dtype)
+    np.add.at(out, old_to_new, rows)
+    return out
 
 
 def max_rel_err(a, b):
