@@ -186,6 +186,8 @@ def kernel_roofline(device):
 
 def run_ours(args):
     from lattice_net_b200 import _cabi
+    from lattice_net_b200.graphed import GraphedTrainStep, estimate_vertex_bounds
+    from lattice_net_b200.losses import segmentation_loss
     from lattice_net_b200.parallel import GradBucket, broadcast_parameters, init_distributed
     rank, world, local_rank = init_distributed("nccl")
     device = torch.device("cuda", local_rank)
@@ -203,23 +205,43 @@ def run_ours(args):
     with torch.no_grad():
         model(lattice, *dev_clouds[0][:2])
     broadcast_parameters(model, 0)
-    optimizer = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=3e-4, amsgrad=True, fused=True)
+    graphed = args.mode == "graph"
+    optimizer = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=3e-4, amsgrad=True, fused=True, capturable=graphed)
     bucket = GradBucket(model.parameters())
     flush_buf = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=device)
 
-    def step_resident(i):
-        pos, vals, labels = dev_clouds[i % POOL]
-        train_step(model, lattice, pos, vals, labels, optimizer, bucket, world)
+    bounds = None
+    if graphed:
+        # static-shape mode + one CUDA graph per step (lattice_net_b200/graphed.py); rows per lattice level from
+        # the vertex counts of this rank's clouds (+30 %), identical on every replay
+        nr_levels = model.nr_downsamples + 1
+        bounds = estimate_vertex_bounds(CAPACITY, [(SIGMA, 3)], [c[0] for c in dev_clouds], nr_levels, headroom=1.3)
+        step = GraphedTrainStep(model, lattice, optimizer, segmentation_loss, NR_POINTS, 3, 1, bounds, bucket, world,
+                                warmup=3, capture_collective=args.capture_collective, example=dev_clouds[0])
+        launches_per_step = step.launches_per_step
 
-    losses = []
+        def step_resident(i):
+            step(*dev_clouds[i % POOL])
 
-    def step_e2e(i):
-        hp, hv, hl = host_clouds[i % POOL]
-        pos = hp.to(device, non_blocking=True)
-        vals = hv.to(device, non_blocking=True)
-        labels = hl.to(device, non_blocking=True)
-        loss = train_step(model, lattice, pos, vals, labels, optimizer, bucket, world)
-        losses.append(float(loss.item()))      # D2H read of the step's result
+        losses = []
+
+        def step_e2e(i):
+            loss = step(*host_clouds[i % POOL])                      # H2D of the cloud from pinned memory
+            losses.append(float(loss.item()))                       # D2H read of the step's result
+    else:
+        def step_resident(i):
+            pos, vals, labels = dev_clouds[i % POOL]
+            train_step(model, lattice, pos, vals, labels, optimizer, bucket, world)
+
+        losses = []
+
+        def step_e2e(i):
+            hp, hv, hl = host_clouds[i % POOL]
+            pos = hp.to(device, non_blocking=True)
+            vals = hv.to(device, non_blocking=True)
+            labels = hl.to(device, non_blocking=True)
+            loss = train_step(model, lattice, pos, vals, labels, optimizer, bucket, world)
+            losses.append(float(loss.item()))      # D2H read of the step's result
 
     for i in range(args.warmup):
         step_resident(i)
@@ -228,11 +250,12 @@ def run_ours(args):
         sampler.start()
     _cabi.reset_launch_count()
     ms = timed_region(step_resident, args.steps, world, device, flush_buf)
-    launches = _cabi.launch_count()
+    launches = _cabi.launch_count() if not graphed else launches_per_step * args.steps
     for i in range(max(1, args.warmup // 2)):
         step_e2e(i)
     ms_e2e = timed_region(step_e2e, args.steps, world, device, flush_buf)
     clocks = sampler.stop() if rank == 0 else None
+    overflowed = step.overflowed_steps() if graphed else 0
 
     if rank != 0:
         return
@@ -247,6 +270,8 @@ def run_ours(args):
         "config": {"workload": "LatticeNet ShapeNet-part segmentation fwd+bwd+AdamW (lnn_train_shapenet.cfg arch), 2048-pt synthetic clouds, 1 scene/step/GPU",
                    "nr_points": NR_POINTS, "nr_classes": NR_CLASSES, "sigma": SIGMA, "hash_table_capacity": CAPACITY,
                    "parallelism": f"scene-parallel dp{world}, one flat NCCL all-reduce of {bucket.nbytes} grad bytes/step",
+                   "execution": ("one CUDA graph per step (static-shape lattice, rows per level %s; %d step(s) skipped for exceeding them)" % (bounds, overflowed))
+                                if graphed else "eager launches (dynamic-shape lattice)",
                    "l2": f"flushed between steps by a {L2_FLUSH_BYTES >> 20} MiB write (inside the timed region)",
                    "conv_precision": {0: "fp32 FMA on CUDA cores", 1: "tcgen05 3xTF32 split, fp32 accumulate (fp32-equivalent)", 2: "tcgen05 TF32"}[args.conv_precision]},
         "e2e": {"value": scans / (ms_e2e * 1e-3), "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -283,6 +308,9 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
+                    help="graph: static-shape lattice + one CUDA graph per step (default); eager: dynamic-shape launches")
+    ap.add_argument("--capture-collective", action="store_true", help="N>1: capture the NCCL all-reduce inside the step graph")
     ap.add_argument("--conv-precision", type=int, default=1, choices=[0, 1, 2],
                     help="0 fp32 CUDA cores, 1 tcgen05 3xTF32 (fp32-equivalent, default), 2 tcgen05 TF32")
     args = ap.parse_args()

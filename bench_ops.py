@@ -101,7 +101,7 @@ def run(n, d, vals, quick):
 
     def build():
         st.clear()
-        call("ln_splat_build", ptr(pos), ptr(sig), n, d, ptr(st.keys), ptr(st.entries), ptr(st.nr_filled), ptr(st.status), st.capacity, ptr(idx), ptr(w), stream_ptr(dev))
+        call("ln_splat_build", ptr(pos), ptr(sig), n, d, ptr(st.keys), ptr(st.entries), ptr(st.nr_filled), ptr(st.status), st.capacity, 0, ptr(idx), ptr(w), stream_ptr(dev))
 
     ref = None
     ref_sec = None

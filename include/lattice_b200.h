@@ -38,12 +38,13 @@ extern "C" {
 #define LN_ERR_CUDA (-2)           /* a CUDA runtime call / launch failed                     */
 #define LN_ERR_UNSUPPORTED (-3)    /* shape outside what the kernels implement                */
 #define LN_ERR_TABLE_FULL (-4)     /* reported by ln_table_status(): an insert found no slot  */
+#define LN_ERR_VERTEX_BOUND (-5)   /* reported by ln_table_status(): more vertices than max_vertices */
 
 /* Version / build info: "lattice_b200 <ver> sm_100a". */
 const char* ln_version(void);
 /* Message describing the last error returned on this host thread. */
 const char* ln_last_error(void);
-/* Number of kernels launched by this library on this host thread since the last reset
+/* Number of kernels launched by this library (all host threads) since the last reset
  * (bench.py reports it as `gpu_launches`). */
 long long ln_launch_count(void);
 void ln_reset_launch_count(void);
@@ -65,9 +66,12 @@ int ln_table_status(const int* nr_filled, const int* status, int* nr_filled_host
  * Lattice::splat_standalone / just_create_verts (/root/reference/src/Lattice.cu:196-290):
  * positions_raw / sigmas, simplex + barycentric computation, insertion of the pos_dim+1 simplex
  * vertices, and (if indices/weights != NULL) the splatting tables.
- *   positions_raw [n x pos_dim], sigmas [pos_dim] (device), indices/weights [n*(pos_dim+1)] or NULL */
+ *   positions_raw [n x pos_dim], sigmas [pos_dim] (device), indices/weights [n*(pos_dim+1)] or NULL
+ * max_vertices (static-shape mode, see DESIGN.md "CUDA-graph step"): the caller's per-vertex tensors have
+ * only max_vertices rows.  Vertices numbered >= max_vertices are still inserted (nr_filled keeps counting)
+ * but are handed out as index -1 / weight -1 and status[0] gets bit 1 set.  <= 0 or > capacity: no bound. */
 int ln_splat_build(const float* positions_raw, const float* sigmas, int n, int pos_dim,
-                   int* keys, int* entries, int* nr_filled, int* status, int capacity,
+                   int* keys, int* entries, int* nr_filled, int* status, int capacity, int max_vertices,
                    int* indices, float* weights, void* stream);
 
 /* Replaces splatCacheNaive<d,V> (LatticeGPU.cuh:926-973):
@@ -82,7 +86,7 @@ int ln_splat_accumulate(const float* values, const int* indices, const float* we
  *        [ positions_raw[p]/sigmas | values[p] | barycentric_r ]                                */
 int ln_distribute(const float* positions_raw, const float* sigmas, const float* values,
                   int n, int pos_dim, int val_dim,
-                  int* keys, int* entries, int* nr_filled, int* status, int capacity,
+                  int* keys, int* entries, int* nr_filled, int* status, int capacity, int max_vertices,
                   int* indices, float* weights, float* distributed, void* stream);
 
 /* Structure part of slice_no_precomputation<d,V> (LatticeGPU.cuh:2598-2750): recompute the simplex
@@ -94,18 +98,23 @@ int ln_lookup_simplex(const float* positions_raw, const float* sigmas, int n, in
 /* Replaces coarsen<d> (LatticeGPU.cuh:2314-2514) used by Lattice::create_coarse_verts
  * (/root/reference/src/Lattice.cu:670-703): every fine vertex whose key is all-even inserts key/2
  * into the coarse table, plus the coarse image of each of its existing fine 1-hop neighbours.
- * nv_fine is read from fine_nr_filled on the device. */
+ * nv_fine is read from fine_nr_filled on the device.  coarse_max_vertices: as max_vertices of ln_splat_build
+ * (only the status flag; this call hands out no indices). */
 int ln_coarsen_keys(const int* fine_keys, const int* fine_entries, const int* fine_nr_filled, int fine_capacity,
                     int* coarse_keys, int* coarse_entries, int* coarse_nr_filled, int* coarse_status, int coarse_capacity,
-                    int pos_dim, int nv_fine_upper, void* stream);
+                    int coarse_max_vertices, int pos_dim, int nv_fine_upper, void* stream);
 
 /* ---- neighbourhood ---------------------------------------------------------------------------
  * The traversal of im2row / im2rowindices / row2im (LatticeGPU.cuh:1464-1688, 1690-1920, 2067-2305)
  * done ONCE per (query lattice, neighbour lattice, dilation): neighbours[q, slot] = vertex id in the
  * neighbour lattice or -1.  Slot order (filter_extent F = 2(pos_dim+1)+1): slot 2a = "np" of axis a,
- * slot 2a+1 = "nm" of axis a, slot F-1 = centre.  lvl_diff = query_lvl - neighbour_lvl in {-1,0,1}. */
-int ln_neighbour_table(const int* query_keys, int nv_query, int pos_dim,
-                       const int* nbr_keys, const int* nbr_entries, int nbr_capacity,
+ * slot 2a+1 = "nm" of axis a, slot F-1 = centre.  lvl_diff = query_lvl - neighbour_lvl in {-1,0,1}.
+ * Static-shape mode: nv_query is the ROW BOUND of the table and nv_query_dev (device int32, may be NULL) the
+ * actual vertex count (the query table's nr_filled): rows >= *nv_query_dev get no neighbours, so every
+ * convolution over the table yields zeros there.  Neighbour ids >= nbr_max_vertices (<= 0: no bound) are
+ * reported as absent. */
+int ln_neighbour_table(const int* query_keys, int nv_query, const int* nv_query_dev, int pos_dim,
+                       const int* nbr_keys, const int* nbr_entries, int nbr_capacity, int nbr_max_vertices,
                        int lvl_diff, int dilation, int* neighbours, void* stream);
 
 /* API-parity materialisations (the conv kernels below never need them).
@@ -206,12 +215,15 @@ int ln_scatter_sum_count(const float* src, const int* index, int m, int c, int n
  * GroupNorm (+ optional fused ReLU) on vertex-major lattice values x [nv x c]: statistics per group over
  * (c/groups channels) x (all nv vertices), biased variance -- torch.nn.GroupNorm(groups, c) applied to the
  * [1, c, nv] view the reference builds with unsqueeze/transpose
- * (/root/reference/latticenet_py/lattice/lattice_modules.py:585-614).  stats [groups x 2] = (mean, rstd). */
-int ln_group_norm_fwd(const float* x, const float* gamma, const float* beta, int nv, int c, int groups, float eps,
-                      int relu, float* y, float* stats, void* stream);
+ * (/root/reference/latticenet_py/lattice/lattice_modules.py:585-614).  stats [groups x 2] = (mean, rstd).
+ * nv_dev (device int32, may be NULL): static-shape mode, only the first min(nv, *nv_dev) rows are vertices;
+ * the others are excluded from the statistics and written as zeros. */
+int ln_group_norm_fwd(const float* x, const float* gamma, const float* beta, int nv, const int* nv_dev, int c, int groups,
+                      float eps, int relu, float* y, float* stats, void* stream);
 /* y = forward output (needed for the ReLU mask when relu != 0).  dgamma/dbeta [c] are overwritten. */
 int ln_group_norm_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* stats,
-                      int nv, int c, int groups, int relu, float* dx, float* dgamma, float* dbeta, void* stream);
+                      int nv, const int* nv_dev, int c, int groups, int relu, float* dx, float* dgamma, float* dbeta,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "liblattice_b200.so")
 
 LN_OK = 0
 LN_ERR_TABLE_FULL = -4
+LN_ERR_VERTEX_BOUND = -5
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int
@@ -18,12 +19,12 @@ _I = ctypes.c_int
 _SIGNATURES = {
     "ln_table_clear": [_P, _P, _P, _I, _P],
     "ln_table_status": [_P, _P, _P, _P, _P],
-    "ln_splat_build": [_P, _P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P],
+    "ln_splat_build": [_P, _P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P],
     "ln_splat_accumulate": [_P, _P, _P, _I, _I, _I, _P, _P],
-    "ln_distribute": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P],
+    "ln_distribute": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P],
     "ln_lookup_simplex": [_P, _P, _I, _I, _P, _P, _I, _P, _P, _P],
-    "ln_coarsen_keys": [_P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P],
-    "ln_neighbour_table": [_P, _I, _I, _P, _P, _I, _I, _I, _P, _P],
+    "ln_coarsen_keys": [_P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "ln_neighbour_table": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P],
     "ln_im2row": [_P, _P, _I, _I, _I, _I, _P, _P],
     "ln_im2rowindices": [_P, _I, _I, _I, _I, _P, _P],
     "ln_row2im": [_P, _P, _I, _I, _I, _P, _P],
@@ -39,8 +40,8 @@ _SIGNATURES = {
     "ln_slice_classify_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "ln_scatter_max": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "ln_scatter_sum_count": [_P, _P, _I, _I, _I, _P, _P, _P],
-    "ln_group_norm_fwd": [_P, _P, _P, _I, _I, _I, ctypes.c_float, _I, _P, _P, _P],
-    "ln_group_norm_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P],
+    "ln_group_norm_fwd": [_P, _P, _P, _I, _P, _I, _I, ctypes.c_float, _I, _P, _P, _P],
+    "ln_group_norm_bwd": [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P],
 }
 _SPECIAL = {
     "ln_version": (ctypes.c_char_p, []),

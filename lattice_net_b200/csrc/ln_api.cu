@@ -1,4 +1,5 @@
 // Host-side plumbing of the C ABI: error strings, launch accounting, table status readback.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include "ln_common.cuh"
@@ -6,7 +7,7 @@
 namespace ln {
 
 static thread_local char g_error[512] = "";
-static thread_local long long g_launches = 0;
+static std::atomic<long long> g_launches{0};   // process-wide: backward launches come from autograd's worker thread
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -24,7 +25,7 @@ int check_launch(const char* what) {
     return LN_OK;
 }
 
-void count_launch(int n) { g_launches += n; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 }  // namespace ln
 
@@ -32,8 +33,8 @@ extern "C" {
 
 const char* ln_version(void) { return "lattice_b200 0.1 sm_100a"; }
 const char* ln_last_error(void) { return ln::g_error; }
-long long ln_launch_count(void) { return ln::g_launches; }
-void ln_reset_launch_count(void) { ln::g_launches = 0; }
+long long ln_launch_count(void) { return ln::g_launches.load(std::memory_order_relaxed); }
+void ln_reset_launch_count(void) { ln::g_launches.store(0, std::memory_order_relaxed); }
 
 int ln_table_status(const int* nr_filled, const int* status, int* nr_filled_host, int* max_probe_host, void* stream) {
     LN_REQUIRE(nr_filled && nr_filled_host, "ln_table_status: null pointer");
@@ -47,9 +48,13 @@ int ln_table_status(const int* nr_filled, const int* status, int* nr_filled_host
         return LN_ERR_CUDA;
     }
     if (max_probe_host) *max_probe_host = st[1];
-    if (st[0] != 0) {
+    if (st[0] & 1) {
         ln::set_error("hash table full: an insert found no free slot (nr_filled=%d); raise hash_table_capacity", *nr_filled_host);
         return LN_ERR_TABLE_FULL;
+    }
+    if (st[0] & 2) {
+        ln::set_error("the lattice has %d vertices, more than the max_vertices bound it was built with", *nr_filled_host);
+        return LN_ERR_VERTEX_BOUND;
     }
     return LN_OK;
 }

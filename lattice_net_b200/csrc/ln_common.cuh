@@ -56,8 +56,9 @@ struct TableView {   // device view of one vertex table (HashTableGPU.cuh:23-28)
     int* keys;
     int* entries;
     int* nr_filled;
-    int* status;     // [0] overflow flag, [1] max probe length seen by inserts
+    int* status;     // [0] overflow flags (bit 0 table full, bit 1 vertex bound exceeded), [1] max probe length seen by inserts
     int capacity;
+    int max_vertices;   // ids >= max_vertices are reported through status[0] bit 1 and handed out as -1 by the callers
 };
 struct ConstTableView {
     const int* keys;
@@ -90,6 +91,7 @@ __device__ __forceinline__ int table_insert(const TableView& t, const int* key, 
             cur = atomicCAS(e, kEmpty, kLocked);
             if (cur == kEmpty) {   // we own the slot: allocate the vertex, publish its key
                 const int id = atomicAdd(t.nr_filled, 1);
+                if (id >= t.max_vertices) atomicOr(t.status, 2);   // caller's row bound exceeded (static-shape mode)
 #pragma unroll
                 for (int i = 0; i < D; i++) t.keys[(size_t)id * D + i] = key[i];
                 __threadfence();
@@ -102,7 +104,7 @@ __device__ __forceinline__ int table_insert(const TableView& t, const int* key, 
         if (key_equal_at<D>(t.keys, cur, key)) return cur;
         h = (h + 1 == t.capacity) ? 0 : h + 1;   // linear probing
     }
-    atomicExch(t.status, 1);   // table full
+    atomicOr(t.status, 1);   // table full
     return -1;
 }
 

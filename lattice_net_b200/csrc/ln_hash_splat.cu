@@ -71,7 +71,7 @@ splat_build_kernel(const float* __restrict__ positions_raw, const float* __restr
             ConstTableView ct{table.keys, table.entries, table.capacity};
             id = table_find<D>(ct, key);
         }
-        ids[r] = id;
+        ids[r] = (id >= table.max_vertices) ? -1 : id;   // beyond the caller's row bound: dropped + flagged
     }
     if (!valid) return;
 
@@ -251,12 +251,16 @@ int ln_table_clear(int* entries, int* nr_filled, int* status, int capacity, void
     return check_launch("table_clear");
 }
 
+static inline int vertex_bound(int max_vertices, int capacity) {
+    return (max_vertices <= 0 || max_vertices > capacity) ? capacity : max_vertices;
+}
+
 int ln_splat_build(const float* positions_raw, const float* sigmas, int n, int pos_dim, int* keys, int* entries,
-                   int* nr_filled, int* status, int capacity, int* indices, float* weights, void* stream) {
+                   int* nr_filled, int* status, int capacity, int max_vertices, int* indices, float* weights, void* stream) {
     LN_REQUIRE(positions_raw && sigmas && keys && entries && nr_filled && status, "ln_splat_build: null pointer");
     LN_REQUIRE(n >= 0 && capacity > 0, "ln_splat_build: bad size n=%d capacity=%d", n, capacity);
     LN_REQUIRE((indices == nullptr) == (weights == nullptr), "ln_splat_build: indices and weights must both be given or both be NULL");
-    TableView t{keys, entries, nr_filled, status, capacity};
+    TableView t{keys, entries, nr_filled, status, capacity, vertex_bound(max_vertices, capacity)};
     switch (pos_dim) {
         case 3: return launch_splat_build<3>(positions_raw, sigmas, nullptr, n, 0, t, indices, weights, nullptr, true, (cudaStream_t)stream);
         case 5: return launch_splat_build<5>(positions_raw, sigmas, nullptr, n, 0, t, indices, weights, nullptr, true, (cudaStream_t)stream);
@@ -266,12 +270,12 @@ int ln_splat_build(const float* positions_raw, const float* sigmas, int n, int p
 }
 
 int ln_distribute(const float* positions_raw, const float* sigmas, const float* values, int n, int pos_dim, int val_dim,
-                  int* keys, int* entries, int* nr_filled, int* status, int capacity, int* indices, float* weights,
-                  float* distributed, void* stream) {
+                  int* keys, int* entries, int* nr_filled, int* status, int capacity, int max_vertices, int* indices,
+                  float* weights, float* distributed, void* stream) {
     LN_REQUIRE(positions_raw && sigmas && values && keys && entries && nr_filled && status && indices && weights && distributed,
                "ln_distribute: null pointer");
     LN_REQUIRE(n >= 0 && capacity > 0 && val_dim >= 1, "ln_distribute: bad size");
-    TableView t{keys, entries, nr_filled, status, capacity};
+    TableView t{keys, entries, nr_filled, status, capacity, vertex_bound(max_vertices, capacity)};
     switch (pos_dim) {
         case 3: return launch_splat_build<3>(positions_raw, sigmas, values, n, val_dim, t, indices, weights, distributed, true, (cudaStream_t)stream);
         case 5: return launch_splat_build<5>(positions_raw, sigmas, values, n, val_dim, t, indices, weights, distributed, true, (cudaStream_t)stream);
@@ -284,7 +288,7 @@ int ln_lookup_simplex(const float* positions_raw, const float* sigmas, int n, in
                       const int* entries, int capacity, int* indices, float* weights, void* stream) {
     LN_REQUIRE(positions_raw && sigmas && keys && entries && indices && weights, "ln_lookup_simplex: null pointer");
     LN_REQUIRE(n >= 0 && capacity > 0, "ln_lookup_simplex: bad size");
-    TableView t{const_cast<int*>(keys), const_cast<int*>(entries), nullptr, nullptr, capacity};
+    TableView t{const_cast<int*>(keys), const_cast<int*>(entries), nullptr, nullptr, capacity, capacity};
     switch (pos_dim) {
         case 3: return launch_splat_build<3>(positions_raw, sigmas, nullptr, n, 0, t, indices, weights, nullptr, false, (cudaStream_t)stream);
         case 5: return launch_splat_build<5>(positions_raw, sigmas, nullptr, n, 0, t, indices, weights, nullptr, false, (cudaStream_t)stream);
@@ -317,13 +321,14 @@ int ln_splat_accumulate(const float* values, const int* indices, const float* we
 
 int ln_coarsen_keys(const int* fine_keys, const int* fine_entries, const int* fine_nr_filled, int fine_capacity,
                     int* coarse_keys, int* coarse_entries, int* coarse_nr_filled, int* coarse_status, int coarse_capacity,
-                    int pos_dim, int nv_fine_upper, void* stream) {
+                    int coarse_max_vertices, int pos_dim, int nv_fine_upper, void* stream) {
     LN_REQUIRE(fine_keys && fine_entries && fine_nr_filled && coarse_keys && coarse_entries && coarse_nr_filled && coarse_status,
                "ln_coarsen_keys: null pointer");
     LN_REQUIRE(fine_capacity > 0 && coarse_capacity > 0 && nv_fine_upper >= 0, "ln_coarsen_keys: bad size");
     if (nv_fine_upper == 0) return LN_OK;
     ConstTableView fine{fine_keys, fine_entries, fine_capacity};
-    TableView coarse{coarse_keys, coarse_entries, coarse_nr_filled, coarse_status, coarse_capacity};
+    TableView coarse{coarse_keys, coarse_entries, coarse_nr_filled, coarse_status, coarse_capacity,
+                     vertex_bound(coarse_max_vertices, coarse_capacity)};
     cudaStream_t s = (cudaStream_t)stream;
     if (pos_dim == 3)
         coarsen_kernel<3><<<cdiv((long long)nv_fine_upper * 9, kBlock), kBlock, 0, s>>>(fine, fine_nr_filled, coarse, nv_fine_upper);

@@ -15,13 +15,18 @@ constexpr int kSkipped = -2;
 // One thread per (query vertex, slot).
 template <int D>
 __global__ void __launch_bounds__(kBlock)
-neighbour_table_kernel(const int* __restrict__ query_keys, int nv_query, ConstTableView nbr, int lvl_diff,
-                       int dilation, int* __restrict__ neighbours) {
+neighbour_table_kernel(const int* __restrict__ query_keys, int nv_query, const int* __restrict__ nv_query_dev,
+                       ConstTableView nbr, int nbr_max_vertices, int lvl_diff, int dilation, int* __restrict__ neighbours) {
     constexpr int F = 2 * (D + 1) + 1;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)nv_query * F) return;
     const int q = (int)(t / F);
     const int slot = (int)(t % F);
+    // static-shape mode: the table has nv_query (bound) rows, only the first *nv_query_dev are vertices
+    if (nv_query_dev != nullptr && q >= __ldg(nv_query_dev)) {
+        neighbours[t] = kSkipped;
+        return;
+    }
 
     // full (D+1)-coordinate key, scaled between levels (LatticeGPU.cuh:1479-1495)
     float kf[D + 1];
@@ -48,7 +53,7 @@ neighbour_table_kernel(const int* __restrict__ query_keys, int nv_query, ConstTa
 #pragma unroll
             for (int i = 0; i < D; i++) key[i] = (int)roundf(kf[i]);
             const int id = table_find<D>(nbr, key);
-            if (id >= 0) result = id;
+            if (id >= 0 && id < nbr_max_vertices) result = id;
         }
     } else {
         // fine query embedded in a coarser lattice: integer keys have no half-step neighbours
@@ -65,6 +70,7 @@ neighbour_table_kernel(const int* __restrict__ query_keys, int nv_query, ConstTa
                 key[i] = (int)roundf(c);
             }
             result = table_find<D>(nbr, key);   // -1 == kAbsent
+            if (result >= nbr_max_vertices) result = kAbsent;
         }
     }
     neighbours[t] = result;
@@ -148,18 +154,20 @@ using namespace ln;
 
 extern "C" {
 
-int ln_neighbour_table(const int* query_keys, int nv_query, int pos_dim, const int* nbr_keys, const int* nbr_entries,
-                       int nbr_capacity, int lvl_diff, int dilation, int* neighbours, void* stream) {
+int ln_neighbour_table(const int* query_keys, int nv_query, const int* nv_query_dev, int pos_dim, const int* nbr_keys,
+                       const int* nbr_entries, int nbr_capacity, int nbr_max_vertices, int lvl_diff, int dilation,
+                       int* neighbours, void* stream) {
     LN_REQUIRE(query_keys && nbr_keys && nbr_entries && neighbours, "ln_neighbour_table: null pointer");
     LN_REQUIRE(nv_query >= 0 && nbr_capacity > 0 && dilation >= 1, "ln_neighbour_table: bad size");
     LN_REQUIRE(lvl_diff >= -1 && lvl_diff <= 1, "ln_neighbour_table: query and neighbour lattices may differ by one level at most (got %d)", lvl_diff);
     if (nv_query == 0) return LN_OK;
     ConstTableView nbr{nbr_keys, nbr_entries, nbr_capacity};
+    if (nbr_max_vertices <= 0 || nbr_max_vertices > nbr_capacity) nbr_max_vertices = nbr_capacity;
     cudaStream_t s = (cudaStream_t)stream;
     if (pos_dim == 3)
-        neighbour_table_kernel<3><<<cdiv((long long)nv_query * 9, kBlock), kBlock, 0, s>>>(query_keys, nv_query, nbr, lvl_diff, dilation, neighbours);
+        neighbour_table_kernel<3><<<cdiv((long long)nv_query * 9, kBlock), kBlock, 0, s>>>(query_keys, nv_query, nv_query_dev, nbr, nbr_max_vertices, lvl_diff, dilation, neighbours);
     else if (pos_dim == 5)
-        neighbour_table_kernel<5><<<cdiv((long long)nv_query * 13, kBlock), kBlock, 0, s>>>(query_keys, nv_query, nbr, lvl_diff, dilation, neighbours);
+        neighbour_table_kernel<5><<<cdiv((long long)nv_query * 13, kBlock), kBlock, 0, s>>>(query_keys, nv_query, nv_query_dev, nbr, nbr_max_vertices, lvl_diff, dilation, neighbours);
     else {
         set_error("ln_neighbour_table: unsupported pos_dim %d", pos_dim);
         return LN_ERR_UNSUPPORTED;

@@ -33,10 +33,18 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 
 __global__ void __launch_bounds__(kGnThreads)
 group_norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      int nv, int c, int cpg, float eps, int relu, float* __restrict__ y, float* __restrict__ stats) {
+                      int nv_rows, const int* __restrict__ nv_dev, int c, int cpg, float eps, int relu,
+                      float* __restrict__ y, float* __restrict__ stats) {
     __shared__ float red[32];
     const int g = blockIdx.x;
     const int c0 = g * cpg;
+    // static-shape mode: the tensors have nv_rows rows, only the first *nv_dev are vertices; padding rows
+    // take no part in the statistics and come out as zeros
+    const int nv = nv_dev ? min(nv_rows, __ldg(nv_dev)) : nv_rows;
+    for (long long i = (long long)nv * cpg + threadIdx.x; i < (long long)nv_rows * cpg; i += blockDim.x) {
+        const long long v = i / cpg;
+        y[v * c + c0 + (int)(i - v * cpg)] = 0.0f;
+    }
     const long long m = (long long)nv * cpg;
     float s = 0.0f;
     for (long long i = threadIdx.x; i < m; i += blockDim.x) {
@@ -73,11 +81,17 @@ group_norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gam
 // dx = rstd * ( dy' gamma - (xhat * ds + db) / m ),  ds = sum dy' gamma xhat, db = sum dy' gamma  (over the group)
 __global__ void __launch_bounds__(kGnThreads)
 group_norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
-                      const float* __restrict__ gamma, const float* __restrict__ stats, int nv, int c, int cpg,
-                      int relu, float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                      const float* __restrict__ gamma, const float* __restrict__ stats, int nv_rows,
+                      const int* __restrict__ nv_dev, int c, int cpg, int relu, float* __restrict__ dx,
+                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
     __shared__ float red[32];
     const int g = blockIdx.x;
     const int c0 = g * cpg;
+    const int nv = nv_dev ? min(nv_rows, __ldg(nv_dev)) : nv_rows;
+    for (long long i = (long long)nv * cpg + threadIdx.x; i < (long long)nv_rows * cpg; i += blockDim.x) {
+        const long long v = i / cpg;
+        dx[v * c + c0 + (int)(i - v * cpg)] = 0.0f;
+    }
     const float mean = stats[2 * g], rstd = stats[2 * g + 1];
     const long long m = (long long)nv * cpg;
     float ds = 0.0f, db = 0.0f;
@@ -119,21 +133,21 @@ using namespace ln;
 
 extern "C" {
 
-int ln_group_norm_fwd(const float* x, const float* gamma, const float* beta, int nv, int c, int groups, float eps,
-                      int relu, float* y, float* stats, void* stream) {
+int ln_group_norm_fwd(const float* x, const float* gamma, const float* beta, int nv, const int* nv_dev, int c, int groups,
+                      float eps, int relu, float* y, float* stats, void* stream) {
     LN_REQUIRE(x && gamma && beta && y && stats, "ln_group_norm_fwd: null pointer");
     LN_REQUIRE(nv >= 1 && c >= 1 && groups >= 1 && c % groups == 0, "ln_group_norm_fwd: bad size nv=%d c=%d groups=%d", nv, c, groups);
-    group_norm_fwd_kernel<<<groups, kGnThreads, 0, (cudaStream_t)stream>>>(x, gamma, beta, nv, c, c / groups, eps, relu, y, stats);
+    group_norm_fwd_kernel<<<groups, kGnThreads, 0, (cudaStream_t)stream>>>(x, gamma, beta, nv, nv_dev, c, c / groups, eps, relu, y, stats);
     count_launch();
     return check_launch("group_norm_fwd");
 }
 
 int ln_group_norm_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* stats, int nv,
-                      int c, int groups, int relu, float* dx, float* dgamma, float* dbeta, void* stream) {
+                      const int* nv_dev, int c, int groups, int relu, float* dx, float* dgamma, float* dbeta, void* stream) {
     LN_REQUIRE(dy && x && gamma && stats && dx && dgamma && dbeta, "ln_group_norm_bwd: null pointer");
     LN_REQUIRE(!relu || y, "ln_group_norm_bwd: the forward output is needed for the ReLU mask");
     LN_REQUIRE(nv >= 1 && c >= 1 && groups >= 1 && c % groups == 0, "ln_group_norm_bwd: bad size");
-    group_norm_bwd_kernel<<<groups, kGnThreads, 0, (cudaStream_t)stream>>>(dy, x, y, gamma, stats, nv, c, c / groups, relu, dx, dgamma, dbeta);
+    group_norm_bwd_kernel<<<groups, kGnThreads, 0, (cudaStream_t)stream>>>(dy, x, y, gamma, stats, nv, nv_dev, c, c / groups, relu, dx, dgamma, dbeta);
     count_launch();
     return check_launch("group_norm_bwd");
 }

@@ -1,0 +1,166 @@
+"""Whole-step CUDA-graph execution of LatticeNet training (B200-first: the ShapeNet-sized step is
+launch-bound -- ~550 kernels of a few microseconds each -- so the host, not the GPU, sets the pace of
+the reference's loop, /root/reference/latticenet_py/ln_train.py:141-189).
+
+A lattice is rebuilt for every cloud and its vertex count differs from cloud to cloud, which is what
+normally rules out graph capture.  Here the lattice runs in *static-shape mode*
+(`Lattice.set_vertex_bounds`): every level allocates a fixed number of rows, the actual vertex count
+stays on the device (`nr_filled`), the kernels that need it (neighbour table, GroupNorm statistics)
+read it there, and rows past it carry zeros / receive zero gradients.  Forward, backward, gradient
+bucket and optimizer then replay as ONE graph launch per cloud.
+
+A cloud whose lattice needs more vertices than a bound is detected on the device: the step's
+optimizer update is skipped in-graph (fused AdamW `found_inf`), the event is counted, and the caller can
+re-run that cloud through the ordinary (dynamic-shape) path.
+"""
+import torch
+import torch.distributed as dist
+
+from .lattice import Lattice
+
+
+def estimate_vertex_bounds(capacity, sigmas, clouds, nr_levels, headroom=1.3, multiple=128):
+    """Rows to reserve per lattice level: max vertex count over sample `clouds` (device tensors [N x d]),
+    times `headroom`, rounded up to a multiple of `multiple` (128 = the M tile of the convolution kernel).
+    Level l+1 is built like the model builds it: the raw points splatted at twice the sigma
+    (Lattice::create_coarse_verts_naive, /root/reference/src/Lattice.cu:706-740)."""
+    maxima = [0] * nr_levels
+    for pos in clouds:
+        lat = Lattice(capacity, sigmas)
+        lat.begin_splat()
+        lat.just_create_verts(pos, False)
+        for lvl in range(nr_levels):
+            maxima[lvl] = max(maxima[lvl], lat.nr_lattice_vertices())
+            if lvl + 1 < nr_levels:
+                lat = lat.create_coarse_verts_naive(pos)
+    return [min(capacity, -(-int(m * headroom + 1) // multiple) * multiple) for m in maxima]
+
+
+class GraphedTrainStep:
+    """forward + loss + backward (+ gradient all-reduce) + optimizer step, captured once, replayed per cloud.
+
+        step = GraphedTrainStep(model, lattice, optimizer, loss_fn, nr_points, val_dim, bounds, bucket, world)
+        loss = step(positions, values, labels)          # device tensors or pinned host tensors
+
+    `optimizer` must be created with capturable=True (fused AdamW supports it).  `bucket` is the
+    parallel.GradBucket of the model (its flat buffer is what gets all-reduced when world > 1).
+    """
+
+    def __init__(self, model, lattice, optimizer, loss_fn, nr_points, pos_dim, val_dim, bounds, bucket, world=1,
+                 warmup=3, capture_collective=False, example=None):
+        self.model, self.lattice, self.optimizer, self.loss_fn = model, lattice, optimizer, loss_fn
+        self.bucket, self.world = bucket, world
+        dev = bucket.flat.device
+        self.device = dev
+        lattice.set_vertex_bounds(bounds)
+        self.bounds = list(bounds)
+        self.pos = torch.zeros((nr_points, pos_dim), dtype=torch.float32, device=dev)
+        self.vals = torch.zeros((nr_points, val_dim), dtype=torch.float32, device=dev)
+        self.labels = torch.zeros((nr_points,), dtype=torch.int64, device=dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.found_inf = torch.zeros((), dtype=torch.float32, device=dev)      # 1.0 = a bound was exceeded: skip the update
+        self.overflow_steps = torch.zeros((), dtype=torch.float32, device=dev)  # running count of such steps
+        self.nv_actual = torch.zeros((len(self.bounds),), dtype=torch.int32, device=dev)
+        if example is not None:                 # a representative cloud for the warm-up / capture passes
+            self.pos.copy_(example[0])
+            self.vals.copy_(example[1])
+            self.labels.copy_(example[2])
+        optimizer.found_inf = self.found_inf
+        self.capture_collective = capture_collective and world > 1
+        self.graphs = []
+        self.launches_per_step = 0
+        self._capture(warmup)
+
+    # -- the three phases of a step; `_allreduce` is the only part that may have to stay outside a graph
+    def _forward_backward(self):
+        logsoftmax, _ = self.model(self.lattice, self.pos, self.vals)
+        loss = self.loss_fn(logsoftmax, self.labels)
+        self.bucket.zero()
+        loss.backward()
+        self.loss.copy_(loss.detach())
+        levels = self.model.last_level_lattices
+        flags = torch.stack([l.m_hash_table.structure.status[0] for l in levels]).max()
+        self.nv_actual.copy_(torch.cat([l.m_hash_table.structure.nr_filled for l in levels]))
+        self.found_inf.copy_((flags > 0).to(torch.float32))
+        if self.world > 1:
+            self.bucket.pack(extra=self.found_inf)
+
+    def _allreduce(self):
+        if self.world > 1:
+            dist.all_reduce(self.bucket.flat_with_extra, op=dist.ReduceOp.SUM)
+
+    def _update(self):
+        if self.world > 1:
+            self.bucket.flat.mul_(1.0 / self.world)
+            self.found_inf.copy_((self.bucket.extra > 0).to(torch.float32).reshape(()))   # any rank overflowed -> all skip
+        self.overflow_steps.add_(self.found_inf)
+        self.optimizer.step()
+
+    def _eager_step(self):
+        self._forward_backward()
+        self._allreduce()
+        self._update()
+
+    def _snapshot(self):
+        params = [p for g in self.optimizer.param_groups for p in g["params"]]
+        saved = []
+        for p in params:
+            st = self.optimizer.state.get(p, None)
+            saved.append((p, p.detach().clone(), None if not st else {k: v.clone() for k, v in st.items() if torch.is_tensor(v)}))
+        return saved
+
+    def _restore(self, saved):
+        # in place: the graph has captured the addresses of the parameters and of the optimizer state
+        with torch.no_grad():
+            for p, value, st in saved:
+                p.copy_(value)
+                for k, v in self.optimizer.state.get(p, {}).items():
+                    if torch.is_tensor(v):
+                        v.copy_(st[k]) if st is not None else v.zero_()
+
+    def _capture(self, warmup):
+        from . import _cabi
+        saved = self._snapshot()                # the warm-up passes are real optimizer steps: undo them afterwards
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):     # lazy initialisations (cuBLAS handles, workspaces, optimizer state)
+                self._eager_step()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.overflow_steps.zero_()
+        _cabi.reset_launch_count()
+        if self.world == 1 or self.capture_collective:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._eager_step()
+            self.graphs = [g]
+            self._between = None
+        else:
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                self._forward_backward()
+            with torch.cuda.graph(gb, pool=ga.pool()):
+                self._update()
+            self.graphs = [ga, gb]
+            self._between = self._allreduce
+        self.launches_per_step = _cabi.launch_count()      # kernels of this library inside one replay
+        self._restore(saved)
+        self.overflow_steps.zero_()
+
+    def __call__(self, positions, values, labels):
+        self.pos.copy_(positions, non_blocking=True)
+        self.vals.copy_(values, non_blocking=True)
+        self.labels.copy_(labels, non_blocking=True)
+        self.graphs[0].replay()
+        if self._between is not None:
+            self._between()
+            self.graphs[1].replay()
+        return self.loss
+
+    def overflowed_steps(self):
+        """Number of replayed steps whose cloud exceeded a vertex bound (blocking read)."""
+        return int(self.overflow_steps.item())
+
+    def last_vertex_counts(self):
+        return [int(v) for v in self.nv_actual.tolist()]

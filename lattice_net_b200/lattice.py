@@ -37,6 +37,7 @@ def set_conv_precision(mode):
 
 
 _workspaces = {}
+_SIGMA_CACHE = {}
 
 
 def _workspace(nbytes, device):
@@ -69,10 +70,13 @@ class _Structure:
     Shared by every handle that aliases the same vertices (the reference shares the tensors between
     clones, Lattice.cu:89-95)."""
 
-    def __init__(self, capacity, pos_dim, device, zero_keys=True):
+    def __init__(self, capacity, pos_dim, device, zero_keys=True, bound=None):
         self.capacity = int(capacity)
         self.pos_dim = int(pos_dim)
         self.device = device
+        # static-shape mode: every per-vertex tensor of this level has exactly `bound` rows and the actual
+        # vertex count stays on the device (nr_filled); nothing below ever syncs with the host
+        self.bound = None if bound is None else min(int(bound), self.capacity)
         alloc = torch.zeros if zero_keys else torch.empty
         self.keys = alloc((self.capacity, self.pos_dim), dtype=torch.int32, device=device)
         self.entries = torch.empty((self.capacity,), dtype=torch.int32, device=device)
@@ -88,8 +92,16 @@ class _Structure:
         self.mark_dirty()
 
     def mark_dirty(self):
-        self.nv = None
+        self.nv = self.bound          # None = unknown until read back; a bound is known without asking the device
         self.neighbour_cache.clear()
+
+    def nr_vertices_actual(self):
+        """Blocking read of the device-side vertex count (raises on table overflow / exceeded bound)."""
+        nv = ctypes.c_int(0)
+        probe = ctypes.c_int(0)
+        call("ln_table_status", ptr(self.nr_filled), ptr(self.status), ctypes.byref(nv), ctypes.byref(probe), stream_ptr(self.device))
+        self.max_probe = int(probe.value)
+        return int(nv.value)
 
     def nr_vertices(self):
         if self.nv is None:
@@ -102,7 +114,7 @@ class _Structure:
 
     def copy(self):
         other = _Structure.__new__(_Structure)
-        other.capacity, other.pos_dim, other.device = self.capacity, self.pos_dim, self.device
+        other.capacity, other.pos_dim, other.device, other.bound = self.capacity, self.pos_dim, self.device, self.bound
         other.keys = self.keys.clone()
         other.entries = self.entries.clone()
         other.nr_filled = self.nr_filled.clone()
@@ -170,6 +182,7 @@ class Lattice:
         self.m_sigmas = []
         self.m_sigmas_val_and_extent = []
         self._sigmas_dev = {}
+        self.m_vertex_bounds = None          # static-shape mode: {level: rows}; see set_vertex_bounds
         if _clone_of is not None:
             return
         _check(capacity is not None and sigmas is not None, "Lattice needs a capacity and sigmas (or use Lattice.create(cfg))")
@@ -193,10 +206,35 @@ class Lattice:
         other.m_sigmas = list(self.m_sigmas)
         other.m_sigmas_val_and_extent = list(self.m_sigmas_val_and_extent)
         other.m_positions = self.m_positions
+        other.m_vertex_bounds = self.m_vertex_bounds
         other.m_hash_table = HashTable(self.m_hash_table.m_capacity)
         other.m_hash_table.structure = self.m_hash_table.structure
         other.m_hash_table.m_values_tensor = self.m_hash_table.m_values_tensor
         return other
+
+    def set_vertex_bounds(self, bounds):
+        """Static-shape mode (extension of the reference API; used for CUDA-graph capture of a whole step).
+        `bounds` = rows per lattice level, a list [lvl1, lvl2, ...] or {lvl: rows}; None switches it off.
+        Lattices built from this handle (distribute / splat / coarse levels) then allocate exactly that many
+        rows, `nr_lattice_vertices()` returns the bound without a device sync, rows past the actual vertex count
+        carry zeros through the network, and a cloud that needs more vertices than the bound is flagged in the
+        structure's status word (its surplus vertices are dropped) instead of re-allocating."""
+        if bounds is None:
+            self.m_vertex_bounds = None
+        elif isinstance(bounds, dict):
+            self.m_vertex_bounds = {int(k): int(v) for k, v in bounds.items()}
+        else:
+            self.m_vertex_bounds = {i + 1: int(b) for i, b in enumerate(bounds)}
+
+    def _bound_for(self, lvl):
+        if self.m_vertex_bounds is None:
+            return None
+        _check(lvl in self.m_vertex_bounds, f"static-shape mode: no vertex bound was given for lattice level {lvl}")
+        return self.m_vertex_bounds[lvl]
+
+    def nr_lattice_vertices_actual(self):
+        """Device-side vertex count (blocking); equals nr_lattice_vertices() outside static-shape mode."""
+        return self._structure().nr_vertices_actual()
 
     def set_sigmas(self, sigmas_list):
         # Lattice::set_sigmas, Lattice.cu:134-160
@@ -279,10 +317,13 @@ class Lattice:
         return st.device if st is not None else torch.device("cuda", torch.cuda.current_device())
 
     def _sigmas_on(self, device):
-        key = str(device)
-        if key not in self._sigmas_dev:
-            self._sigmas_dev[key] = torch.tensor(self.m_sigmas, dtype=torch.float32, device=device)
-        return self._sigmas_dev[key]
+        # process-wide cache: coarse handles are re-created every scan, and an H2D copy per level would both
+        # cost a launch and be illegal inside a CUDA-graph capture
+        key = (str(device), tuple(self.m_sigmas))
+        t = _SIGMA_CACHE.get(key)
+        if t is None:
+            t = _SIGMA_CACHE[key] = torch.tensor(self.m_sigmas, dtype=torch.float32, device=device)
+        return t
 
     def _check_positions(self, positions_raw):
         # Lattice::check_positions, Lattice.cu:162-170
@@ -318,7 +359,8 @@ class Lattice:
         n.nr_vertices()   # surfaces a table overflow of the neighbour lattice before it is read
         F = 2 * (q.pos_dim + 1) + 1
         table = torch.empty((nv, F), dtype=torch.int32, device=q.device)
-        call("ln_neighbour_table", ptr(q.keys), nv, q.pos_dim, ptr(n.keys), ptr(n.entries), n.capacity,
+        call("ln_neighbour_table", ptr(q.keys), nv, ptr(q.nr_filled) if q.bound is not None else None, q.pos_dim,
+             ptr(n.keys), ptr(n.entries), n.capacity, n.bound or 0,
              self.m_lvl - lattice_neighbours.m_lvl, int(dilation), ptr(table), stream_ptr(q.device))
         q.neighbour_cache[key] = (weakref.ref(n), table)
         return table
@@ -349,6 +391,7 @@ class Lattice:
         if not ht.is_initialized():
             ht.init(d, v, device)
         st = ht.structure
+        st.bound = self._bound_for(self.m_lvl)
         pos = _as_cuda_f32(positions_raw, st.device)
         val = _as_cuda_f32(values, st.device)
         if ht.m_values_tensor is None or tuple(ht.m_values_tensor.shape) != (ht.m_capacity, v):
@@ -358,7 +401,7 @@ class Lattice:
         s = stream_ptr(st.device)
         if n > 0:
             call("ln_splat_build", ptr(pos), ptr(self._sigmas_on(st.device)), n, d, ptr(st.keys), ptr(st.entries),
-                 ptr(st.nr_filled), ptr(st.status), st.capacity, ptr(idx), ptr(w), s)
+                 ptr(st.nr_filled), ptr(st.status), st.capacity, st.bound or 0, ptr(idx), ptr(w), s)
             call("ln_splat_accumulate", ptr(val), ptr(idx), ptr(w), n, d, v, ptr(ht.m_values_tensor), s)
         st.mark_dirty()
         return idx, w
@@ -371,6 +414,7 @@ class Lattice:
         if not ht.is_initialized():
             ht.init(d, 1, device)
         st = ht.structure
+        st.bound = self._bound_for(self.m_lvl)
         pos = _as_cuda_f32(positions_raw, st.device)
         idx = w = None
         if return_indices_and_weights:
@@ -378,7 +422,7 @@ class Lattice:
             w = torch.empty((n * (d + 1),), dtype=torch.float32, device=st.device)
         if n > 0:
             call("ln_splat_build", ptr(pos), ptr(self._sigmas_on(st.device)), n, d, ptr(st.keys), ptr(st.entries),
-                 ptr(st.nr_filled), ptr(st.status), st.capacity, ptr(idx), ptr(w), stream_ptr(st.device))
+                 ptr(st.nr_filled), ptr(st.status), st.capacity, st.bound or 0, ptr(idx), ptr(w), stream_ptr(st.device))
         st.mark_dirty()
         return idx, w
 
@@ -401,8 +445,17 @@ class Lattice:
         new = self.clone_lattice()
         new.m_name = "distributed_lattice"
         # the reference clones the parent's table and clears it (Lattice.cu:377-390); a fresh table is the same thing
-        new.m_hash_table.structure = _Structure(parent.capacity, d, dev) if reset_hashmap else parent.copy()
-        if ht.m_values_tensor is not None and ht.m_values_tensor.shape[1] == v:
+        bound = self._bound_for(self.m_lvl)
+        if reset_hashmap:
+            new.m_hash_table.structure = _Structure(parent.capacity, d, dev, zero_keys=bound is None, bound=bound)
+        else:
+            new.m_hash_table.structure = parent.copy()
+            new.m_hash_table.structure.bound = bound
+        if bound is not None:
+            # static-shape mode: the [capacity x V] placeholder of the reference is never read by the network
+            # (PointNet replaces the values); a one-row stand-in avoids a capacity-sized clear per scan
+            new.m_hash_table.m_values_tensor = torch.zeros((1, v), dtype=torch.float32, device=dev)
+        elif ht.m_values_tensor is not None and ht.m_values_tensor.shape[1] == v:
             new.m_hash_table.m_values_tensor = torch.zeros_like(ht.m_values_tensor)
         else:
             new.m_hash_table.m_values_tensor = torch.zeros((ht.m_capacity, v), dtype=torch.float32, device=dev)
@@ -412,7 +465,7 @@ class Lattice:
         w = torch.empty((n * (d + 1),), dtype=torch.float32, device=dev)
         if n > 0:
             call("ln_distribute", ptr(pos), ptr(self._sigmas_on(dev)), ptr(val), n, d, v, ptr(st.keys), ptr(st.entries),
-                 ptr(st.nr_filled), ptr(st.status), st.capacity, ptr(idx), ptr(w), ptr(distributed), stream_ptr(dev))
+                 ptr(st.nr_filled), ptr(st.status), st.capacity, st.bound or 0, ptr(idx), ptr(w), ptr(distributed), stream_ptr(dev))
         st.mark_dirty()
         return new, distributed, idx, w
 
@@ -449,7 +502,8 @@ class Lattice:
         coarse.m_sigmas_val_and_extent = [(s * 2.0, n) for s, n in self.m_sigmas_val_and_extent]
         coarse._sigmas_dev = {}
         coarse.m_hash_table = HashTable(st.capacity)
-        coarse.m_hash_table.structure = _Structure(st.capacity, st.pos_dim, st.device)
+        bound = coarse._bound_for(coarse.m_lvl)
+        coarse.m_hash_table.structure = _Structure(st.capacity, st.pos_dim, st.device, zero_keys=bound is None, bound=bound)
         coarse.m_hash_table.m_values_tensor = torch.zeros((1, self.val_dim()), dtype=torch.float32, device=st.device)
         return coarse
 
@@ -460,7 +514,8 @@ class Lattice:
         coarse = self._new_coarse_handle()
         cst = coarse.m_hash_table.structure
         call("ln_coarsen_keys", ptr(st.keys), ptr(st.entries), ptr(st.nr_filled), st.capacity, ptr(cst.keys),
-             ptr(cst.entries), ptr(cst.nr_filled), ptr(cst.status), cst.capacity, st.pos_dim, nv, stream_ptr(st.device))
+             ptr(cst.entries), ptr(cst.nr_filled), ptr(cst.status), cst.capacity, cst.bound or 0, st.pos_dim, nv,
+             stream_ptr(st.device))
         cst.mark_dirty()
         coarse.m_hash_table.m_values_tensor = torch.zeros((coarse.nr_lattice_vertices(), self.val_dim()), dtype=torch.float32, device=st.device)
         return coarse

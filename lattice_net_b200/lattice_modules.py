@@ -72,15 +72,16 @@ class _GroupNormReLU(torch.autograd.Function):
     """GroupNorm (+ReLU) on vertex-major values [nv x C] in one kernel each way (ln_group_norm_fwd/bwd)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, groups, eps, relu):
+    def forward(ctx, x, gamma, beta, groups, eps, relu, nv_dev=None):
+        # nv_dev: device int32[1] with the actual vertex count when x is padded to a row bound (static-shape mode)
         x = x.contiguous()
         nv, c = x.shape
         y = torch.empty_like(x)
         stats = torch.empty((groups, 2), dtype=torch.float32, device=x.device)
-        call("ln_group_norm_fwd", ptr(x), ptr(gamma.contiguous()), ptr(beta.contiguous()), nv, c, groups, float(eps),
+        call("ln_group_norm_fwd", ptr(x), ptr(gamma.contiguous()), ptr(beta.contiguous()), nv, ptr(nv_dev), c, groups, float(eps),
              1 if relu else 0, ptr(y), ptr(stats), stream_ptr(x.device))
         ctx.save_for_backward(x, y, gamma, stats)
-        ctx.groups, ctx.relu = groups, relu
+        ctx.groups, ctx.relu, ctx.nv_dev = groups, relu, nv_dev
         return y
 
     @staticmethod
@@ -90,9 +91,9 @@ class _GroupNormReLU(torch.autograd.Function):
         dx = torch.empty_like(x)
         dgamma = torch.empty_like(gamma)
         dbeta = torch.empty_like(gamma)
-        call("ln_group_norm_bwd", ptr(dy.contiguous()), ptr(x), ptr(y), ptr(gamma.contiguous()), ptr(stats), nv, c, ctx.groups,
-             1 if ctx.relu else 0, ptr(dx), ptr(dgamma), ptr(dbeta), stream_ptr(x.device))
-        return dx, dgamma, dbeta, None, None, None
+        call("ln_group_norm_bwd", ptr(dy.contiguous()), ptr(x), ptr(y), ptr(gamma.contiguous()), ptr(stats), nv, ptr(ctx.nv_dev), c,
+             ctx.groups, 1 if ctx.relu else 0, ptr(dx), ptr(dgamma), ptr(dbeta), stream_ptr(x.device))
+        return dx, dgamma, dbeta, None, None, None, None
 
 
 # one CTA per group: meant for the lattice sizes where launch count, not bandwidth, is the cost
@@ -367,8 +368,10 @@ class GroupNormLatticeModule(torch.nn.Module):
         # statistics run over (channels of a group) x (all vertices): vertices are the "length" axis
         gn = self.gn
         nv, c = lattice_values.shape
-        if lattice_values.is_cuda and nv * (c // gn.num_groups) <= FUSED_NORM_MAX_ELEMS_PER_GROUP:
-            lv = _GroupNormReLU.apply(lattice_values, gn.weight, gn.bias, gn.num_groups, gn.eps, relu)
+        st = lattice_py.m_hash_table.structure
+        nv_dev = st.nr_filled if (st is not None and st.bound is not None) else None
+        if lattice_values.is_cuda and (nv_dev is not None or nv * (c // gn.num_groups) <= FUSED_NORM_MAX_ELEMS_PER_GROUP):
+            lv = _GroupNormReLU.apply(lattice_values, gn.weight, gn.bias, gn.num_groups, gn.eps, relu, nv_dev)
         else:
             lv = gn(lattice_values.t().unsqueeze(0)).squeeze(0).t()
             if relu:

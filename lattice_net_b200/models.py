@@ -85,6 +85,7 @@ class LNN(torch.nn.Module):
         with torch.no_grad():
             ls, distributed, indices, weights = self.distribute(ls, positions, values)
         self.last_level1_lattice = ls          # kept for inspection / tests (vertex numbering of this pass)
+        self.last_level_lattices = [ls]        # one handle per lattice level of this pass (level 1 first)
         lv, ls = self.point_net(ls, distributed, indices)
 
         fine_structures, fine_values = [], []
@@ -94,6 +95,7 @@ class LNN(torch.nn.Module):
             fine_structures.append(ls)
             fine_values.append(lv)
             lv, ls = self.coarsens_list[lvl](lv, ls)
+            self.last_level_lattices.append(ls)
 
         for block in self.resnet_blocks_bottleneck:
             lv, ls = block(lv, ls)

@@ -51,7 +51,11 @@ class GradBucket:
         assert self.params, "no trainable parameters (run a warm-up forward first: they are created lazily)"
         dev = self.params[0].device
         total = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        # one extra trailing element rides along with the gradients in the same collective (a per-step flag,
+        # e.g. "this rank's cloud exceeded its vertex bound", graphed.py)
+        self.flat_with_extra = torch.zeros(total + 1, dtype=torch.float32, device=dev)
+        self.flat = self.flat_with_extra[:total]
+        self.extra = self.flat_with_extra[total:]
         self.views = []
         off = 0
         for p in self.params:
@@ -65,12 +69,14 @@ class GradBucket:
         for p in self.params:
             p.grad = None
 
-    def pack(self):
+    def pack(self, extra=None):
         """Call after backward: flat <- all grads (one fused copy), .grad <- views of flat."""
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
         torch._foreach_copy_(self.views, grads)
         for p, v in zip(self.params, self.views):
             p.grad = v
+        if extra is not None:
+            self.extra.copy_(extra.reshape(1))
 
     def allreduce_mean(self, world):
         """One collective for the whole model; averages over ranks.  Single process: nothing to do."""

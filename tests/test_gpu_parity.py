@@ -512,3 +512,139 @@ def test_conv_transposed_filter_equals_relayout(built, precision):
         lattice_mod.set_conv_precision(0)
     assert tuple(a.shape) == (b["nv"], Cin)
     assert_close(a.cpu().numpy(), c.cpu().numpy(), 1e-6, "transposed-filter dgrad")
+
+
+# --------------------------------------------------------------------------------------------------
+# static-shape mode (fixed rows per level, vertex count on the device) and the CUDA-graph step
+def test_static_shape_lattice_matches_dynamic(built):
+    """Same cloud through a row-bounded lattice: structure identical, padding rows inert."""
+    from lattice_net_b200 import Lattice
+    b = built
+    nv, d = b["nv"], b["d"]
+    bound = -(-int(nv * 1.3) // 128) * 128
+    lat = _lattice(b["spec"])
+    lat.set_vertex_bounds([bound])
+    lat.begin_splat()
+    idx, w = lat.splat_standalone(b["pos"], cuda(b["vals_np"]))
+    assert lat.nr_lattice_vertices() == bound                 # no device sync: the bound
+    assert lat.nr_lattice_vertices_actual() == nv
+    ks, o2n, n2o = canonical(lat.hash_table().m_keys_tensor[:nv].cpu().numpy())
+    assert np.array_equal(ks, b["cpu"]["keys"])
+    assert np.array_equal(lo.relabel(idx.cpu().numpy(), o2n), b["cpu"]["indices"])
+    assert bits_equal(w.cpu().numpy(), b["cpu"]["weights"]) == 0
+    # convolution over the bounded table: rows < nv equal the oracle, rows >= nv are exactly zero
+    F = 2 * (d + 1) + 1
+    Cin, Cout = 32, 32
+    lv = cases.randn((nv, Cin), 21)
+    lv_gpu = np.zeros((bound, Cin), np.float32)
+    lv_gpu[n2o_rows(o2n, nv)] = lv                         # canonical row c lives at GPU row n2o[c]
+    fb = (cases.randn((F * Cin, Cout), 22) * 0.1).astype(np.float32)
+    l2 = lat.clone_lattice()
+    l2.set_values(cuda(lv_gpu))
+    out = l2.convolve_im2row_standalone(cuda(fb), 1, l2, False).values().cpu().numpy()
+    assert out.shape == (bound, Cout)
+    table = lo.neighbour_table(b["cpu"]["keys"], b["cpu"]["keys"])
+    assert_close(out[n2o_rows(o2n, nv)], lo.conv_fwd(lv, table, fb), TOL_VALUES, "static-shape conv")
+    assert not out[nv:].any()
+
+
+def n2o_rows(o2n, nv):
+    """GPU row of each canonical vertex (inverse of old_to_new when there are no duplicate keys)."""
+    inv = np.empty(nv, np.int64)
+    inv[o2n[:nv]] = np.arange(nv)
+    return inv
+
+
+def test_static_shape_bound_exceeded_is_flagged():
+    from lattice_net_b200 import Lattice
+    from lattice_net_b200._cabi import LatticeBackendError
+    pos = cuda(cases.box_surface(2048, 0))
+    lat = Lattice(60000, [(0.05, 3)])
+    lat.set_vertex_bounds([128])
+    lat.begin_splat()
+    idx, w = lat.splat_standalone(pos, torch.zeros((2048, 1), device="cuda"))
+    i = idx.cpu().numpy()
+    assert i.max() < 128 and (i == -1).any()
+    assert np.array_equal(w.cpu().numpy()[i < 0], np.full((i < 0).sum(), -1.0, np.float32))
+    with pytest.raises(LatticeBackendError, match="max_vertices"):
+        lat.nr_lattice_vertices_actual()
+
+
+@pytest.mark.parametrize("relu", [False, True])
+def test_group_norm_ignores_padding_rows(relu):
+    from lattice_net_b200.lattice_modules import _GroupNormReLU
+    torch.manual_seed(5)
+    nv, rows, C, groups = 700, 1024, 64, 32
+    x = torch.randn((rows, C), device="cuda") * 3 + 1          # padding rows hold garbage on purpose
+    g = torch.randn((rows, C), device="cuda")
+    g[nv:] = 0                                                   # upstream gradients of padding rows are zero
+    gamma, beta = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+    nv_dev = torch.tensor([nv], dtype=torch.int32, device="cuda")
+    xa = x[:nv].clone().requires_grad_(True)
+    pa = (gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True))
+    ya = torch.nn.functional.group_norm(xa.t().unsqueeze(0), groups, pa[0], pa[1], 1e-5).squeeze(0).t()
+    ya = torch.relu(ya) if relu else ya
+    ya.backward(g[:nv])
+    xb = x.clone().requires_grad_(True)
+    pb = (gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True))
+    yb = _GroupNormReLU.apply(xb, pb[0], pb[1], groups, 1e-5, relu, nv_dev)
+    yb.backward(g)
+    assert_close(yb[:nv].detach().cpu().numpy(), ya.detach().cpu().numpy(), 1e-5, "padded group norm forward")
+    assert not yb[nv:].detach().cpu().numpy().any() and not xb.grad[nv:].cpu().numpy().any()
+    assert_close(xb.grad[:nv].cpu().numpy(), xa.grad.cpu().numpy(), 1e-4, "padded group norm dx")
+    assert_close(pb[0].grad.cpu().numpy(), pa[0].grad.cpu().numpy(), 1e-4, "padded group norm dgamma")
+    assert_close(pb[1].grad.cpu().numpy(), pa[1].grad.cpu().numpy(), 1e-4, "padded group norm dbeta")
+
+
+def test_graphed_step_matches_eager_step():
+    """One CUDA-graph replay of the whole training step (static-shape lattice) == the eager dynamic-shape step:
+    same loss, same parameter gradients, vertex counts reported from the device."""
+    import copy
+    from lattice_net_b200 import Lattice, ModelParams
+    from lattice_net_b200.graphed import GraphedTrainStep, estimate_vertex_bounds
+    from lattice_net_b200.losses import segmentation_loss
+    from lattice_net_b200.models import LNN
+    from lattice_net_b200.parallel import GradBucket
+    torch.manual_seed(1)
+    dev = torch.device("cuda", 0)
+    clouds = [(cuda(cases.box_surface(2048, s)), torch.zeros((2048, 1), device=dev),
+               cuda(np.random.RandomState(s).randint(0, 7, 2048))) for s in (0, 1, 2)]
+    lat_a = Lattice(60000, [(0.05, 3)])
+    model_a = LNN(7, ModelParams(), device=dev)
+    with torch.no_grad():
+        model_a(lat_a, *clouds[0][:2])                      # creates the lazy parameters
+    model_b = copy.deepcopy(model_a)
+    lat_b = Lattice(60000, [(0.05, 3)])
+    opt_b = torch.optim.AdamW(model_b.parameters(), lr=1e-3, weight_decay=3e-4, amsgrad=True, fused=True, capturable=True)
+    bucket_b = GradBucket(model_b.parameters())
+    bounds = estimate_vertex_bounds(60000, [(0.05, 3)], [c[0] for c in clouds], 4)
+    step = GraphedTrainStep(model_b, lat_b, opt_b, segmentation_loss, 2048, 3, 1, bounds, bucket_b, example=clouds[0])
+    # the capture's warm-up passes must leave parameters untouched
+    for (na, pa), (nb, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
+        assert torch.equal(pa, pb), f"{na} changed during graph capture"
+    for pos, vals, labels in clouds[1:]:
+        logsm, _ = model_a(lat_a, pos, vals)
+        loss_a = segmentation_loss(logsm, labels)
+        for p in model_a.parameters():
+            p.grad = None
+        loss_a.backward()
+        before = [p.detach().clone() for p in model_b.parameters()]
+        loss_b = step(pos, vals, labels)
+        torch.cuda.synchronize()
+        nv_levels = [l.nr_lattice_vertices() for l in model_a.last_level_lattices]
+        assert step.last_vertex_counts() == nv_levels
+        assert all(n <= b for n, b in zip(nv_levels, bounds))
+        assert abs(loss_a.item() - loss_b.item()) <= 2e-3 * abs(loss_a.item())
+        checked = 0
+        for (name, pa), pb in zip(model_a.named_parameters(), model_b.parameters()):
+            if pa.grad is None:
+                continue
+            assert_close(pb.grad.cpu().numpy(), pa.grad.cpu().numpy(), 2e-2, f"graphed gradient of {name}")
+            checked += 1
+        assert checked > 100
+        assert any(not torch.equal(x, p.detach()) for x, p in zip(before, model_b.parameters())), "optimizer step did not run"
+        # keep the two models in lock step for the next cloud
+        with torch.no_grad():
+            for pa, pb in zip(model_a.parameters(), model_b.parameters()):
+                pa.copy_(pb)
+    assert step.overflowed_steps() == 0
