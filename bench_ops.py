@@ -176,7 +176,12 @@ def run(n, d, vals, quick):
                 rs = timeit(lambda: ref.convolve(fb, ref, lvr, 1, False), reps=3)
                 emit("conv_fwd reference (im2row kernel + fp32 mm)", dict(cfg, c_out=V), rs, nbytes=cbytes, flops=flops)
             gout = torch.randn((nv, V), device=dev)
-            emit("conv_wgrad fp32 SIMT", dict(cfg, c_out=V), timeit(lambda: lat2.conv_weight_grad(lat2, gout, F, 1), reps=5), flops=flops)
+            for prec, name in ((0, "conv_wgrad fp32 SIMT"), (1, "conv_wgrad tcgen05 3xTF32"), (2, "conv_wgrad tcgen05 TF32")):
+                lm.set_conv_precision(prec)
+                try:
+                    emit(name, dict(cfg, c_out=V), timeit(lambda: lat2.conv_weight_grad(lat2, gout, F, 1), reps=5), flops=flops)
+                finally:
+                    lm.set_conv_precision(0)
             del fb, gout
         del lat2, lvr
     # neighbour table
@@ -194,9 +199,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, nargs="*", default=[100000, 1000000])
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--vals", type=int, nargs="*", default=None)
     args = ap.parse_args()
     for n in args.n:
-        run(n, 3, [8, 32, 64] if args.quick else [1, 8, 32, 64, 128], args.quick)
+        run(n, 3, args.vals if args.vals else ([8, 32, 64] if args.quick else [1, 8, 32, 64, 128]), args.quick)
     if not args.quick:
         run(args.n[-1] // 2, 5, [8, 32], True)
 

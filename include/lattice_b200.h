@@ -151,9 +151,11 @@ long long ln_conv_workspace_bytes(int filter_extent, int c_in, int c_out, int pr
 
 /* Weight gradient, replaces `lattice_rowified.transpose(0,1).mm(grad)` (lattice_funcs.py:302,378,443):
  *   grad_filter[slot*c_in + ci, co] = sum_q nbr_values[neighbours[q, slot], ci] * grad_out[q, co]
- * grad_filter [F*c_in x c_out] is overwritten (zeroed, then accumulated with fp32 reductions). */
+ * grad_filter [F*c_in x c_out] is overwritten (zeroed, then accumulated with fp32 reductions).
+ * precision as in ln_conv_fwd: 1 / 2 run the gathered-A^T . G product on tcgen05 (MN-major operands, the
+ * reduction runs over the vertices) when c_in % 32 == 0 and c_out % 4 == 0, c_out <= 256; else fp32 FMA. */
 int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* grad_out,
-                  int nv_query, int filter_extent, int c_in, int c_out,
+                  int nv_query, int filter_extent, int c_in, int c_out, int precision,
                   float* grad_filter, void* stream);
 
 /* Whole backward pass of one lattice convolution out = conv(query <- neighbours) in one call

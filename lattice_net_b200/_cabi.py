@@ -29,7 +29,7 @@ _SIGNATURES = {
     "ln_im2rowindices": [_P, _I, _I, _I, _I, _P, _P],
     "ln_row2im": [_P, _P, _I, _I, _I, _P, _P],
     "ln_conv_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
-    "ln_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "ln_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "ln_conv_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "ln_filter_for_dgrad": [_P, _I, _I, _I, _P, _P],
     "ln_slice_fwd": [_P, _P, _P, _I, _I, _I, _P, _P],

@@ -90,7 +90,15 @@ __device__ __forceinline__ int table_insert(const TableView& t, const int* key, 
         if (cur == kEmpty) {
             cur = atomicCAS(e, kEmpty, kLocked);
             if (cur == kEmpty) {   // we own the slot: allocate the vertex, publish its key
-                const int id = atomicAdd(t.nr_filled, 1);
+                // the vertex counter is ONE address for the whole grid: lanes of this warp that won a slot in the
+                // same probe step share a single atomic (warp-aggregated allocation)
+                const unsigned winners = __activemask();
+                const int lane = threadIdx.x & 31;
+                const int first = __ffs(winners) - 1;
+                int base = 0;
+                if (lane == first) base = atomicAdd(t.nr_filled, __popc(winners));
+                base = __shfl_sync(winners, base, first);
+                const int id = base + __popc(winners & ((1u << lane) - 1u));
                 if (id >= t.max_vertices) atomicOr(t.status, 2);   // caller's row bound exceeded (static-shape mode)
 #pragma unroll
                 for (int i = 0; i < D; i++) t.keys[(size_t)id * D + i] = key[i];

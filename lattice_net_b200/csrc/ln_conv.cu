@@ -15,6 +15,9 @@ int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* fil
                 float* also_zero, long long also_zero_n, cudaStream_t s);
 size_t conv_tc_workspace_bytes(int F, int c_in, int c_out);
 bool conv_tc_supported(int F, int c_in, int c_out);
+bool conv_wgrad_tc_supported(int F, int c_in, int c_out);
+int conv_wgrad_tc(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query, int F, int c_in,
+                  int c_out, int precision, float* grad_filter, cudaStream_t s);
 
 constexpr int kThreads = 256;
 constexpr int BM = 64, BN = 64, BK = 16;
@@ -210,10 +213,13 @@ int ln_conv_fwd(const float* nbr_values, const int* neighbours, const float* fil
 }
 
 static int conv_wgrad_launch(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query,
-                             int filter_extent, int c_in, int c_out, float* grad_filter, bool already_zero, cudaStream_t s) {
+                             int filter_extent, int c_in, int c_out, int precision, float* grad_filter, bool already_zero,
+                             cudaStream_t s) {
     const size_t bytes = (size_t)filter_extent * c_in * c_out * sizeof(float);
     if (!already_zero && cudaMemsetAsync(grad_filter, 0, bytes, s) != cudaSuccess) return check_launch("conv_wgrad memset");
     if (nv_query == 0) return LN_OK;
+    if (precision != 0 && conv_wgrad_tc_supported(filter_extent, c_in, c_out))
+        return conv_wgrad_tc(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, precision, grad_filter, s);
     const int ci_tiles = cdiv(c_in, BM), co_tiles = cdiv(c_out, BN);
     // enough q-chunks to fill the machine (~4 waves of 148 SMs), at least 256 rows each
     const int tiles = ci_tiles * co_tiles * filter_extent;
@@ -227,10 +233,11 @@ static int conv_wgrad_launch(const float* nbr_values, const int* neighbours, con
 }
 
 int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query,
-                  int filter_extent, int c_in, int c_out, float* grad_filter, void* stream) {
+                  int filter_extent, int c_in, int c_out, int precision, float* grad_filter, void* stream) {
     LN_REQUIRE(nbr_values && neighbours && grad_out && grad_filter, "ln_conv_wgrad: null pointer");
     LN_REQUIRE(nv_query >= 0 && filter_extent >= 3 && c_in >= 1 && c_out >= 1, "ln_conv_wgrad: bad size");
-    return conv_wgrad_launch(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, grad_filter, false, (cudaStream_t)stream);
+    LN_REQUIRE(precision >= 0 && precision <= 2, "ln_conv_wgrad: precision must be 0 (fp32), 1 (3xTF32) or 2 (TF32)");
+    return conv_wgrad_launch(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, precision, grad_filter, false, (cudaStream_t)stream);
 }
 
 int ln_conv_bwd(const float* nbr_values, const int* neighbours_fwd, const float* grad_out, const int* neighbours_bwd,
@@ -260,7 +267,7 @@ int ln_conv_bwd(const float* nbr_values, const int* neighbours_fwd, const float*
         }
     }
     if (grad_filter)
-        return conv_wgrad_launch(nbr_values, neighbours_fwd, grad_out, nv_query, filter_extent, c_in, c_out, grad_filter, filter_zeroed, s);
+        return conv_wgrad_launch(nbr_values, neighbours_fwd, grad_out, nv_query, filter_extent, c_in, c_out, precision, grad_filter, filter_zeroed, s);
     return LN_OK;
 }
 

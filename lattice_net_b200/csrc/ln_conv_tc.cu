@@ -11,14 +11,19 @@
 // (A = Ah + Al, B = Bh + Bl;  D += Ah.Bh + Ah.Bl + Al.Bh), which reproduces fp32 SGEMM to ~1e-6 and
 // keeps the parity tolerance of the fp32 reference; precision 2 = single TF32 pass.
 //
-// CTA layout (160 threads):
-//   warps 0-3  producers: gather A rows (ld.global.v4 -> split -> st.shared into the 128B-swizzled
-//              K-major UMMA layout); thread 0 also launches the bulk-async copy (UBLKCP) of the
-//              B slab, which the prep kernel stored pre-swizzled so one copy lands a whole stage;
-//              after the K loop the same warps are the epilogue (tcgen05.ld -> bias -> st.global)
-//   warp 4     TMEM allocation, and one elected lane issues tcgen05.mma / tcgen05.commit
-// smem ring of kStages, full/empty mbarriers between producers and the MMA lane, one mbarrier for
-// "accumulator complete".
+// Persistent CTAs (one per SM) walk work items = (M tile, K split); the smem stage ring and the two TMEM
+// accumulator buffers run straight across item boundaries, so the gathers of item i+1 overlap the MMAs of
+// item i and the epilogue of item i-1.  CTA layout (288 threads):
+//   warps 0-3  producers: neighbour rows are gathered with cp.async (LDGSTS, 16 B, zero-fill for absent
+//              neighbours) DIRECTLY into the 128B-swizzled K-major UMMA layout, kLookahead K blocks in
+//              flight per thread; when a block has landed its owner derives the TF32 low part
+//              (x - trunc_tf32(x)) into the second A tile (3xTF32 only), fences the async proxy and
+//              arrives on the stage's "full" barrier.  Thread 0 also launches the bulk-async copy
+//              (UBLKCP) of the pre-swizzled B slab of that stage.
+//   warp 4     TMEM allocation; one lane issues tcgen05.mma / tcgen05.commit
+//   warps 5-8  epilogue: tcgen05.ld (32 columns = one 128-byte line per thread) -> bias -> st.global
+//              (vector fp32 atomics when K is split across CTAs)
+#include <cstdlib>
 #include "ln_common.cuh"
 
 namespace ln {
@@ -96,6 +101,47 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {   // 32 la
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {   // 32 lanes x 32 consecutive columns
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+// 16-byte async copy global -> shared; src_bytes = 0 zero-fills the destination (absent neighbour)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {   // round-to-nearest TF32, returned as fp32 bits
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// low part of the TF32 split when the tensor core TRUNCATES the raw fp32 operand: x - (x with 13 low mantissa bits cleared)
+__device__ __forceinline__ float tf32_residual(float x) {
+    return to_tf32(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
+}
+
 // K-major, 128B-swizzled shared-memory matrix descriptor (sm_100 format: version 1, SBO = 8 rows * 128 B)
 __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
     uint64_t desc = 0;
@@ -111,11 +157,6 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ float to_tf32(float x) {   // round-to-nearest TF32, returned as fp32 bits
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
 
 // ---- filter preparation ----------------------------------------------------------------------------
 // W [F*c_in x c_out] (row = slot*c_in + ci) -> per K block kb a slab [n_pad rows x 128 B] holding
@@ -322,12 +363,553 @@ conv_fwd_tc_kernel(const float* __restrict__ values, const int* __restrict__ nei
     }
 }
 
+
+// ---- persistent, cp.async-fed kernel (v2) -----------------------------------------------------------
+constexpr int kTc2Threads = 288;
+constexpr int kMaxStages = 6;
+
+struct Tc2Item {   // one unit of work of a persistent CTA
+    int q0, kb_begin, num_kb, split;
+};
+__device__ __forceinline__ Tc2Item tc2_item(int item, int m_tiles, int total_kb, int kb_per_split) {
+    Tc2Item w;
+    w.split = item / m_tiles;                    // items of one split are contiguous: neighbouring CTAs share B slabs in L2
+    w.q0 = (item - w.split * m_tiles) * kTileM;
+    w.kb_begin = w.split * kb_per_split;
+    w.num_kb = min(total_kb, w.kb_begin + kb_per_split) - w.kb_begin;
+    return w;
+}
+
+template <int kSplit>   // 1: 3xTF32, 0: single pass
+__global__ void __launch_bounds__(kTc2Threads, 1)
+conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighbours,
+                const float* __restrict__ b_hi, const float* __restrict__ b_lo, const float* __restrict__ bias,
+                int nv_query, int F, int c_in, int c_out, int n_pad, int flip, int stages, int lookahead,
+                int m_tiles, int n_items, int kb_per_split, int truncating_operand, float* __restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t b_tile_bytes = (uint32_t)n_pad * kRowBytes;
+    const uint32_t stage_bytes = (kSplit ? 2 : 1) * (kATileBytes + b_tile_bytes);
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    int* nbr_sh = (int*)(base + (size_t)stages * stage_bytes);                      // [2][kTileM * F]
+    uint64_t* bars = (uint64_t*)(((uintptr_t)(nbr_sh + 2 * kTileM * F) + 15) & ~(uintptr_t)15);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kMaxStages + 4);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const uint32_t base_u32 = smem_u32(base);
+    const uint32_t bars_u32 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bars_u32 + 8u * (uint32_t)s; };
+    auto empty_bar = [&](int s) { return bars_u32 + 8u * (uint32_t)(kMaxStages + s); };
+    auto acc_full_bar = [&](int a) { return bars_u32 + 8u * (uint32_t)(2 * kMaxStages + a); };
+    auto acc_empty_bar = [&](int a) { return bars_u32 + 8u * (uint32_t)(2 * kMaxStages + 2 + a); };
+    auto a_hi = [&](int s) { return base_u32 + (uint32_t)s * stage_bytes; };
+    auto a_lo = [&](int s) { return a_hi(s) + kATileBytes; };
+    auto b_hi_s = [&](int s) { return a_hi(s) + (kSplit ? 2 : 1) * kATileBytes; };
+    auto b_lo_s = [&](int s) { return b_hi_s(s) + b_tile_bytes; };
+
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < 2 * n_pad) tmem_cols <<= 1;       // two accumulator buffers
+    if (tid == 0) {
+        for (int s = 0; s < stages; s++) {
+            mbar_init(full_bar(s), 128 + 1);   // 128 producer threads + the expect_tx arrival for B
+            mbar_init(empty_bar(s), 1);        // one tcgen05.commit
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(acc_full_bar(a), 1);     // one tcgen05.commit
+            mbar_init(acc_empty_bar(a), 128);  // the 128 epilogue threads
+        }
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int cpb = c_in / kBlockK;          // K blocks per slot
+    const int total_kb = F * cpb;
+    const bool split_k = n_items > m_tiles;
+
+    if (warp < 4) {
+        // ================= producers =================
+        const int chunk = tid & 7;
+        const int row0 = tid >> 3;           // this thread's rows: row0 + 16*i; (row & 7) is the same for all of them
+        const uint32_t my_off = (uint32_t)row0 * kRowBytes + (uint32_t)((chunk ^ (row0 & 7)) << 4);
+        const int per_thread = (kTileM * F + 127) / 128;      // neighbour ids staged per thread and item (<= 13)
+        int ibuf = 0;
+        // neighbour ids of the first item
+        if ((int)blockIdx.x < n_items) {
+            const Tc2Item w = tc2_item(blockIdx.x, m_tiles, total_kb, kb_per_split);
+            for (int i = tid; i < kTileM * F; i += 128) {
+                const int q = w.q0 + i / F;
+                nbr_sh[i] = (q < nv_query) ? __ldg(neighbours + (size_t)w.q0 * F + i) : -1;
+            }
+        }
+        producer_bar_sync();
+        int g = 0;                           // K blocks issued so far by this CTA (all items)
+        auto publish = [&](int b) {          // block b has landed in this thread's view: finish it and signal the MMA lane
+            const int s = b % stages;
+            if (kSplit) {
+                const uint32_t hi = a_hi(s) + my_off, lo = a_lo(s) + my_off;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float4 x = lds128(hi + (uint32_t)i * 16u * kRowBytes);
+                    if (truncating_operand) {     // the tensor core drops the 13 low mantissa bits of the raw fp32 operand itself
+                        sts128(lo + (uint32_t)i * 16u * kRowBytes,
+                               make_float4(tf32_residual(x.x), tf32_residual(x.y), tf32_residual(x.z), tf32_residual(x.w)));
+                    } else {                       // explicit round-to-nearest high part, independent of the operand read-out
+                        const float4 h = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
+                        sts128(hi + (uint32_t)i * 16u * kRowBytes, h);
+                        sts128(lo + (uint32_t)i * 16u * kRowBytes,
+                               make_float4(to_tf32(x.x - h.x), to_tf32(x.y - h.y), to_tf32(x.z - h.z), to_tf32(x.w - h.w)));
+                    }
+                }
+            }
+            fence_proxy_async();             // generic-proxy writes (cp.async data, lo tile) -> visible to the tensor-core proxy
+            mbar_arrive(full_bar(s));
+        };
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const Tc2Item w = tc2_item(item, m_tiles, total_kb, kb_per_split);
+            const int* ids = nbr_sh + ibuf * (kTileM * F);
+            // prefetch the next item's neighbour ids into registers (stored to the other buffer at the end of this item)
+            int next_ids[13];
+            const int next = item + gridDim.x;
+            if (next < n_items) {
+                const Tc2Item wn = tc2_item(next, m_tiles, total_kb, kb_per_split);
+#pragma unroll
+                for (int j = 0; j < 13; j++) {
+                    const int i = tid + 128 * j;
+                    next_ids[j] = -1;
+                    if (j < per_thread && i < kTileM * F && wn.q0 + i / F < nv_query) next_ids[j] = __ldg(neighbours + (size_t)wn.q0 * F + i);
+                }
+            }
+            for (int it = 0; it < w.num_kb; it++, g++) {
+                const int kb = w.kb_begin + it;
+                const int s = g % stages;
+                mbar_wait(empty_bar(s), (((uint32_t)(g / stages)) & 1u) ^ 1u);
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(full_bar(s), (kSplit ? 2u : 1u) * b_tile_bytes);
+                    bulk_copy_g2s(b_hi_s(s), b_hi + (size_t)kb * n_pad * kBlockK, b_tile_bytes, full_bar(s));
+                    if (kSplit) bulk_copy_g2s(b_lo_s(s), b_lo + (size_t)kb * n_pad * kBlockK, b_tile_bytes, full_bar(s));
+                }
+                const int slot = kb / cpb;
+                const int cb = kb - slot * cpb;
+                const int src_slot = (flip && slot < F - 1) ? (slot ^ 1) : slot;
+                const uint32_t dst = a_hi(s) + my_off;
+                const float* col = values + (size_t)cb * kBlockK + chunk * 4;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int id = ids[(row0 + 16 * i) * F + src_slot];
+                    cp_async16(dst + (uint32_t)i * 16u * kRowBytes, id >= 0 ? col + (size_t)id * c_in : values, id >= 0 ? 16u : 0u);
+                }
+                cp_async_commit();
+                if (g >= lookahead) {
+                    switch (lookahead) {     // cp.async.wait_group takes an immediate
+                        case 1: cp_async_wait<1>(); break;
+                        case 2: cp_async_wait<2>(); break;
+                        case 3: cp_async_wait<3>(); break;
+                        case 4: cp_async_wait<4>(); break;
+                        default: cp_async_wait<5>(); break;
+                    }
+                    publish(g - lookahead);
+                }
+            }
+            if (next < n_items) {
+                int* dst_ids = nbr_sh + (ibuf ^ 1) * (kTileM * F);
+#pragma unroll
+                for (int j = 0; j < 13; j++) {
+                    const int i = tid + 128 * j;
+                    if (j < per_thread && i < kTileM * F) dst_ids[i] = next_ids[j];
+                }
+            }
+            producer_bar_sync();
+            ibuf ^= 1;
+        }
+        cp_async_wait<0>();
+        for (int b = max(0, g - lookahead); b < g; b++) publish(b);
+    } else if (warp == 4) {
+        // ================= MMA issuer (one lane) =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(kTileM, n_pad);
+            int g = 0, j = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, j++) {
+                const Tc2Item w = tc2_item(item, m_tiles, total_kb, kb_per_split);
+                const int a = j & 1;
+                mbar_wait(acc_empty_bar(a), (((uint32_t)(j >> 1)) & 1u) ^ 1u);   // epilogue has drained this buffer
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * n_pad);
+                for (int it = 0; it < w.num_kb; it++, g++) {
+                    const int s = g % stages;
+                    mbar_wait(full_bar(s), ((uint32_t)(g / stages)) & 1u);
+                    tc_fence_after();
+                    const uint64_t da_hi = umma_desc_kmajor_sw128(a_hi(s));
+                    const uint64_t db_hi = umma_desc_kmajor_sw128(b_hi_s(s));
+                    const uint64_t da_lo = umma_desc_kmajor_sw128(a_lo(s));
+                    const uint64_t db_lo = umma_desc_kmajor_sw128(b_lo_s(s));
+#pragma unroll
+                    for (int ks = 0; ks < kBlockK / 8; ks++) {   // UMMA K = 8 tf32 = 32 bytes = 2 x 16-byte units
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        if (kSplit) {                             // small cross terms first, then the main product
+                            umma_tf32(d_tmem, da_lo + adv, db_hi + adv, idesc, (it | ks) != 0 ? 1u : 0u);
+                            umma_tf32(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
+                            umma_tf32(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+                        } else {
+                            umma_tf32(d_tmem, da_hi + adv, db_hi + adv, idesc, (it | ks) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(empty_bar(s));   // frees the stage when these MMAs have read it
+                }
+                umma_commit(acc_full_bar(a));    // accumulator complete -> epilogue
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue (warps 5-8; TMEM lane quadrant = warp % 4) =================
+        const int quad = warp & 3;
+        int j = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, j++) {
+            const Tc2Item w = tc2_item(item, m_tiles, total_kb, kb_per_split);
+            const int a = j & 1;
+            mbar_wait(acc_full_bar(a), ((uint32_t)(j >> 1)) & 1u);
+            tc_fence_after();
+            const int q = w.q0 + quad * 32 + lane;
+            const bool live = q < nv_query;
+            float* orow = out + (size_t)q * c_out;
+            const bool add_bias = bias != nullptr && w.split == 0;
+            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * n_pad);
+            for (int n0 = 0; n0 < n_pad; n0 += 32) {
+                float acc[32];
+                if (n0 + 32 <= n_pad) {
+                    tmem_ld32(t_row + (uint32_t)n0, acc);
+                } else {                       // n_pad is a multiple of 16: a 16-column tail
+                    tmem_ld16(t_row + (uint32_t)n0, acc);
+#pragma unroll
+                    for (int k = 16; k < 32; k++) acc[k] = 0.0f;
+                }
+                if (!live) continue;
+                if ((c_out & 3) == 0) {
+#pragma unroll
+                    for (int k = 0; k < 32; k += 4) {
+                        if (n0 + k < c_out) {
+                            float4 o = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
+                            if (add_bias) {
+                                o.x += __ldg(bias + n0 + k); o.y += __ldg(bias + n0 + k + 1);
+                                o.z += __ldg(bias + n0 + k + 2); o.w += __ldg(bias + n0 + k + 3);
+                            }
+                            if (split_k)
+                                atomicAdd(reinterpret_cast<float4*>(orow + n0 + k), o);
+                            else
+                                *reinterpret_cast<float4*>(orow + n0 + k) = o;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) {
+                        if (n0 + k < c_out) {
+                            const float o = acc[k] + (add_bias ? __ldg(bias + n0 + k) : 0.0f);
+                            if (split_k)
+                                atomicAdd(orow + n0 + k, o);
+                            else
+                                orow[n0 + k] = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acc_empty_bar(a));     // this thread has read its rows of the buffer
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
 size_t conv_tc_workspace_bytes(int F, int c_in, int c_out) {
     const int n_pad = (c_out + 15) / 16 * 16;
     return (size_t)2 * F * c_in * n_pad * sizeof(float);
 }
 
 bool conv_tc_supported(int F, int c_in, int c_out) { return c_in % kBlockK == 0 && c_out >= 1 && c_out <= 256 && F >= 3; }
+
+static int env_int(const char* name, int dflt) {   // development knobs, read on every call (cheap: a few per launch)
+    const char* e = getenv(name);
+    return (e != nullptr && e[0] != 0) ? atoi(e) : dflt;
+}
+static bool use_v1() {   // development switch: LN_CONV_TC_V1=1 selects the first-generation (non-persistent) kernel
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LN_CONV_TC_V1");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+
+// ---- weight gradient on the tensor cores -------------------------------------------------------------
+//   grad_filter[slot*c_in + ci, co] = sum_q values[nbr[q, slot], ci] * grad_out[q, co]
+// per slot a GEMM  D[c_in x c_out] = A^T[c_in x nv] . G[nv x c_out]  whose reduction runs over the VERTICES.
+// Both operands sit in shared memory exactly as they sit in HBM -- one 128-byte row segment (32 channels) per
+// vertex, 128B-swizzled by the row -- which is the MN-major UMMA layout (channels contiguous, K = vertices down
+// the rows), so the gather needs no transposition: M = 128 channels of c_in (4 groups of 32), N = c_out (groups
+// of 32), K = 8 vertices per tcgen05.mma, 32 vertices per pipeline stage.
+// Work item = (slot, 128-channel tile of c_in, vertex range); partial sums of different vertex ranges are
+// combined with vector fp32 atomics into the pre-zeroed gradient.
+constexpr int kWgRows = 32;                       // vertices per stage
+constexpr int kWgGroupBytes = kWgRows * kRowBytes;   // one 32-channel group of a stage: 4 KB
+constexpr int kWgThreads = 160;
+
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
+    uint64_t desc = 0;
+    desc |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address, 16-byte units
+    desc |= (uint64_t)(kWgGroupBytes >> 4) << 16;             // leading byte offset: next 32-channel (MN) group
+    desc |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset: next 8 vertices (K)
+    desc |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
+    desc |= (uint64_t)2 << 61;                                // layout type: SWIZZLE_128B
+    return desc;
+}
+__device__ __forceinline__ uint32_t umma_idesc_tf32_mn(int m, int n) {   // as umma_idesc_tf32, A and B MN-major
+    return umma_idesc_tf32(m, n) | (1u << 15) | (1u << 16);
+}
+
+template <int kSplit>
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ neighbours,
+                     const float* __restrict__ grad_out, int nv_query, int F, int c_in, int c_out, int n_pad,
+                     int ci_tiles, int q_splits, int chunks_per_split, int stages, int lookahead,
+                     float* __restrict__ grad_filter) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int n_groups = (n_pad + 31) / 32;
+    const uint32_t a_bytes = 4u * kWgGroupBytes;                       // 128 channels x 32 vertices = 16 KB
+    const uint32_t g_bytes = (uint32_t)n_groups * kWgGroupBytes;
+    const uint32_t stage_bytes = (kSplit ? 2 : 1) * (a_bytes + g_bytes);
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(base + (size_t)stages * stage_bytes);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kMaxStages + 1);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const uint32_t base_u32 = smem_u32(base);
+    const uint32_t bars_u32 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bars_u32 + 8u * (uint32_t)s; };
+    auto empty_bar = [&](int s) { return bars_u32 + 8u * (uint32_t)(kMaxStages + s); };
+    const uint32_t accum_bar = bars_u32 + 8u * (uint32_t)(2 * kMaxStages);
+    auto a_hi = [&](int s) { return base_u32 + (uint32_t)s * stage_bytes; };
+    auto g_hi = [&](int s) { return a_hi(s) + a_bytes; };
+    auto a_lo = [&](int s) { return g_hi(s) + g_bytes; };
+    auto g_lo = [&](int s) { return a_lo(s) + a_bytes; };
+
+    // work item
+    int item = blockIdx.x;
+    const int qs = item % q_splits;
+    item /= q_splits;
+    const int ct = item % ci_tiles;
+    const int slot = item / ci_tiles;
+    const int ci0 = ct * 128;
+    const int ci_n = min(128, c_in - ci0);                             // channels of this tile (multiple of 32)
+    const int total_chunks = (nv_query + kWgRows - 1) / kWgRows;
+    const int chunk_begin = qs * chunks_per_split;
+    const int num_chunks = max(0, min(total_chunks, chunk_begin + chunks_per_split) - chunk_begin);
+
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < n_pad) tmem_cols <<= 1;
+    if (tid == 0) {
+        for (int s = 0; s < stages; s++) {
+            mbar_init(full_bar(s), 128);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ================= producers: 8 lanes per vertex row (one 16-byte chunk each), 16 rows per pass =================
+        const int cc = tid & 7;                   // 16-byte chunk inside a 128-byte group row
+        const int r0 = tid >> 3;                  // rows r0 and r0 + 16 of the stage
+        const int a_groups = ci_n / 32;
+        auto publish = [&](int b) {
+            const int s = b % stages;
+            if (kSplit) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int r = r0 + 16 * h;
+                    const uint32_t off = (uint32_t)r * kRowBytes + (uint32_t)((cc ^ (r & 7)) << 4);
+                    for (int grp = 0; grp < a_groups + n_groups; grp++) {
+                        const bool is_a = grp < a_groups;
+                        const uint32_t hi = (is_a ? a_hi(s) + (uint32_t)grp * kWgGroupBytes : g_hi(s) + (uint32_t)(grp - a_groups) * kWgGroupBytes) + off;
+                        const uint32_t lo = (is_a ? a_lo(s) + (uint32_t)grp * kWgGroupBytes : g_lo(s) + (uint32_t)(grp - a_groups) * kWgGroupBytes) + off;
+                        const float4 x = lds128(hi);
+                        const float4 hv = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
+                        sts128(hi, hv);
+                        sts128(lo, make_float4(to_tf32(x.x - hv.x), to_tf32(x.y - hv.y), to_tf32(x.z - hv.z), to_tf32(x.w - hv.w)));
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(full_bar(s));
+        };
+        for (int g = 0; g < num_chunks; g++) {
+            const int s = g % stages;
+            mbar_wait(empty_bar(s), (((uint32_t)(g / stages)) & 1u) ^ 1u);
+            const int qbase = (chunk_begin + g) * kWgRows;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int r = r0 + 16 * h;
+                const int q = qbase + r;
+                const uint32_t off = (uint32_t)r * kRowBytes + (uint32_t)((cc ^ (r & 7)) << 4);
+                int id = -1;
+                if (q < nv_query) id = __ldg(neighbours + (size_t)q * F + slot);
+                const float* arow = values + (size_t)(id >= 0 ? id : 0) * c_in + ci0 + cc * 4;
+                for (int grp = 0; grp < a_groups; grp++)
+                    cp_async16(a_hi(s) + (uint32_t)grp * kWgGroupBytes + off, arow + grp * 32, id >= 0 ? 16u : 0u);
+                const float* grow = grad_out + (size_t)(q < nv_query ? q : 0) * c_out + cc * 4;
+                for (int grp = 0; grp < n_groups; grp++) {
+                    const bool ok = q < nv_query && grp * 32 + cc * 4 < c_out;      // c_out % 4 == 0: whole chunks only
+                    cp_async16(g_hi(s) + (uint32_t)grp * kWgGroupBytes + off, ok ? grow + grp * 32 : grad_out, ok ? 16u : 0u);
+                }
+            }
+            cp_async_commit();
+            if (g >= lookahead) {
+                switch (lookahead) {
+                    case 1: cp_async_wait<1>(); break;
+                    case 2: cp_async_wait<2>(); break;
+                    case 3: cp_async_wait<3>(); break;
+                    case 4: cp_async_wait<4>(); break;
+                    default: cp_async_wait<5>(); break;
+                }
+                publish(g - lookahead);
+            }
+        }
+        cp_async_wait<0>();
+        for (int b = max(0, num_chunks - lookahead); b < num_chunks; b++) publish(b);
+
+        // ================= epilogue: TMEM lane = channel of the tile, columns = c_out =================
+        if (num_chunks > 0) {
+            mbar_wait(accum_bar, 0);
+            tc_fence_after();
+            const int m = warp * 32 + lane;
+            const bool live = m < ci_n;
+            float* orow = grad_filter + ((size_t)slot * c_in + ci0 + m) * c_out;
+            for (int n0 = 0; n0 < n_pad; n0 += 16) {
+                float acc[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, acc);
+                if (!live) continue;
+#pragma unroll
+                for (int k = 0; k < 16; k += 4) {
+                    if (n0 + k < c_out) {
+                        const float4 o = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
+                        if (q_splits > 1)
+                            atomicAdd(reinterpret_cast<float4*>(orow + n0 + k), o);
+                        else
+                            *reinterpret_cast<float4*>(orow + n0 + k) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    } else {
+        // ================= MMA issuer =================
+        if (lane == 0 && num_chunks > 0) {
+            const uint32_t idesc = umma_idesc_tf32_mn(128, n_pad);
+            for (int g = 0; g < num_chunks; g++) {
+                const int s = g % stages;
+                mbar_wait(full_bar(s), ((uint32_t)(g / stages)) & 1u);
+                tc_fence_after();
+                const uint64_t da_hi = umma_desc_mnmajor_sw128(a_hi(s));
+                const uint64_t dg_hi = umma_desc_mnmajor_sw128(g_hi(s));
+                const uint64_t da_lo = umma_desc_mnmajor_sw128(a_lo(s));
+                const uint64_t dg_lo = umma_desc_mnmajor_sw128(g_lo(s));
+#pragma unroll
+                for (int ks = 0; ks < kWgRows / 8; ks++) {       // 8 vertices per MMA = one 1024-byte swizzle atom down the rows
+                    const uint64_t adv = (uint64_t)(ks * (1024 >> 4));
+                    if (kSplit) {
+                        umma_tf32(tmem_base, da_lo + adv, dg_hi + adv, idesc, (g | ks) != 0 ? 1u : 0u);
+                        umma_tf32(tmem_base, da_hi + adv, dg_lo + adv, idesc, 1u);
+                        umma_tf32(tmem_base, da_hi + adv, dg_hi + adv, idesc, 1u);
+                    } else {
+                        umma_tf32(tmem_base, da_hi + adv, dg_hi + adv, idesc, (g | ks) != 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(accum_bar);
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+bool conv_wgrad_tc_supported(int F, int c_in, int c_out) {
+    return c_in % 32 == 0 && c_out % 4 == 0 && c_out >= 4 && c_out <= 256 && F >= 3;
+}
+
+// grad_filter must be zero when q_splits > 1 (the caller clears it).  Returns the number of vertex-range splits used.
+int conv_wgrad_tc(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query, int F, int c_in,
+                  int c_out, int precision, float* grad_filter, cudaStream_t s) {
+    const int split = precision == 1 ? 1 : 0;
+    const int n_pad = (c_out + 15) / 16 * 16;
+    const int n_groups = (n_pad + 31) / 32;
+    const int ci_tiles = cdiv(c_in, 128);
+    const int total_chunks = cdiv(nv_query, kWgRows);
+    const int tiles = F * ci_tiles;
+    // enough CTAs for the machine (two waves at most), at least 4 stages of vertices per CTA
+    int q_splits = max(1, min(cdiv(total_chunks, 4), (2 * sm_count()) / tiles));
+    const int chunks_per_split = cdiv(total_chunks, q_splits);
+    q_splits = cdiv(total_chunks, chunks_per_split);
+    const size_t stage_bytes = (size_t)(split ? 2 : 1) * (4 + n_groups) * kWgGroupBytes;
+    const size_t fixed = (2 * kMaxStages + 1) * 8 + 16 + 1024;
+    int stages = (int)min((size_t)kMaxStages, (227 * 1024 - fixed) / stage_bytes);
+    if (stages < 2) {
+        set_error("conv_wgrad_tc: tile does not fit shared memory (c_out=%d)", c_out);
+        return LN_ERR_UNSUPPORTED;
+    }
+    stages = min(stages, max(2, env_int("LN_CONV_STAGES", kMaxStages)));
+    const int lookahead = min(stages - 1, max(1, env_int("LN_CONV_LOOKAHEAD", stages / 2)));   // see conv_fwd_tc
+    // > half of the SM's shared memory: one CTA per SM (TMEM columns, see conv_tc2)
+    const size_t smem = max((size_t)stages * stage_bytes + fixed, (size_t)120 * 1024);
+    const int grid = tiles * q_splits;
+    cudaError_t err;
+    if (split) {
+        err = cudaFuncSetAttribute(conv_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err == cudaSuccess)
+            conv_wgrad_tc_kernel<1><<<grid, kWgThreads, smem, s>>>(nbr_values, neighbours, grad_out, nv_query, F, c_in, c_out, n_pad, ci_tiles,
+                                                                    q_splits, chunks_per_split, stages, lookahead, grad_filter);
+    } else {
+        err = cudaFuncSetAttribute(conv_wgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err == cudaSuccess)
+            conv_wgrad_tc_kernel<0><<<grid, kWgThreads, smem, s>>>(nbr_values, neighbours, grad_out, nv_query, F, c_in, c_out, n_pad, ci_tiles,
+                                                                    q_splits, chunks_per_split, stages, lookahead, grad_filter);
+    }
+    if (err != cudaSuccess) {
+        set_error("conv_wgrad_tc: %s", cudaGetErrorString(err));
+        return LN_ERR_CUDA;
+    }
+    count_launch();
+    return check_launch("conv_wgrad_tc");
+}
 
 int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
                 int F, int c_in, int c_out, int flip, int precision, int transposed, float* workspace, float* out,
@@ -352,6 +934,42 @@ int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* fil
     }
     const size_t b_tile = (size_t)n_pad * kRowBytes;
     const size_t stage_bytes = (split ? 2 : 1) * (kATileBytes + b_tile);
+    cudaError_t err;
+    if (!use_v1()) {
+        // persistent kernel: one CTA per SM, items = (M tile, K split)
+        const size_t fixed = (size_t)2 * kTileM * F * sizeof(int) + 16 + (2 * kMaxStages + 4) * 8 + 16 + 1024;
+        int stages = (int)((227 * 1024 - fixed) / stage_bytes);
+        stages = min(stages, kMaxStages);
+        if (stages < 2) {
+            set_error("ln_conv_fwd: tensor-core tile does not fit shared memory (c_out=%d)", c_out);
+            return LN_ERR_UNSUPPORTED;
+        }
+        // K blocks in flight per producer thread.  Half the ring: a stage published `stages - lookahead` iterations ago has
+        // had that long for its MMAs to retire before the producer needs it back (lookahead = stages - 1 serialises the two)
+        stages = min(stages, max(2, env_int("LN_CONV_STAGES", kMaxStages)));
+        const int lookahead = min(stages - 1, max(1, env_int("LN_CONV_LOOKAHEAD", stages / 2)));
+        // > half of the SM's shared memory: exactly one CTA per SM, so the 2*n_pad TMEM columns are always available
+        const size_t smem = max((size_t)stages * stage_bytes + fixed, (size_t)120 * 1024);
+        const int n_items = m_tiles * splits;
+        const int grid = min(n_items, sm_count());
+        if (split) {
+            err = cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err == cudaSuccess)
+                conv_tc2_kernel<1><<<grid, kTc2Threads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias, nv_query, F, c_in, c_out, n_pad, flip,
+                                                                    stages, lookahead, m_tiles, n_items, kb_per_split, env_int("LN_CONV_TRUNC", 0), out);
+        } else {
+            err = cudaFuncSetAttribute(conv_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err == cudaSuccess)
+                conv_tc2_kernel<0><<<grid, kTc2Threads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias, nv_query, F, c_in, c_out, n_pad, flip,
+                                                                    stages, lookahead, m_tiles, n_items, kb_per_split, 0, out);
+        }
+        if (err != cudaSuccess) {
+            set_error("conv_tc2: %s", cudaGetErrorString(err));
+            return LN_ERR_CUDA;
+        }
+        count_launch();
+        return check_launch("conv_tc2");
+    }
     const size_t fixed = (size_t)kTileM * F * sizeof(int) + 16 + (2 * 8 + 1) * 8 + 16 + 1024;
     int stages = (int)((227 * 1024 - fixed) / stage_bytes);
     stages = min(stages, 8);
@@ -362,7 +980,6 @@ int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* fil
     }
     const size_t smem = (size_t)stages * stage_bytes + fixed;
     const dim3 grid(m_tiles, splits);
-    cudaError_t err;
     if (split) {
         err = cudaFuncSetAttribute(conv_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err == cudaSuccess)

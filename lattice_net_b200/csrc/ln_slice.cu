@@ -24,10 +24,12 @@ static inline int ilog2(int x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int VEC>
+// SPV = simplex vertices per point (pos_dim + 1) as a compile-time constant: ids / weights stay in registers and
+// the SPV row gathers of one thread are independent loads in flight together.
+template <int VEC, int SPV>
 __global__ void __launch_bounds__(kBlock)
 slice_fwd_kernel(const float* __restrict__ lattice_values, const int* __restrict__ indices,
-                 const float* __restrict__ weights, int n, int spv, int val_dim, int lpp_log2,
+                 const float* __restrict__ weights, int n, int val_dim, int lpp_log2,
                  float* __restrict__ out) {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long p = tid >> lpp_log2;
@@ -35,34 +37,44 @@ slice_fwd_kernel(const float* __restrict__ lattice_values, const int* __restrict
     const int g = (int)(tid & ((1 << lpp_log2) - 1));
     const int lpp = 1 << lpp_log2;
     const int vpr = val_dim / VEC;
-    int id[kMaxSpv];
-    float w[kMaxSpv];
+    int id[SPV];
+    float w[SPV];
+    if (SPV == 4) {
+        const int4 i4 = __ldg(reinterpret_cast<const int4*>(indices) + p);
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(weights) + p);
+        id[0] = i4.x; id[1] = i4.y; id[2] = i4.z; id[3] = i4.w;
+        w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+    } else {
 #pragma unroll
-    for (int r = 0; r < kMaxSpv; r++) {
-        if (r < spv) {
-            id[r] = __ldg(indices + p * spv + r);
-            w[r] = __ldg(weights + p * spv + r);
-        } else {
-            id[r] = -1;
-            w[r] = 0.f;
+        for (int r = 0; r < SPV; r++) {
+            id[r] = __ldg(indices + p * SPV + r);
+            w[r] = __ldg(weights + p * SPV + r);
         }
     }
     for (int c = g; c < vpr; c += lpp) {
+        float4 x[SPV];
+#pragma unroll
+        for (int r = 0; r < SPV; r++) {
+            x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (id[r] >= 0) {
+                const float* src = lattice_values + (size_t)id[r] * val_dim + (size_t)c * VEC;
+                if (VEC == 4)
+                    x[r] = __ldg(reinterpret_cast<const float4*>(src));
+                else
+                    x[r].x = __ldg(src);
+            }
+        }
         float acc[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; k++) acc[k] = 0.0f;
 #pragma unroll
-        for (int r = 0; r < kMaxSpv; r++) {
-            if (r < spv && id[r] >= 0) {   // same FMA chain, in the same order, as LatticeGPU.cuh:2575-2585
-                const float* src = lattice_values + (size_t)id[r] * val_dim + (size_t)c * VEC;
+        for (int r = 0; r < SPV; r++) {
+            if (id[r] >= 0) {   // same FMA chain, in the same order, as LatticeGPU.cuh:2575-2585
+                acc[0] = fmaf(x[r].x, w[r], acc[0]);
                 if (VEC == 4) {
-                    const float4 x = __ldg(reinterpret_cast<const float4*>(src));
-                    acc[0] = fmaf(x.x, w[r], acc[0]);
-                    acc[1] = fmaf(x.y, w[r], acc[1]);
-                    acc[2] = fmaf(x.z, w[r], acc[2]);
-                    acc[3] = fmaf(x.w, w[r], acc[3]);
-                } else {
-                    acc[0] = fmaf(__ldg(src), w[r], acc[0]);
+                    acc[1] = fmaf(x[r].y, w[r], acc[1]);
+                    acc[2] = fmaf(x[r].z, w[r], acc[2]);
+                    acc[3] = fmaf(x[r].w, w[r], acc[3]);
                 }
             }
         }
@@ -370,10 +382,18 @@ int ln_slice_fwd(const float* lattice_values, const int* indices, const float* w
     const int vec = (val_dim % 4 == 0) ? 4 : 1;
     const int lpp = lanes_per_point(val_dim / vec);
     const int grid = cdiv((long long)n * lpp, kBlock);
-    if (vec == 4)
-        slice_fwd_kernel<4><<<grid, kBlock, 0, s>>>(lattice_values, indices, weights, n, pos_dim + 1, val_dim, ilog2(lpp), out);
-    else
-        slice_fwd_kernel<1><<<grid, kBlock, 0, s>>>(lattice_values, indices, weights, n, pos_dim + 1, val_dim, ilog2(lpp), out);
+#define LN_LAUNCH_SLICE(VEC, SPV) slice_fwd_kernel<VEC, SPV><<<grid, kBlock, 0, s>>>(lattice_values, indices, weights, n, val_dim, ilog2(lpp), out)
+    const int spv = pos_dim + 1;
+    if (spv != 4 && spv != 6) {
+        set_error("ln_slice_fwd: pos_dim %d not built (3 and 5 are)", pos_dim);
+        return LN_ERR_UNSUPPORTED;
+    }
+    if (vec == 4) {
+        if (spv == 4) LN_LAUNCH_SLICE(4, 4); else LN_LAUNCH_SLICE(4, 6);
+    } else {
+        if (spv == 4) LN_LAUNCH_SLICE(1, 4); else LN_LAUNCH_SLICE(1, 6);
+    }
+#undef LN_LAUNCH_SLICE
     count_launch();
     return check_launch("slice_fwd");
 }

@@ -606,7 +606,7 @@ class Lattice:
         _check(g.shape[0] == nv, "grad_values rows must match the query lattice")
         grad_filter = torch.empty((filter_extent * vn, g.shape[1]), dtype=torch.float32, device=st.device)
         call("ln_conv_wgrad", ptr(nbrs.values().contiguous()), ptr(table), ptr(g), nv, filter_extent, vn,
-             int(g.shape[1]), ptr(grad_filter), stream_ptr(st.device))
+             int(g.shape[1]), CONV_PRECISION, ptr(grad_filter), stream_ptr(st.device))
         return grad_filter
 
     @staticmethod

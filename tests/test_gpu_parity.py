@@ -442,6 +442,11 @@ def test_conv_tensor_core(built, Cin, Cout, precision, tol):
             got = out.values().cpu().numpy()[b["n2o"]]
             exp = lo.conv_fwd(lv, table, fb, flip=flip) + bias
             assert_close(got, exp, tol, f"tensor-core conv precision={precision} flip={flip}")
+        # weight gradient on the tensor cores (MN-major operands, reduction over the vertices)
+        g = cases.randn((b["nv"], Cout), 90 + Cout)
+        query = ours.clone_lattice()
+        gw = query.conv_weight_grad(ours, cuda(g[b["o2n"]]), F, 1).cpu().numpy()
+        assert_close(gw, lo.conv_wgrad(lv, table, g), tol, f"tensor-core weight gradient precision={precision}")
     finally:
         lattice_mod.set_conv_precision(0)
 
@@ -598,7 +603,11 @@ def test_group_norm_ignores_padding_rows(relu):
 
 def test_graphed_step_matches_eager_step():
     """One CUDA-graph replay of the whole training step (static-shape lattice) == the eager dynamic-shape step:
-    same loss, same parameter gradients, vertex counts reported from the device."""
+    same loss, same parameter gradients, vertex counts reported from the device.
+
+    Which vertex gets id 0 is a race in the hash insert (in the reference too, HashTableGPU.cuh:454) and the
+    model zeroes that vertex (lattice_modules.py:72-94, 712), so two runs are comparable only when they
+    happened to number the same vertex 0; the test repeats both paths until that is the case."""
     import copy
     from lattice_net_b200 import Lattice, ModelParams
     from lattice_net_b200.graphed import GraphedTrainStep, estimate_vertex_bounds
@@ -615,36 +624,52 @@ def test_graphed_step_matches_eager_step():
         model_a(lat_a, *clouds[0][:2])                      # creates the lazy parameters
     model_b = copy.deepcopy(model_a)
     lat_b = Lattice(60000, [(0.05, 3)])
-    opt_b = torch.optim.AdamW(model_b.parameters(), lr=1e-3, weight_decay=3e-4, amsgrad=True, fused=True, capturable=True)
+    # lr = 0: the replayed optimizer step runs but leaves the parameters where they are, so every attempt
+    # below compares the two paths on identical weights
+    opt_b = torch.optim.AdamW(model_b.parameters(), lr=0.0, weight_decay=3e-4, amsgrad=True, fused=True, capturable=True)
     bucket_b = GradBucket(model_b.parameters())
     bounds = estimate_vertex_bounds(60000, [(0.05, 3)], [c[0] for c in clouds], 4)
     step = GraphedTrainStep(model_b, lat_b, opt_b, segmentation_loss, 2048, 3, 1, bounds, bucket_b, example=clouds[0])
     # the capture's warm-up passes must leave parameters untouched
     for (na, pa), (nb, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
         assert torch.equal(pa, pb), f"{na} changed during graph capture"
+    replays = 0
     for pos, vals, labels in clouds[1:]:
-        logsm, _ = model_a(lat_a, pos, vals)
-        loss_a = segmentation_loss(logsm, labels)
-        for p in model_a.parameters():
-            p.grad = None
-        loss_a.backward()
-        before = [p.detach().clone() for p in model_b.parameters()]
-        loss_b = step(pos, vals, labels)
-        torch.cuda.synchronize()
-        nv_levels = [l.nr_lattice_vertices() for l in model_a.last_level_lattices]
-        assert step.last_vertex_counts() == nv_levels
-        assert all(n <= b for n, b in zip(nv_levels, bounds))
-        assert abs(loss_a.item() - loss_b.item()) <= 2e-3 * abs(loss_a.item())
-        checked = 0
-        for (name, pa), pb in zip(model_a.named_parameters(), model_b.parameters()):
-            if pa.grad is None:
+        matched = False
+        eager_runs = {}
+        for attempt in range(40):
+            # graph replay
+            loss_b = step(pos, vals, labels)
+            replays += 1
+            torch.cuda.synchronize()
+            key0_b = tuple(model_b.last_level1_lattice.hash_table().m_keys_tensor[0].tolist())
+            grads_b = [p.grad.detach().clone() for p in model_b.parameters()]
+            # eager dynamic-shape run (kept per vertex-0 key, so later replays can match earlier eager runs)
+            if key0_b not in eager_runs:
+                logsm, _ = model_a(lat_a, pos, vals)
+                loss_a = segmentation_loss(logsm, labels)
+                for p in model_a.parameters():
+                    p.grad = None
+                loss_a.backward()
+                key0_a = tuple(model_a.last_level1_lattice.hash_table().m_keys_tensor[0].tolist())
+                nv_levels = [l.nr_lattice_vertices() for l in model_a.last_level_lattices]
+                assert step.last_vertex_counts() == nv_levels
+                assert all(n <= b for n, b in zip(nv_levels, bounds))
+                eager_runs[key0_a] = (loss_a.item(), [None if p.grad is None else p.grad.detach().clone() for p in model_a.parameters()])
+            if key0_b not in eager_runs:
                 continue
-            assert_close(pb.grad.cpu().numpy(), pa.grad.cpu().numpy(), 2e-2, f"graphed gradient of {name}")
-            checked += 1
-        assert checked > 100
-        assert any(not torch.equal(x, p.detach()) for x, p in zip(before, model_b.parameters())), "optimizer step did not run"
-        # keep the two models in lock step for the next cloud
-        with torch.no_grad():
-            for pa, pb in zip(model_a.parameters(), model_b.parameters()):
-                pa.copy_(pb)
+            loss_a_val, grads_a = eager_runs[key0_b]
+            assert abs(loss_a_val - loss_b.item()) <= 1e-4 * abs(loss_a_val)
+            checked = 0
+            for (name, _), ga, gb in zip(model_a.named_parameters(), grads_a, grads_b):
+                if ga is None:
+                    continue
+                assert_close(gb.cpu().numpy(), ga.cpu().numpy(), 5e-3, f"graphed gradient of {name}")
+                checked += 1
+            assert checked > 100
+            matched = True
+            break
+        assert matched, "eager and graphed runs never numbered the same vertex 0 in 40 attempts"
     assert step.overflowed_steps() == 0
+    steps = {int(st["step"].item()) for st in opt_b.state.values()}
+    assert steps == {replays}, "the optimizer step inside the graph did not run once per replay"
