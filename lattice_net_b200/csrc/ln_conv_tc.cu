@@ -123,7 +123,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 producer warps of conv_tc2
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -365,7 +365,9 @@ conv_fwd_tc_kernel(const float* __restrict__ values, const int* __restrict__ nei
 
 
 // ---- persistent, cp.async-fed kernel (v2) -----------------------------------------------------------
-constexpr int kTc2Threads = 288;
+constexpr int kTc2ProducerWarps = 8;
+constexpr int kTc2Producers = kTc2ProducerWarps * 32;
+constexpr int kTc2Threads = kTc2Producers + 32 + 128;   // producers, MMA warp, 4 epilogue warps
 constexpr int kMaxStages = 6;
 
 struct Tc2Item {   // one unit of work of a persistent CTA
@@ -412,7 +414,7 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
     while ((int)tmem_cols < 2 * n_pad) tmem_cols <<= 1;       // two accumulator buffers
     if (tid == 0) {
         for (int s = 0; s < stages; s++) {
-            mbar_init(full_bar(s), 128 + 1);   // 128 producer threads + the expect_tx arrival for B
+            mbar_init(full_bar(s), kTc2Producers + 1);   // the producer threads + the expect_tx arrival for B
             mbar_init(empty_bar(s), 1);        // one tcgen05.commit
         }
         for (int a = 0; a < 2; a++) {
@@ -421,7 +423,7 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
         }
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+    if (warp == kTc2ProducerWarps) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -431,80 +433,120 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
     const int total_kb = F * cpb;
     const bool split_k = n_items > m_tiles;
 
-    if (warp < 4) {
-        // ================= producers =================
+    if (warp < kTc2ProducerWarps) {
+        // ================= producers (8 warps: the loop is instruction-bound, two warps per scheduler) =================
+        // All per-block state (stage address, barrier address, phase, slot / channel-block position, B source) is
+        // advanced incrementally: no division, no 64-bit multiply and no stage arithmetic inside the K loop.
         const int chunk = tid & 7;
-        const int row0 = tid >> 3;           // this thread's rows: row0 + 16*i; (row & 7) is the same for all of them
+        const int row0 = tid >> 3;           // this thread's rows: row0 + 32*i, i < 4; (row & 7) is the same for all of them
         const uint32_t my_off = (uint32_t)row0 * kRowBytes + (uint32_t)((chunk ^ (row0 & 7)) << 4);
-        const int per_thread = (kTileM * F + 127) / 128;      // neighbour ids staged per thread and item (<= 13)
+        const int tile_ids = kTileM * F;
+        const int row_stride = 32 * F;       // neighbour ids between two of this thread's rows
+        const int per_thread = (tile_ids + kTc2Producers - 1) / kTc2Producers;      // ids staged per thread and item (<= 7)
         int ibuf = 0;
-        // neighbour ids of the first item
-        if ((int)blockIdx.x < n_items) {
+        {   // neighbour ids of the first item
             const Tc2Item w = tc2_item(blockIdx.x, m_tiles, total_kb, kb_per_split);
-            for (int i = tid; i < kTileM * F; i += 128) {
+            for (int i = tid; i < tile_ids; i += kTc2Producers) {
                 const int q = w.q0 + i / F;
                 nbr_sh[i] = (q < nv_query) ? __ldg(neighbours + (size_t)w.q0 * F + i) : -1;
             }
         }
         producer_bar_sync();
-        int g = 0;                           // K blocks issued so far by this CTA (all items)
-        auto publish = [&](int b) {          // block b has landed in this thread's view: finish it and signal the MMA lane
-            const int s = b % stages;
+        const uint32_t ring_end = base_u32 + (uint32_t)stages * stage_bytes;
+        uint32_t issue_addr = base_u32, issue_full = full_bar(0), issue_empty = empty_bar(0), issue_phase = 0;   // next block to issue
+        uint32_t pub_addr = base_u32, pub_full = full_bar(0);                                                  // next block to publish
+        int in_flight = 0;
+        const float* col0 = values + chunk * 4;
+        const size_t b_block = (size_t)n_pad * kBlockK;          // floats of one B slab
+        auto publish = [&]() {               // the oldest in-flight block has landed in this thread's view: finish it, signal the MMA lane
             if (kSplit) {
-                const uint32_t hi = a_hi(s) + my_off, lo = a_lo(s) + my_off;
+                const uint32_t hi = pub_addr + my_off, lo = pub_addr + kATileBytes + my_off;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const float4 x = lds128(hi + (uint32_t)i * 16u * kRowBytes);
+                for (int i = 0; i < 4; i++) {
+                    const float4 x = lds128(hi + (uint32_t)i * 32u * kRowBytes);
                     if (truncating_operand) {     // the tensor core drops the 13 low mantissa bits of the raw fp32 operand itself
-                        sts128(lo + (uint32_t)i * 16u * kRowBytes,
+                        sts128(lo + (uint32_t)i * 32u * kRowBytes,
                                make_float4(tf32_residual(x.x), tf32_residual(x.y), tf32_residual(x.z), tf32_residual(x.w)));
                     } else {                       // explicit round-to-nearest high part, independent of the operand read-out
                         const float4 h = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
-                        sts128(hi + (uint32_t)i * 16u * kRowBytes, h);
-                        sts128(lo + (uint32_t)i * 16u * kRowBytes,
+                        sts128(hi + (uint32_t)i * 32u * kRowBytes, h);
+                        sts128(lo + (uint32_t)i * 32u * kRowBytes,
                                make_float4(to_tf32(x.x - h.x), to_tf32(x.y - h.y), to_tf32(x.z - h.z), to_tf32(x.w - h.w)));
                     }
                 }
             }
             fence_proxy_async();             // generic-proxy writes (cp.async data, lo tile) -> visible to the tensor-core proxy
-            mbar_arrive(full_bar(s));
+            mbar_arrive(pub_full);
+            pub_addr += stage_bytes;
+            pub_full += 8;
+            if (pub_addr == ring_end) {
+                pub_addr = base_u32;
+                pub_full = full_bar(0);
+            }
+            in_flight--;
         };
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const Tc2Item w = tc2_item(item, m_tiles, total_kb, kb_per_split);
-            const int* ids = nbr_sh + ibuf * (kTileM * F);
+            const int* ids = nbr_sh + ibuf * tile_ids + row0 * F;
             // prefetch the next item's neighbour ids into registers (stored to the other buffer at the end of this item)
-            int next_ids[13];
+            int next_ids[7];
             const int next = item + gridDim.x;
             if (next < n_items) {
                 const Tc2Item wn = tc2_item(next, m_tiles, total_kb, kb_per_split);
 #pragma unroll
-                for (int j = 0; j < 13; j++) {
-                    const int i = tid + 128 * j;
+                for (int j = 0; j < 7; j++) {
+                    const int i = tid + kTc2Producers * j;
                     next_ids[j] = -1;
-                    if (j < per_thread && i < kTileM * F && wn.q0 + i / F < nv_query) next_ids[j] = __ldg(neighbours + (size_t)wn.q0 * F + i);
+                    if (j < per_thread && i < tile_ids && wn.q0 + i / F < nv_query) next_ids[j] = __ldg(neighbours + (size_t)wn.q0 * F + i);
                 }
             }
-            for (int it = 0; it < w.num_kb; it++, g++) {
-                const int kb = w.kb_begin + it;
-                const int s = g % stages;
-                mbar_wait(empty_bar(s), (((uint32_t)(g / stages)) & 1u) ^ 1u);
-                if (tid == 0) {
-                    mbar_arrive_expect_tx(full_bar(s), (kSplit ? 2u : 1u) * b_tile_bytes);
-                    bulk_copy_g2s(b_hi_s(s), b_hi + (size_t)kb * n_pad * kBlockK, b_tile_bytes, full_bar(s));
-                    if (kSplit) bulk_copy_g2s(b_lo_s(s), b_lo + (size_t)kb * n_pad * kBlockK, b_tile_bytes, full_bar(s));
-                }
-                const int slot = kb / cpb;
-                const int cb = kb - slot * cpb;
-                const int src_slot = (flip && slot < F - 1) ? (slot ^ 1) : slot;
-                const uint32_t dst = a_hi(s) + my_off;
-                const float* col = values + (size_t)cb * kBlockK + chunk * 4;
+            int slot = w.kb_begin / cpb;
+            int cb = w.kb_begin - slot * cpb;
+            const float* b_src_hi = b_hi + (size_t)w.kb_begin * b_block;
+            const float* b_src_lo = b_lo + (size_t)w.kb_begin * b_block;
+            int id[4];
+            bool reload = true;
+            for (int it = 0; it < w.num_kb; it++) {
+                if (reload) {                // a new filter slot: this thread's four neighbour ids change
+                    const int src_slot = (flip && slot < F - 1) ? (slot ^ 1) : slot;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int id = ids[(row0 + 16 * i) * F + src_slot];
-                    cp_async16(dst + (uint32_t)i * 16u * kRowBytes, id >= 0 ? col + (size_t)id * c_in : values, id >= 0 ? 16u : 0u);
+                    for (int i = 0; i < 4; i++) id[i] = ids[i * row_stride + src_slot];
+                    reload = false;
+                }
+                mbar_wait(issue_empty, issue_phase ^ 1u);
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(issue_full, (kSplit ? 2u : 1u) * b_tile_bytes);
+                    bulk_copy_g2s(issue_addr + (kSplit ? 2 : 1) * kATileBytes, b_src_hi, b_tile_bytes, issue_full);
+                    if (kSplit) bulk_copy_g2s(issue_addr + 2 * kATileBytes + b_tile_bytes, b_src_lo, b_tile_bytes, issue_full);
+                }
+                const uint32_t dst = issue_addr + my_off;
+                const float* col = col0 + cb * kBlockK;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const bool have = id[i] >= 0;
+                    const float* src = have ? col + (unsigned long long)(unsigned)id[i] * (unsigned)c_in : values;   // mul.wide.u32
+                    cp_async16(dst + (uint32_t)i * 32u * kRowBytes, src, have ? 16u : 0u);
                 }
                 cp_async_commit();
-                if (g >= lookahead) {
+                in_flight++;
+                // advance the issue state
+                b_src_hi += b_block;
+                b_src_lo += b_block;
+                if (++cb == cpb) {
+                    cb = 0;
+                    slot++;
+                    reload = true;
+                }
+                issue_addr += stage_bytes;
+                issue_full += 8;
+                issue_empty += 8;
+                if (issue_addr == ring_end) {
+                    issue_addr = base_u32;
+                    issue_full = full_bar(0);
+                    issue_empty = empty_bar(0);
+                    issue_phase ^= 1u;
+                }
+                if (in_flight > lookahead) {
                     switch (lookahead) {     // cp.async.wait_group takes an immediate
                         case 1: cp_async_wait<1>(); break;
                         case 2: cp_async_wait<2>(); break;
@@ -512,23 +554,23 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
                         case 4: cp_async_wait<4>(); break;
                         default: cp_async_wait<5>(); break;
                     }
-                    publish(g - lookahead);
+                    publish();
                 }
             }
             if (next < n_items) {
-                int* dst_ids = nbr_sh + (ibuf ^ 1) * (kTileM * F);
+                int* dst_ids = nbr_sh + (ibuf ^ 1) * tile_ids;
 #pragma unroll
-                for (int j = 0; j < 13; j++) {
-                    const int i = tid + 128 * j;
-                    if (j < per_thread && i < kTileM * F) dst_ids[i] = next_ids[j];
+                for (int j = 0; j < 7; j++) {
+                    const int i = tid + kTc2Producers * j;
+                    if (j < per_thread && i < tile_ids) dst_ids[i] = next_ids[j];
                 }
             }
             producer_bar_sync();
             ibuf ^= 1;
         }
         cp_async_wait<0>();
-        for (int b = max(0, g - lookahead); b < g; b++) publish(b);
-    } else if (warp == 4) {
+        while (in_flight > 0) publish();
+    } else if (warp == kTc2ProducerWarps) {
         // ================= MMA issuer (one lane) =================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(kTileM, n_pad);
@@ -565,7 +607,7 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
         }
         __syncwarp();
     } else {
-        // ================= epilogue (warps 5-8; TMEM lane quadrant = warp % 4) =================
+        // ================= epilogue (4 warps; TMEM lane quadrant = warp % 4) =================
         const int quad = warp & 3;
         int j = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, j++) {
@@ -622,7 +664,7 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kTc2ProducerWarps) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
     }
@@ -661,23 +703,25 @@ static int sm_count() {
 // ---- weight gradient on the tensor cores -------------------------------------------------------------
 //   grad_filter[slot*c_in + ci, co] = sum_q values[nbr[q, slot], ci] * grad_out[q, co]
 // per slot a GEMM  D[c_in x c_out] = A^T[c_in x nv] . G[nv x c_out]  whose reduction runs over the VERTICES.
-// Both operands sit in shared memory exactly as they sit in HBM -- one 128-byte row segment (32 channels) per
-// vertex, 128B-swizzled by the row -- which is the MN-major UMMA layout (channels contiguous, K = vertices down
-// the rows), so the gather needs no transposition: M = 128 channels of c_in (4 groups of 32), N = c_out (groups
-// of 32), K = 8 vertices per tcgen05.mma, 32 vertices per pipeline stage.
+// Both operands sit in shared memory the way they sit in HBM -- one 128-byte row segment (32 channels) per
+// vertex -- which is the MN-major UMMA layout (channels contiguous, K = vertices down the rows), so the gather
+// needs no transposition.  32-bit MN-major operands must use the SWIZZLE_128B_BASE32B pattern: the four 32-byte
+// units of a row are XOR-ed with (row & 3), period 4 rows.  M = 128 channels of c_in (4 groups of 32), N = c_out
+// (groups of 32), K = 8 vertices per tcgen05.mma, 32 vertices per pipeline stage.
 // Work item = (slot, 128-channel tile of c_in, vertex range); partial sums of different vertex ranges are
 // combined with vector fp32 atomics into the pre-zeroed gradient.
-constexpr int kWgRows = 32;                       // vertices per stage
+constexpr int kWgRows = 32;                          // vertices per stage
 constexpr int kWgGroupBytes = kWgRows * kRowBytes;   // one 32-channel group of a stage: 4 KB
-constexpr int kWgThreads = 160;
+constexpr int kWgProducers = 256;                    // 8 lanes per vertex row (one 16-byte chunk each), 32 rows
+constexpr int kWgThreads = kWgProducers + 32;
 
-__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128_32b(uint32_t smem_addr) {
     uint64_t desc = 0;
     desc |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address, 16-byte units
     desc |= (uint64_t)(kWgGroupBytes >> 4) << 16;             // leading byte offset: next 32-channel (MN) group
-    desc |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset: next 8 vertices (K)
+    desc |= (uint64_t)(512 >> 4) << 32;                       // stride byte offset: next 4 vertices (one swizzle period down K)
     desc |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
-    desc |= (uint64_t)2 << 61;                                // layout type: SWIZZLE_128B
+    desc |= (uint64_t)1 << 61;                                // layout type: SWIZZLE_128B_BASE32B
     return desc;
 }
 __device__ __forceinline__ uint32_t umma_idesc_tf32_mn(int m, int n) {   // as umma_idesc_tf32, A and B MN-major
@@ -694,7 +738,7 @@ conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ n
     const int n_groups = (n_pad + 31) / 32;
     const uint32_t a_bytes = 4u * kWgGroupBytes;                       // 128 channels x 32 vertices = 16 KB
     const uint32_t g_bytes = (uint32_t)n_groups * kWgGroupBytes;
-    const uint32_t stage_bytes = (kSplit ? 2 : 1) * (a_bytes + g_bytes);
+    const uint32_t stage_bytes = (kSplit ? 2 : 1) * (a_bytes + g_bytes);   // [A hi | G hi | A lo | G lo]
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(base + (size_t)stages * stage_bytes);
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kMaxStages + 1);
@@ -707,10 +751,7 @@ conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ n
     auto full_bar = [&](int s) { return bars_u32 + 8u * (uint32_t)s; };
     auto empty_bar = [&](int s) { return bars_u32 + 8u * (uint32_t)(kMaxStages + s); };
     const uint32_t accum_bar = bars_u32 + 8u * (uint32_t)(2 * kMaxStages);
-    auto a_hi = [&](int s) { return base_u32 + (uint32_t)s * stage_bytes; };
-    auto g_hi = [&](int s) { return a_hi(s) + a_bytes; };
-    auto a_lo = [&](int s) { return g_hi(s) + g_bytes; };
-    auto g_lo = [&](int s) { return a_lo(s) + a_bytes; };
+    const uint32_t lo_off = a_bytes + g_bytes;                          // hi -> lo copy of the same tile
 
     // work item
     int item = blockIdx.x;
@@ -728,66 +769,84 @@ conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ n
     while ((int)tmem_cols < n_pad) tmem_cols <<= 1;
     if (tid == 0) {
         for (int s = 0; s < stages; s++) {
-            mbar_init(full_bar(s), 128);
+            mbar_init(full_bar(s), kWgProducers);
             mbar_init(empty_bar(s), 1);
         }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
-        // ================= producers: 8 lanes per vertex row (one 16-byte chunk each), 16 rows per pass =================
+    if (warp < 8) {
+        // ================= producers: one vertex row per thread-octet =================
         const int cc = tid & 7;                   // 16-byte chunk inside a 128-byte group row
-        const int r0 = tid >> 3;                  // rows r0 and r0 + 16 of the stage
+        const int r = tid >> 3;                   // row of the stage
         const int a_groups = ci_n / 32;
-        auto publish = [&](int b) {
-            const int s = b % stages;
+        // SWIZZLE_128B_BASE32B: 32-byte unit (cc >> 1) goes to unit (cc >> 1) ^ (r & 3); the 16-byte half keeps its place
+        const uint32_t my_off = (uint32_t)r * kRowBytes + (uint32_t)((((cc >> 1) ^ (r & 3)) << 5) | ((cc & 1) << 4));
+        const uint32_t ring_end = base_u32 + (uint32_t)stages * stage_bytes;
+        uint32_t issue_addr = base_u32, issue_full = full_bar(0), issue_empty = empty_bar(0), issue_phase = 0;
+        uint32_t pub_addr = base_u32, pub_full = full_bar(0);
+        int in_flight = 0;
+        auto publish = [&]() {
             if (kSplit) {
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int r = r0 + 16 * h;
-                    const uint32_t off = (uint32_t)r * kRowBytes + (uint32_t)((cc ^ (r & 7)) << 4);
-                    for (int grp = 0; grp < a_groups + n_groups; grp++) {
-                        const bool is_a = grp < a_groups;
-                        const uint32_t hi = (is_a ? a_hi(s) + (uint32_t)grp * kWgGroupBytes : g_hi(s) + (uint32_t)(grp - a_groups) * kWgGroupBytes) + off;
-                        const uint32_t lo = (is_a ? a_lo(s) + (uint32_t)grp * kWgGroupBytes : g_lo(s) + (uint32_t)(grp - a_groups) * kWgGroupBytes) + off;
-                        const float4 x = lds128(hi);
-                        const float4 hv = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
-                        sts128(hi, hv);
-                        sts128(lo, make_float4(to_tf32(x.x - hv.x), to_tf32(x.y - hv.y), to_tf32(x.z - hv.z), to_tf32(x.w - hv.w)));
-                    }
+                const uint32_t hi0 = pub_addr + my_off;
+                for (int grp = 0; grp < 4 + n_groups; grp++) {              // A groups then G groups are contiguous 4 KB blocks
+                    if (grp >= a_groups && grp < 4) continue;               // channels past c_in: never gathered, never stored
+                    const uint32_t hi = hi0 + (uint32_t)grp * kWgGroupBytes;
+                    const float4 x = lds128(hi);
+                    const float4 hv = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
+                    sts128(hi, hv);
+                    sts128(hi + lo_off, make_float4(to_tf32(x.x - hv.x), to_tf32(x.y - hv.y), to_tf32(x.z - hv.z), to_tf32(x.w - hv.w)));
                 }
             }
             fence_proxy_async();
-            mbar_arrive(full_bar(s));
+            mbar_arrive(pub_full);
+            pub_addr += stage_bytes;
+            pub_full += 8;
+            if (pub_addr == ring_end) {
+                pub_addr = base_u32;
+                pub_full = full_bar(0);
+            }
+            in_flight--;
         };
+        int q = chunk_begin * kWgRows + r;
+        const int* nbr_p = neighbours + (size_t)q * F + slot;
+        const float* g_p = grad_out + (size_t)q * c_out + cc * 4;
+        const float* a_col = values + ci0 + cc * 4;
         for (int g = 0; g < num_chunks; g++) {
-            const int s = g % stages;
-            mbar_wait(empty_bar(s), (((uint32_t)(g / stages)) & 1u) ^ 1u);
-            const int qbase = (chunk_begin + g) * kWgRows;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int r = r0 + 16 * h;
-                const int q = qbase + r;
-                const uint32_t off = (uint32_t)r * kRowBytes + (uint32_t)((cc ^ (r & 7)) << 4);
-                int id = -1;
-                if (q < nv_query) id = __ldg(neighbours + (size_t)q * F + slot);
-                const float* arow = values + (size_t)(id >= 0 ? id : 0) * c_in + ci0 + cc * 4;
-                for (int grp = 0; grp < a_groups; grp++)
-                    cp_async16(a_hi(s) + (uint32_t)grp * kWgGroupBytes + off, arow + grp * 32, id >= 0 ? 16u : 0u);
-                const float* grow = grad_out + (size_t)(q < nv_query ? q : 0) * c_out + cc * 4;
-                for (int grp = 0; grp < n_groups; grp++) {
-                    const bool ok = q < nv_query && grp * 32 + cc * 4 < c_out;      // c_out % 4 == 0: whole chunks only
-                    cp_async16(g_hi(s) + (uint32_t)grp * kWgGroupBytes + off, ok ? grow + grp * 32 : grad_out, ok ? 16u : 0u);
-                }
+            mbar_wait(issue_empty, issue_phase ^ 1u);
+            const bool in_range = q < nv_query;
+            int id = -1;
+            if (in_range) id = __ldg(nbr_p);
+            const bool have = id >= 0;
+            const float* arow = have ? a_col + (unsigned long long)(unsigned)id * (unsigned)c_in : values;
+            const uint32_t dst = issue_addr + my_off;
+            for (int grp = 0; grp < a_groups; grp++)
+                cp_async16(dst + (uint32_t)grp * kWgGroupBytes, have ? arow + grp * 32 : values, have ? 16u : 0u);
+            for (int grp = 0; grp < n_groups; grp++) {
+                const bool ok = in_range && grp * 32 + cc * 4 < c_out;      // c_out % 4 == 0: whole chunks only
+                cp_async16(dst + a_bytes + (uint32_t)grp * kWgGroupBytes, ok ? g_p + grp * 32 : grad_out, ok ? 16u : 0u);
             }
             cp_async_commit();
-            if (g >= lookahead) {
+            in_flight++;
+            q += kWgRows;
+            nbr_p += (size_t)kWgRows * F;
+            g_p += (size_t)kWgRows * c_out;
+            issue_addr += stage_bytes;
+            issue_full += 8;
+            issue_empty += 8;
+            if (issue_addr == ring_end) {
+                issue_addr = base_u32;
+                issue_full = full_bar(0);
+                issue_empty = empty_bar(0);
+                issue_phase ^= 1u;
+            }
+            if (in_flight > lookahead) {
                 switch (lookahead) {
                     case 1: cp_async_wait<1>(); break;
                     case 2: cp_async_wait<2>(); break;
@@ -795,14 +854,14 @@ conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ n
                     case 4: cp_async_wait<4>(); break;
                     default: cp_async_wait<5>(); break;
                 }
-                publish(g - lookahead);
+                publish();
             }
         }
         cp_async_wait<0>();
-        for (int b = max(0, num_chunks - lookahead); b < num_chunks; b++) publish(b);
+        while (in_flight > 0) publish();
 
-        // ================= epilogue: TMEM lane = channel of the tile, columns = c_out =================
-        if (num_chunks > 0) {
+        // ================= epilogue (warps 0-3): TMEM lane = channel of the tile, columns = c_out =================
+        if (warp < 4 && num_chunks > 0) {
             mbar_wait(accum_bar, 0);
             tc_fence_after();
             const int m = warp * 32 + lane;
@@ -829,16 +888,16 @@ conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ n
         // ================= MMA issuer =================
         if (lane == 0 && num_chunks > 0) {
             const uint32_t idesc = umma_idesc_tf32_mn(128, n_pad);
+            uint32_t addr = base_u32, full = full_bar(0), empty = empty_bar(0), phase = 0;
             for (int g = 0; g < num_chunks; g++) {
-                const int s = g % stages;
-                mbar_wait(full_bar(s), ((uint32_t)(g / stages)) & 1u);
+                mbar_wait(full, phase);
                 tc_fence_after();
-                const uint64_t da_hi = umma_desc_mnmajor_sw128(a_hi(s));
-                const uint64_t dg_hi = umma_desc_mnmajor_sw128(g_hi(s));
-                const uint64_t da_lo = umma_desc_mnmajor_sw128(a_lo(s));
-                const uint64_t dg_lo = umma_desc_mnmajor_sw128(g_lo(s));
+                const uint64_t da_hi = umma_desc_mnmajor_sw128_32b(addr);
+                const uint64_t dg_hi = umma_desc_mnmajor_sw128_32b(addr + a_bytes);
+                const uint64_t da_lo = umma_desc_mnmajor_sw128_32b(addr + lo_off);
+                const uint64_t dg_lo = umma_desc_mnmajor_sw128_32b(addr + lo_off + a_bytes);
 #pragma unroll
-                for (int ks = 0; ks < kWgRows / 8; ks++) {       // 8 vertices per MMA = one 1024-byte swizzle atom down the rows
+                for (int ks = 0; ks < kWgRows / 8; ks++) {       // 8 vertices per MMA = two 512-byte swizzle periods down the rows
                     const uint64_t adv = (uint64_t)(ks * (1024 >> 4));
                     if (kSplit) {
                         umma_tf32(tmem_base, da_lo + adv, dg_hi + adv, idesc, (g | ks) != 0 ? 1u : 0u);
@@ -848,7 +907,16 @@ conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ n
                         umma_tf32(tmem_base, da_hi + adv, dg_hi + adv, idesc, (g | ks) != 0 ? 1u : 0u);
                     }
                 }
-                umma_commit(empty_bar(s));
+                umma_commit(empty);
+                addr += stage_bytes;
+                full += 8;
+                empty += 8;
+                if (addr == base_u32 + (uint32_t)stages * stage_bytes) {
+                    addr = base_u32;
+                    full = full_bar(0);
+                    empty = empty_bar(0);
+                    phase ^= 1u;
+                }
             }
             umma_commit(accum_bar);
         }
@@ -856,7 +924,7 @@ conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ n
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
     }

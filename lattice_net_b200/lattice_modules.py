@@ -99,6 +99,12 @@ class _GroupNormReLU(torch.autograd.Function):
 # one CTA per group: meant for the lattice sizes where launch count, not bandwidth, is the cost
 FUSED_NORM_MAX_ELEMS_PER_GROUP = 1 << 17
 
+# The reference treats lattice vertex 0 as the "invalid" row: points whose index was clamped from -1 land there,
+# so its mean / features are zeroed (lattice_modules.py:72-94, 683, 712).  Which real vertex gets id 0 is a race
+# of the hash insert, in the reference as here, which makes model outputs differ from run to run.  True keeps the
+# reference behaviour; tests that compare two independent runs switch it off to get a numbering-invariant model.
+REFERENCE_VERTEX0_QUIRK = True
+
 
 # --------------------------------------------------------------------------------------------------
 # weight normalisation with a per-output gain and a whole-tensor norm: what the reference's
@@ -167,10 +173,12 @@ class DistributeLatticeModule(torch.nn.Module):
         pos_cols = distributed[:, :d].contiguous()
         sums, counts = scatter_sum_count(pos_cols, idx, nv)
         mean = sums / counts.clamp(min=1.0).unsqueeze(1)
-        mean[0] = 0.0                                  # vertex 0 doubles as the "invalid" row in the reference
         idx_long = idx.long()
+        if REFERENCE_VERTEX0_QUIRK:
+            mean[0] = 0.0                              # vertex 0 doubles as the "invalid" row in the reference
         distributed[:, :d] = pos_cols - mean.index_select(0, idx_long)
-        distributed = distributed.masked_fill((idx_long == 0).unsqueeze(1), 0.0)
+        if REFERENCE_VERTEX0_QUIRK:
+            distributed = distributed.masked_fill((idx_long == 0).unsqueeze(1), 0.0)
         return dist_lattice, distributed, indices, weights
 
 
@@ -433,9 +441,10 @@ class PointNetModule(torch.nn.Module):
         bary_reduced = bary_pad.index_select(0, argmax.flatten().long()).view(argmax.shape)
         reduced = torch.cat((reduced, bary_reduced), 1)
         reduced = reduced.masked_fill((counts < 4).unsqueeze(1), 0.0)   # vertices touched by < 4 points
-        keep = torch.ones((nv, 1), device=x.device)
-        keep[0] = 0.0                                                    # row 0 collects the invalid points
-        reduced = reduced * keep
+        if REFERENCE_VERTEX0_QUIRK:
+            keep = torch.ones((nv, 1), device=x.device)
+            keep[0] = 0.0                                                # row 0 collects the invalid points
+            reduced = reduced * keep
         lattice_py.set_values(reduced)
         lv, ls = self.last_conv(reduced, lattice_py)
         lv = self.act(lv)

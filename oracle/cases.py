@@ -42,3 +42,36 @@ CASES = {
 
 def randn(shape, seed):
     return np.random.RandomState(seed).randn(*shape).astype(np.float32)
+
+
+def kitti_like(n, seed):
+    """SemanticKITTI-sized lidar-like scan (BASELINE configs[2]): range concentrated near the
+    sensor (2 m + exponential, clipped at 60 m), 70 % of the returns on the ground plane z = -1.7 +- 0.05,
+    the rest between the ground and 3 m.  With sigma 0.9 this stays well below the cfg's 100 000-slot table."""
+    rng = np.random.RandomState(seed)
+    r = np.minimum(2.0 + rng.exponential(9.0, n), 60.0)
+    a = rng.uniform(0.0, 2.0 * np.pi, n)
+    ground = rng.rand(n) < 0.7
+    z = np.where(ground, -1.7 + rng.randn(n) * 0.05, rng.uniform(-1.7, 3.0, n))
+    return np.stack([r * np.cos(a), r * np.sin(a), z], 1).astype(np.float32)
+
+
+def scannet_like(n, seed):
+    """ScanNet-sized indoor scene (BASELINE configs[3]): points on the faces of an 8 x 6 x 3 m room
+    plus random boxes (furniture); values = rgb (3) + height (1)."""
+    rng = np.random.RandomState(seed)
+    room = np.array([8.0, 6.0, 3.0])
+    nb = n // 3
+    p = box_surface(n - nb, seed + 1, size=room).astype(np.float64) + room / 2
+    boxes = []
+    per = nb // 8
+    for b in range(8):
+        size = rng.uniform(0.4, 1.6, 3) * np.array([1.0, 1.0, 0.6])
+        centre = np.array([rng.uniform(1, 7), rng.uniform(1, 5), size[2] / 2])
+        m = per if b < 7 else nb - 7 * per
+        boxes.append(box_surface(m, seed + 10 + b, size=size).astype(np.float64) + centre)
+    p = np.concatenate([p] + boxes, 0)
+    p = p[rng.permutation(len(p))]
+    rgb = rng.rand(len(p), 3)
+    vals = np.concatenate([rgb, p[:, 2:3] / 3.0], 1)
+    return p.astype(np.float32), vals.astype(np.float32)
