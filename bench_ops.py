@@ -67,21 +67,31 @@ def emit(op, cfg, sec, nbytes=None, flops=None, ref_sec=None, extra=None):
     print(json.dumps(rec), flush=True)
 
 
-def uniform_cloud(n, d, seed, target_ratio=0.5):
-    """n points uniform in a cube sized so that nv ~ target_ratio * n * ... (nv ~ N/2)."""
+def uniform_cloud(n, d, seed, order="random"):
+    """n points uniform in the unit cube (sigma is then tuned so that nv ~ N/2).
+    order="morton": the same points sorted along a Z-order curve of their first three coordinates -- the
+    ordering a spatially coherent scan (lidar sweep, mesh sampling) has; neighbouring points then share
+    lattice vertices, which is what lets the gathers hit in L1 instead of L2."""
     rng = np.random.RandomState(seed)
     pos = rng.rand(n, d).astype(np.float32)
-    return pos
+    if order == "morton":
+        q = np.minimum((pos[:, :3] * 1024).astype(np.uint64), 1023)
+        code = np.zeros(n, np.uint64)
+        for bit in range(10):
+            for a in range(3):
+                code |= ((q[:, a] >> np.uint64(bit)) & np.uint64(1)) << np.uint64(3 * bit + a)
+        pos = pos[np.argsort(code, kind="stable")]
+    return np.ascontiguousarray(pos)
 
 
-def run(n, d, vals, quick):
+def run(n, d, vals, quick, order="random"):
     from lattice_net_b200 import Lattice, lattice as lm
     from lattice_net_b200._cabi import call, ptr, stream_ptr
     from oracle import ref_cuda
     have_ref = ref_cuda.available()
     dev = torch.device("cuda", 0)
     # sigma so that nv ~ n/2: vertices ~ (d+1)! * volume/sigma^d density; tune by a coarse search
-    pos = torch.from_numpy(uniform_cloud(n, d, 0)).to(dev)
+    pos = torch.from_numpy(uniform_cloud(n, d, 0, order)).to(dev)
     cap = int(4 * n)
     sigma = (1.0 / n) ** (1.0 / d) * (2.2 if d == 3 else 1.6)
     for _ in range(6):
@@ -95,7 +105,7 @@ def run(n, d, vals, quick):
             sigma *= 0.85
         else:
             break
-    cfg0 = {"n": n, "pos_dim": d, "nv": nv, "capacity": cap, "sigma": round(sigma, 5)}
+    cfg0 = {"n": n, "pos_dim": d, "nv": nv, "capacity": cap, "sigma": round(sigma, 5), "point_order": order}
     st = lat.hash_table().structure
     sig = lat._sigmas_on(dev)
 
@@ -200,9 +210,10 @@ def main():
     ap.add_argument("--n", type=int, nargs="*", default=[100000, 1000000])
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--vals", type=int, nargs="*", default=None)
+    ap.add_argument("--order", default="random", choices=["random", "morton"], help="point order of the synthetic cloud")
     args = ap.parse_args()
     for n in args.n:
-        run(n, 3, args.vals if args.vals else ([8, 32, 64] if args.quick else [1, 8, 32, 64, 128]), args.quick)
+        run(n, 3, args.vals if args.vals else ([8, 32, 64] if args.quick else [1, 8, 32, 64, 128]), args.quick, args.order)
     if not args.quick:
         run(args.n[-1] // 2, 5, [8, 32], True)
 

@@ -14,6 +14,10 @@ namespace ln {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 void count_launch(int n = 1);
+cudaError_t allow_max_smem(const void* kernel);   // ln_conv_tc.cu: opt a kernel into 227 KB dynamic smem, once per device
+// rows[idx[p,r], :] += src[p, :] * w[p,r]  (ln_slice.cu; shared by ln_slice_bwd and ln_splat_accumulate)
+int launch_scatter_rows(const float* src, const int* indices, const float* weights, int n, int pos_dim, int val_dim,
+                        float* rows, cudaStream_t s, const char* what);
 
 #define LN_REQUIRE(cond, ...)                 \
     do {                                      \

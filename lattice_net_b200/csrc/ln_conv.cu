@@ -5,6 +5,8 @@
 // Reference: Lattice::convolve_im2row_standalone (/root/reference/src/Lattice.cu:424-474) =
 // im2row kernel (LatticeGPU.cuh:1464-1688) + cuBLAS SGEMM; backward algebra in
 // /root/reference/latticenet_py/lattice/lattice_funcs.py:294-313.
+#include <cstdlib>
+#include <mutex>
 #include "ln_common.cuh"
 
 namespace ln {
@@ -12,7 +14,7 @@ namespace ln {
 // ln_conv_tc.cu
 int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
                 int F, int c_in, int c_out, int flip, int precision, int transposed, float* workspace, float* out,
-                float* also_zero, long long also_zero_n, cudaStream_t s);
+                float* also_zero, long long also_zero_n, cudaStream_t s, cudaEvent_t after_prep);
 size_t conv_tc_workspace_bytes(int F, int c_in, int c_out);
 bool conv_tc_supported(int F, int c_in, int c_out);
 bool conv_wgrad_tc_supported(int F, int c_in, int c_out);
@@ -204,7 +206,7 @@ int ln_conv_fwd(const float* nbr_values, const int* neighbours, const float* fil
     cudaStream_t s = (cudaStream_t)stream;
     if (precision != 0 && conv_tc_supported(filter_extent, c_in, c_out)) {
         LN_REQUIRE(workspace != nullptr, "ln_conv_fwd: precision %d needs a workspace of ln_conv_workspace_bytes() bytes", precision);
-        return conv_fwd_tc(nbr_values, neighbours, filter, bias, nv_query, filter_extent, c_in, c_out, flip, precision, transposed_filter, workspace, out, nullptr, 0, s);
+        return conv_fwd_tc(nbr_values, neighbours, filter, bias, nv_query, filter_extent, c_in, c_out, flip, precision, transposed_filter, workspace, out, nullptr, 0, s, nullptr);
     }
     dim3 grid(cdiv(nv_query, BM), cdiv(c_out, BN));
     conv_fwd_simt_kernel<<<grid, kThreads, 0, s>>>(nbr_values, neighbours, filter, bias, nv_query, filter_extent, c_in, c_out, flip, transposed_filter, out);
@@ -240,6 +242,40 @@ int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* g
     return conv_wgrad_launch(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, precision, grad_filter, false, (cudaStream_t)stream);
 }
 
+// Second stream for the weight gradient: it depends on grad_out and the forward inputs only, never on the data
+// gradient, so ln_conv_bwd runs the two kernels side by side (fork after the filter-prep kernel that clears
+// grad_filter, join before returning).  Inside a CUDA-graph capture the fork/join become graph edges.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream* side_stream() {
+    static SideStream per_device[64];
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    SideStream& ss = per_device[dev];
+    if (ss.stream == nullptr) {
+        if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) {
+            ss.stream = nullptr;
+            cudaGetLastError();
+            return nullptr;
+        }
+    }
+    return &ss;
+}
+static bool fork_enabled() {   // LN_CONV_BWD_FORK=0 keeps both gradients on the caller's stream
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LN_CONV_BWD_FORK");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 int ln_conv_bwd(const float* nbr_values, const int* neighbours_fwd, const float* grad_out, const int* neighbours_bwd,
                 const float* filter, int nv_query, int nv_nbr, int filter_extent, int c_in, int c_out, int precision,
                 float* workspace, float* grad_nbr_values, float* grad_filter, void* stream) {
@@ -254,10 +290,19 @@ int ln_conv_bwd(const float* nbr_values, const int* neighbours_fwd, const float*
         // forward bank read transposed (c_in <-> c_out)
         if (precision != 0 && conv_tc_supported(filter_extent, c_out, c_in)) {
             LN_REQUIRE(workspace != nullptr, "ln_conv_bwd: precision %d needs a workspace", precision);
+            SideStream* ss = (grad_filter != nullptr && nv_query > 0 && fork_enabled()) ? side_stream() : nullptr;
             const int rc = conv_fwd_tc(grad_out, neighbours_bwd, filter, nullptr, nv_nbr, filter_extent, c_out, c_in, 1, precision, 1,
-                                       workspace, grad_nbr_values, grad_filter, grad_filter ? nfilt : 0, s);
+                                       workspace, grad_nbr_values, grad_filter, grad_filter ? nfilt : 0, s, ss ? ss->fork : nullptr);
             if (rc != LN_OK) return rc;
             filter_zeroed = grad_filter != nullptr;
+            if (ss != nullptr) {
+                if (cudaStreamWaitEvent(ss->stream, ss->fork, 0) != cudaSuccess) return check_launch("conv_bwd fork");
+                const int rw = conv_wgrad_launch(nbr_values, neighbours_fwd, grad_out, nv_query, filter_extent, c_in, c_out, precision,
+                                                 grad_filter, true, ss->stream);
+                if (cudaEventRecord(ss->join, ss->stream) != cudaSuccess || cudaStreamWaitEvent(s, ss->join, 0) != cudaSuccess)
+                    return check_launch("conv_bwd join");
+                return rw;
+            }
         } else {
             dim3 grid(cdiv(nv_nbr, BM), cdiv(c_in, BN));
             conv_fwd_simt_kernel<<<grid, kThreads, 0, s>>>(grad_out, neighbours_bwd, filter, nullptr, nv_nbr, filter_extent, c_out, c_in, 1, 1, grad_nbr_values);

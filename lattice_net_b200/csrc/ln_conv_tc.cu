@@ -24,6 +24,9 @@
 //   warps 5-8  epilogue: tcgen05.ld (32 columns = one 128-byte line per thread) -> bias -> st.global
 //              (vector fp32 atomics when K is split across CTAs)
 #include <cstdlib>
+#include <mutex>
+#include <set>
+#include <utility>
 #include "ln_common.cuh"
 
 namespace ln {
@@ -689,6 +692,20 @@ static bool use_v1() {   // development switch: LN_CONV_TC_V1=1 selects the firs
     }
     return v == 1;
 }
+// Opt a kernel into the full 227 KB of dynamic shared memory ONCE per (kernel, device), not per launch: the call is
+// not free on the host, and an attribute change in the middle of a stream capture trips profilers.
+cudaError_t allow_max_smem(const void* kernel) {
+    static std::mutex mu;
+    static std::set<std::pair<int, const void*>> done;
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({dev, kernel})) return cudaSuccess;
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (err == cudaSuccess) done.insert({dev, kernel});
+    return err;
+}
 static int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -961,12 +978,12 @@ int conv_wgrad_tc(const float* nbr_values, const int* neighbours, const float* g
     const int grid = tiles * q_splits;
     cudaError_t err;
     if (split) {
-        err = cudaFuncSetAttribute(conv_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        err = allow_max_smem((const void*)conv_wgrad_tc_kernel<1>);
         if (err == cudaSuccess)
             conv_wgrad_tc_kernel<1><<<grid, kWgThreads, smem, s>>>(nbr_values, neighbours, grad_out, nv_query, F, c_in, c_out, n_pad, ci_tiles,
                                                                     q_splits, chunks_per_split, stages, lookahead, grad_filter);
     } else {
-        err = cudaFuncSetAttribute(conv_wgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        err = allow_max_smem((const void*)conv_wgrad_tc_kernel<0>);
         if (err == cudaSuccess)
             conv_wgrad_tc_kernel<0><<<grid, kWgThreads, smem, s>>>(nbr_values, neighbours, grad_out, nv_query, F, c_in, c_out, n_pad, ci_tiles,
                                                                     q_splits, chunks_per_split, stages, lookahead, grad_filter);
@@ -979,9 +996,11 @@ int conv_wgrad_tc(const float* nbr_values, const int* neighbours, const float* g
     return check_launch("conv_wgrad_tc");
 }
 
+// after_prep (optional): recorded on `s` once the filter-prep kernel (which also clears `also_zero`) is enqueued, so a
+// second stream can start work that depends on the clearing while this stream runs the convolution itself.
 int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
                 int F, int c_in, int c_out, int flip, int precision, int transposed, float* workspace, float* out,
-                float* also_zero, long long also_zero_n, cudaStream_t s) {
+                float* also_zero, long long also_zero_n, cudaStream_t s, cudaEvent_t after_prep) {
     const int n_pad = (c_out + 15) / 16 * 16;
     const int k_total = F * c_in;
     const int split = precision == 1 ? 1 : 0;
@@ -999,6 +1018,7 @@ int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* fil
         filter_prep_kernel<<<cdiv(total, 256), 256, 0, s>>>(filter, k_total, c_in, c_out, n_pad, split, transposed, b_hi, b_lo,
                                                             out, splits > 1 ? (long long)nv_query * c_out : 0, also_zero, also_zero_n);
         count_launch();
+        if (after_prep != nullptr && cudaEventRecord(after_prep, s) != cudaSuccess) return check_launch("conv_fwd_tc event");
     }
     const size_t b_tile = (size_t)n_pad * kRowBytes;
     const size_t stage_bytes = (split ? 2 : 1) * (kATileBytes + b_tile);
@@ -1021,12 +1041,12 @@ int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* fil
         const int n_items = m_tiles * splits;
         const int grid = min(n_items, sm_count());
         if (split) {
-            err = cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            err = allow_max_smem((const void*)conv_tc2_kernel<1>);
             if (err == cudaSuccess)
                 conv_tc2_kernel<1><<<grid, kTc2Threads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias, nv_query, F, c_in, c_out, n_pad, flip,
                                                                     stages, lookahead, m_tiles, n_items, kb_per_split, env_int("LN_CONV_TRUNC", 0), out);
         } else {
-            err = cudaFuncSetAttribute(conv_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            err = allow_max_smem((const void*)conv_tc2_kernel<0>);
             if (err == cudaSuccess)
                 conv_tc2_kernel<0><<<grid, kTc2Threads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias, nv_query, F, c_in, c_out, n_pad, flip,
                                                                     stages, lookahead, m_tiles, n_items, kb_per_split, 0, out);
@@ -1049,11 +1069,11 @@ int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* fil
     const size_t smem = (size_t)stages * stage_bytes + fixed;
     const dim3 grid(m_tiles, splits);
     if (split) {
-        err = cudaFuncSetAttribute(conv_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        err = allow_max_smem((const void*)conv_fwd_tc_kernel<1>);
         if (err == cudaSuccess)
             conv_fwd_tc_kernel<1><<<grid, kTcThreads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias, nv_query, F, c_in, c_out, n_pad, flip, stages, kb_per_split, out);
     } else {
-        err = cudaFuncSetAttribute(conv_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        err = allow_max_smem((const void*)conv_fwd_tc_kernel<0>);
         if (err == cudaSuccess)
             conv_fwd_tc_kernel<0><<<grid, kTcThreads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias, nv_query, F, c_in, c_out, n_pad, flip, stages, kb_per_split, out);
     }

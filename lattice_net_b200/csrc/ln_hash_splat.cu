@@ -152,33 +152,6 @@ splat_accumulate_small_kernel(const float* __restrict__ values, const int* __res
     }
 }
 
-// General V: one thread per (point, simplex vertex, channel vector).  Consecutive lanes cover
-// consecutive channels of one vertex row, so every atomic instruction is a run of coalesced
-// 16-byte vector reductions (red.global.add.v4.f32, sm_90+).
-template <int VEC>
-__global__ void __launch_bounds__(kBlock)
-splat_accumulate_vec_kernel(const float* __restrict__ values, const int* __restrict__ indices,
-                            const float* __restrict__ weights, int n, int spv, int val_dim,
-                            float* __restrict__ lattice_values) {
-    const int vpr = val_dim / VEC;   // vectors per row
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)n * spv * vpr;
-    if (t >= total) return;
-    const int j = (int)(t % vpr);
-    const long long pr = t / vpr;
-    const int id = __ldg(indices + pr);
-    if (id < 0) return;
-    const float w = __ldg(weights + pr);
-    const int p = (int)(pr / spv);
-    if (VEC == 4) {
-        float4 x = __ldg(reinterpret_cast<const float4*>(values + (size_t)p * val_dim) + j);
-        x.x *= w; x.y *= w; x.z *= w; x.w *= w;
-        atomicAdd(reinterpret_cast<float4*>(lattice_values + (size_t)id * val_dim) + j, x);
-    } else {
-        atomicAdd(lattice_values + (size_t)id * val_dim + j, __ldg(values + (size_t)p * val_dim + j) * w);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // coarsen<d>: one thread per (fine vertex, task); task 0 inserts key/2, task 1+2a / 2+2a handle the
 // np / nm neighbour of axis a.
@@ -310,10 +283,9 @@ int ln_splat_accumulate(const float* values, const int* indices, const float* we
         if (val_dim == 1) splat_accumulate_small_kernel<1><<<grid, kBlock, 0, s>>>(values, indices, weights, n, spv, lattice_values);
         if (val_dim == 2) splat_accumulate_small_kernel<2><<<grid, kBlock, 0, s>>>(values, indices, weights, n, spv, lattice_values);
         if (val_dim == 3) splat_accumulate_small_kernel<3><<<grid, kBlock, 0, s>>>(values, indices, weights, n, spv, lattice_values);
-    } else if (val_dim % 4 == 0) {
-        splat_accumulate_vec_kernel<4><<<cdiv(rows * (val_dim / 4), kBlock), kBlock, 0, s>>>(values, indices, weights, n, spv, val_dim, lattice_values);
     } else {
-        splat_accumulate_vec_kernel<1><<<cdiv(rows * val_dim, kBlock), kBlock, 0, s>>>(values, indices, weights, n, spv, val_dim, lattice_values);
+        // general V: the same scatter as the backward of slice (ln_slice.cu)
+        return launch_scatter_rows(values, indices, weights, n, pos_dim, val_dim, lattice_values, s, "splat_accumulate");
     }
     count_launch();
     return check_launch("splat_accumulate");

@@ -24,6 +24,50 @@ static inline int ilog2(int x) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// L2 residency: the per-vertex table (values / gradient rows, re-read or re-accumulated (D+1)x per point in random
+// order) is the only tensor with reuse; the per-point streams (indices, weights, sliced rows) are touched once.
+// ncu on the 1M-point sweep showed 2x the algorithmic DRAM traffic when they compete for L2 on equal terms, so
+// the table is accessed with an evict_last policy and the streams with evict-first (.cs) accesses.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ldg_v4_hint(const float* a, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ldg_f32_hint(const float* a, uint64_t pol) {
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void red_v4_hint(float* a, float4 v, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_f32_hint(float* a, float v, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(a), "f"(v), "l"(pol) : "memory");
+}
+
+// ids / weights of one point: one 16-byte streaming load each when the simplex has four vertices
+template <int SPV>
+__device__ __forceinline__ void load_simplex(const int* __restrict__ indices, const float* __restrict__ weights, long long p,
+                                             int* id, float* w) {
+    if (SPV == 4) {
+        const int4 i4 = __ldcs(reinterpret_cast<const int4*>(indices) + p);
+        const float4 w4 = __ldcs(reinterpret_cast<const float4*>(weights) + p);
+        id[0] = i4.x; id[1] = i4.y; id[2] = i4.z; id[3] = i4.w;
+        w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+    } else {
+#pragma unroll
+        for (int r = 0; r < SPV; r++) {
+            id[r] = __ldcs(indices + p * SPV + r);
+            w[r] = __ldcs(weights + p * SPV + r);
+        }
+    }
+}
+
 // SPV = simplex vertices per point (pos_dim + 1) as a compile-time constant: ids / weights stay in registers and
 // the SPV row gathers of one thread are independent loads in flight together.
 template <int VEC, int SPV>
@@ -37,20 +81,10 @@ slice_fwd_kernel(const float* __restrict__ lattice_values, const int* __restrict
     const int g = (int)(tid & ((1 << lpp_log2) - 1));
     const int lpp = 1 << lpp_log2;
     const int vpr = val_dim / VEC;
+    const uint64_t keep = l2_policy_evict_last();
     int id[SPV];
     float w[SPV];
-    if (SPV == 4) {
-        const int4 i4 = __ldg(reinterpret_cast<const int4*>(indices) + p);
-        const float4 w4 = __ldg(reinterpret_cast<const float4*>(weights) + p);
-        id[0] = i4.x; id[1] = i4.y; id[2] = i4.z; id[3] = i4.w;
-        w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
-    } else {
-#pragma unroll
-        for (int r = 0; r < SPV; r++) {
-            id[r] = __ldg(indices + p * SPV + r);
-            w[r] = __ldg(weights + p * SPV + r);
-        }
-    }
+    load_simplex<SPV>(indices, weights, p, id, w);
     for (int c = g; c < vpr; c += lpp) {
         float4 x[SPV];
 #pragma unroll
@@ -59,9 +93,9 @@ slice_fwd_kernel(const float* __restrict__ lattice_values, const int* __restrict
             if (id[r] >= 0) {
                 const float* src = lattice_values + (size_t)id[r] * val_dim + (size_t)c * VEC;
                 if (VEC == 4)
-                    x[r] = __ldg(reinterpret_cast<const float4*>(src));
+                    x[r] = ldg_v4_hint(src, keep);
                 else
-                    x[r].x = __ldg(src);
+                    x[r].x = ldg_f32_hint(src, keep);
             }
         }
         float acc[VEC];
@@ -80,41 +114,68 @@ slice_fwd_kernel(const float* __restrict__ lattice_values, const int* __restrict
         }
         float* dst = out + (size_t)p * val_dim + (size_t)c * VEC;
         if (VEC == 4)
-            *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            __stcs(reinterpret_cast<float4*>(dst), make_float4(acc[0], acc[1], acc[2], acc[3]));
         else
-            dst[0] = acc[0];
+            __stcs(dst, acc[0]);
     }
 }
 
-template <int VEC>
+// rows[idx[p,r], :] += src[p, :] * w[p,r]: the backward of slice AND the value accumulation of splat
+// (splatCacheNaive, LatticeGPU.cuh:926-973) are this one scatter.  Lanes run along the channels of one point, so
+// every reduction instruction is a run of coalesced 16-byte vector REDs (red.global.add.v4.f32).
+template <int VEC, int SPV>
 __global__ void __launch_bounds__(kBlock)
-slice_bwd_kernel(const float* __restrict__ grad_out, const int* __restrict__ indices,
-                 const float* __restrict__ weights, int n, int spv, int val_dim, int lpp_log2,
-                 float* __restrict__ grad_values) {
+scatter_rows_kernel(const float* __restrict__ src, const int* __restrict__ indices,
+                    const float* __restrict__ weights, int n, int val_dim, int lpp_log2,
+                    float* __restrict__ rows) {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long p = tid >> lpp_log2;
     if (p >= n) return;
     const int g = (int)(tid & ((1 << lpp_log2) - 1));
     const int lpp = 1 << lpp_log2;
     const int vpr = val_dim / VEC;
+    const uint64_t keep = l2_policy_evict_last();
+    int id[SPV];
+    float w[SPV];
+    load_simplex<SPV>(indices, weights, p, id, w);
     for (int c = g; c < vpr; c += lpp) {
-        const float* src = grad_out + (size_t)p * val_dim + (size_t)c * VEC;
+        const float* s = src + (size_t)p * val_dim + (size_t)c * VEC;
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (VEC == 4)
-            x = __ldg(reinterpret_cast<const float4*>(src));
+            x = __ldcs(reinterpret_cast<const float4*>(s));
         else
-            x.x = __ldg(src);
-        for (int r = 0; r < spv; r++) {
-            const int id = __ldg(indices + p * spv + r);
-            if (id < 0) continue;
-            const float w = __ldg(weights + p * spv + r);
-            float* dst = grad_values + (size_t)id * val_dim + (size_t)c * VEC;
+            x.x = __ldcs(s);
+#pragma unroll
+        for (int r = 0; r < SPV; r++) {
+            if (id[r] < 0) continue;
+            float* dst = rows + (size_t)id[r] * val_dim + (size_t)c * VEC;
             if (VEC == 4)
-                atomicAdd(reinterpret_cast<float4*>(dst), make_float4(x.x * w, x.y * w, x.z * w, x.w * w));
+                red_v4_hint(dst, make_float4(x.x * w[r], x.y * w[r], x.z * w[r], x.w * w[r]), keep);
             else
-                atomicAdd(dst, x.x * w);
+                red_f32_hint(dst, x.x * w[r], keep);
         }
     }
+}
+
+int launch_scatter_rows(const float* src, const int* indices, const float* weights, int n, int pos_dim, int val_dim,
+                        float* rows, cudaStream_t s, const char* what) {
+    const int vec = (val_dim % 4 == 0) ? 4 : 1;
+    const int lpp = lanes_per_point(val_dim / vec);
+    const int grid = cdiv((long long)n * lpp, kBlock);
+    const int spv = pos_dim + 1;
+    if (spv != 4 && spv != 6) {
+        set_error("%s: pos_dim %d not built (3 and 5 are)", what, pos_dim);
+        return LN_ERR_UNSUPPORTED;
+    }
+#define LN_LAUNCH_SCATTER(VEC, SPV) scatter_rows_kernel<VEC, SPV><<<grid, kBlock, 0, s>>>(src, indices, weights, n, val_dim, ilog2(lpp), rows)
+    if (vec == 4) {
+        if (spv == 4) LN_LAUNCH_SCATTER(4, 4); else LN_LAUNCH_SCATTER(4, 6);
+    } else {
+        if (spv == 4) LN_LAUNCH_SCATTER(1, 4); else LN_LAUNCH_SCATTER(1, 6);
+    }
+#undef LN_LAUNCH_SCATTER
+    count_launch();
+    return check_launch(what);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -403,16 +464,7 @@ int ln_slice_bwd(const float* grad_out, const int* indices, const float* weights
     LN_REQUIRE(grad_out && indices && weights && grad_values, "ln_slice_bwd: null pointer");
     LN_SLICE_ARGS_OK("ln_slice_bwd");
     if (n == 0) return LN_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    const int vec = (val_dim % 4 == 0) ? 4 : 1;
-    const int lpp = lanes_per_point(val_dim / vec);
-    const int grid = cdiv((long long)n * lpp, kBlock);
-    if (vec == 4)
-        slice_bwd_kernel<4><<<grid, kBlock, 0, s>>>(grad_out, indices, weights, n, pos_dim + 1, val_dim, ilog2(lpp), grad_values);
-    else
-        slice_bwd_kernel<1><<<grid, kBlock, 0, s>>>(grad_out, indices, weights, n, pos_dim + 1, val_dim, ilog2(lpp), grad_values);
-    count_launch();
-    return check_launch("slice_bwd");
+    return launch_scatter_rows(grad_out, indices, weights, n, pos_dim, val_dim, grad_values, (cudaStream_t)stream, "slice_bwd");
 }
 
 int ln_gather_fwd(const float* lattice_values, const int* indices, const float* weights, int n, int pos_dim,
@@ -455,7 +507,7 @@ int ln_slice_classify_fwd(const float* lattice_values, const int* indices, const
     const int kv = cdiv(val_dim, 32);
 #define LN_LAUNCH_SCF(KV)                                                                                          \
     do {                                                                                                           \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(slice_classify_fwd_kernel<KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (smem > 48 * 1024) allow_max_smem((const void*)slice_classify_fwd_kernel<KV>); \
         slice_classify_fwd_kernel<KV><<<grid, kBlock, smem, s>>>(lattice_values, indices, weights, delta_weights, cls_weight, cls_bias, n, pos_dim + 1, val_dim, nr_classes, logits); \
     } while (0)
     if (kv <= 1) LN_LAUNCH_SCF(1);
@@ -487,7 +539,7 @@ int ln_slice_classify_bwd(const float* grad_logits, const float* lattice_values,
     const int kv = cdiv(val_dim, 32);
 #define LN_LAUNCH_SCB(KV)                                                                                          \
     do {                                                                                                           \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(slice_classify_bwd_kernel<KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (smem > 48 * 1024) allow_max_smem((const void*)slice_classify_bwd_kernel<KV>); \
         slice_classify_bwd_kernel<KV><<<grid, kBlock, smem, s>>>(grad_logits, lattice_values, indices, weights, delta_weights, cls_weight, n, pos_dim + 1, val_dim, nr_classes, grad_lattice_values, grad_delta_weights, grad_cls_weight, grad_cls_bias); \
     } while (0)
     if (kv <= 1) LN_LAUNCH_SCB(1);

@@ -376,7 +376,8 @@ class GroupNormLatticeModule(torch.nn.Module):
         # statistics run over (channels of a group) x (all vertices): vertices are the "length" axis
         gn = self.gn
         nv, c = lattice_values.shape
-        st = lattice_py.m_hash_table.structure
+        ht = getattr(lattice_py, "m_hash_table", None)      # (bench.py's reference arm passes its own handle type)
+        st = ht.structure if ht is not None else None
         nv_dev = st.nr_filled if (st is not None and st.bound is not None) else None
         if lattice_values.is_cuda and (nv_dev is not None or nv * (c // gn.num_groups) <= FUSED_NORM_MAX_ELEMS_PER_GROUP):
             lv = _GroupNormReLU.apply(lattice_values, gn.weight, gn.bias, gn.num_groups, gn.eps, relu, nv_dev)

@@ -1,0 +1,13 @@
+#!/bin/bash
+# parity re-check after the test fixes, reference arm, eager + graph launch lists, full ncu captures of the op kernels
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest gpu rc=$?"
+tail -5 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/bench_ref.log 2>&1; echo "bench ref rc=$?"
+tail -1 gpurun_out/bench_ref.log | cut -c1-400
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/launches_eager.csv python bench.py --steps 2 --warmup 3 --mode eager > gpurun_out/ncu_bench_eager.log 2>&1; echo "ncu launches eager rc=$?"
+timeout 900 ncu --graph-profiling node --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/launches_graph.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_bench_graph.log 2>&1; echo "ncu launches graph rc=$?"
+tail -3 gpurun_out/ncu_bench_graph.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'conv_tc2|conv_wgrad_tc|slice_fwd|slice_bwd|splat_accumulate|splat_build|neighbour_table|slice_classify|gather_fwd' -o gpurun_out/r01e_ops -f python scripts/ncu_ops.py > gpurun_out/ncu_ops.log 2>&1; echo "ncu ops rc=$?"
+tail -3 gpurun_out/ncu_ops.log
+ls -la gpurun_out

@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from oracle import cases, lattice_oracle as lo
-from tests.util import agg, assert_close, bits_equal, canonical, max_rel_err
+from tests.util import agg, assert_close, bits_equal, canonical, first, max_rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -83,7 +83,7 @@ def test_splat_values(built):
     ours = b["ours"].values()
     assert tuple(ours.shape) == (b["spec"]["capacity"], 3)           # [capacity x V], like the reference
     ours_np = ours[:b["nv"]].cpu().numpy()[b["n2o"]]
-    ref_np = agg(b["ref"].values[:b["nv"]].cpu().numpy(), b["ro2n"])
+    ref_np = agg(b["ref"].values[:b["rnv"]].cpu().numpy(), b["ro2n"])
     assert_close(ours_np, ref_np, TOL_VALUES, "splat values vs reference kernels")
     assert_close(ours_np, lo.splat_accumulate(b["vals_np"], b["cpu"]["indices"], b["cpu"]["weights"], b["nv"]), TOL_VALUES, "splat values vs oracle")
     assert float(ours[b["nv"]:].abs().max()) == 0.0
@@ -290,10 +290,10 @@ def test_conv_fwd_wgrad_dgrad(built, Cin, Cout):
     assert_close(got, exp, TOL_VALUES, "conv forward vs oracle")
     ref = b["ref"]
     if ref.k.has(f"im2row<{b['d']},{Cin}>"):
-        rout = agg(ref.convolve(cuda(fb), ref, cuda(lv[b["ro2n"]]), 1, False).cpu().numpy(), b["ro2n"])
+        rout = first(ref.convolve(cuda(fb), ref, cuda(lv[b["ro2n"]]), 1, False).cpu().numpy(), b["rn2o"])
         assert_close(got, rout, TOL_VALUES, "conv forward vs reference im2row+mm")
         rows = ours.im2row(ours, F, 1, False).cpu().numpy()[b["n2o"]]
-        rrows = agg(ref.im2row(ref, cuda(lv[b["ro2n"]]), 1, False).cpu().numpy(), b["ro2n"])
+        rrows = first(ref.im2row(ref, cuda(lv[b["ro2n"]]), 1, False).cpu().numpy(), b["rn2o"])
         assert bits_equal(rows, rrows) == 0, "im2row differs from the reference"
     # weight gradient and data gradient
     g = cases.randn((b["nv"], Cout), 80 + Cout)
@@ -322,7 +322,7 @@ def test_row2im(built):
     rows = ours.im2row(ours, F, 1, False)
     back = ours.row2im(rows, 1, F, 16, ours).cpu().numpy()[b["n2o"]]
     rrows = ref.im2row(ref, cuda(lv[b["ro2n"]]), 1, False)
-    rback = agg(ref.row2im(rrows, ref, V, 1).cpu().numpy(), b["ro2n"])
+    rback = first(ref.row2im(rrows, ref, V, 1).cpu().numpy(), b["rn2o"])
     assert_close(back, rback, 1e-6, "row2im vs reference kernels")
     table = lo.neighbour_table(b["ks"], b["ks"], 0, 1)
     assert_close(back, lo.row2im(lo.im2row(lv, table), table, V), 1e-6, "row2im vs oracle")
@@ -399,26 +399,39 @@ def test_lnn_model_matches_cpu_port():
     model = LNN(7, ModelParams(), device=dev)
     pos, vals, labels = cuda(pos_np), torch.zeros((2048, 1), device=dev), cuda(labels_np)
     logsm, logits = model(lattice, pos, vals)
-    loss = segmentation_loss(logsm, labels)
+    # Gradients are compared under the NLL term alone.  The Lovasz term is piecewise linear in the SORTED errors:
+    # two errors that differ in the last bits swap places between two fp32 evaluations and the gradients of those
+    # two points jump by O(1/|union|) -- measured on the B200: identical loss to 7 digits, per-tensor gradient
+    # deviations of 1e-2..2e-1 between two runs of the very same kernels.  Its VALUE is compared below.
+    loss = torch.nn.functional.nll_loss(logsm, labels)
     loss.backward()
+    full_loss = segmentation_loss(logsm.detach(), labels)
     l1 = model.last_level1_lattice
     keys = l1.hash_table().m_keys_tensor[:l1.nr_lattice_vertices()].cpu().numpy()
     cpu = cpu_port.CpuLNN(7, ModelParams())
     cpu.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()}, strict=True)
     clogsm, clogits = cpu(pos_np, torch.zeros(2048, 1), [0.05] * 3, level1_keys=keys)
-    closs = segmentation_loss(clogsm, torch.from_numpy(labels_np))
+    closs = torch.nn.functional.nll_loss(clogsm, torch.from_numpy(labels_np))
     closs.backward()
+    cfull_loss = segmentation_loss(clogsm.detach(), torch.from_numpy(labels_np))
     assert_close(logits.detach().cpu().numpy(), clogits.detach().numpy(), 2e-3, "LNN logits vs CPU port")
     assert abs(loss.item() - closs.item()) <= 1e-3 * abs(closs.item())
+    assert abs(full_loss.item() - cfull_loss.item()) <= 1e-3 * abs(cfull_loss.item()), "0.5 Lovasz + 0.5 NLL value"
     cpu_grads = dict(cpu.named_parameters())
     checked = 0
+    num = den = 0.0
     for name, p in model.named_parameters():
         if p.grad is None:
             continue
         g, cg = p.grad.detach().cpu().numpy(), cpu_grads[name].grad.numpy()
+        # two fp32 evaluations of a 40-layer network: a per-tensor max error bound (2e-2 of the tensor's scale)
+        # plus a tight bound on the relative L2 error over ALL gradients together
         assert_close(g, cg, 2e-2, f"gradient of {name}")
+        num += float(((g.astype(np.float64) - cg) ** 2).sum())
+        den += float((cg.astype(np.float64) ** 2).sum())
         checked += 1
     assert checked > 100
+    assert (num / den) ** 0.5 <= 5e-3, f"relative L2 error over all gradients {(num / den) ** 0.5:.3e}"
 
 
 @pytest.mark.parametrize("precision,tol", [(1, 2e-5), (2, 5e-3)])
@@ -630,7 +643,10 @@ def test_graphed_step_matches_eager_step():
         opt_b = torch.optim.AdamW(model_b.parameters(), lr=0.0, weight_decay=3e-4, amsgrad=True, fused=True, capturable=True)
         bucket_b = GradBucket(model_b.parameters())
         bounds = estimate_vertex_bounds(60000, [(0.05, 3)], [c[0] for c in clouds], 4)
-        step = GraphedTrainStep(model_b, lat_b, opt_b, segmentation_loss, 2048, 3, 1, bounds, bucket_b, example=clouds[0])
+        # gradients are compared under the smooth NLL term (the Lovasz term's gradient jumps when two near-equal
+        # errors swap places in its sort, see test_lnn_model_matches_cpu_port)
+        nll = torch.nn.functional.nll_loss
+        step = GraphedTrainStep(model_b, lat_b, opt_b, nll, 2048, 3, 1, bounds, bucket_b, example=clouds[0])
         # the capture's warm-up passes must leave parameters untouched
         for (na, pa), (nb, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
             assert torch.equal(pa, pb), f"{na} changed during graph capture"
@@ -639,7 +655,7 @@ def test_graphed_step_matches_eager_step():
             loss_b = step(pos, vals, labels)
             replays += 1
             logsm, _ = model_a(lat_a, pos, vals)
-            loss_a = segmentation_loss(logsm, labels)
+            loss_a = nll(logsm, labels)
             for p in model_a.parameters():
                 p.grad = None
             loss_a.backward()

@@ -21,6 +21,12 @@ def agg(rows, old_to_new):
     return out
 
 
+def first(rows, new_to_old):
+    """Per-vertex rows in GPU order -> canonical order for GATHER-type outputs (conv, im2row, row2im): every copy
+    of a duplicated vertex holds the same row, so the first occurrence is taken instead of the sum."""
+    return np.asarray(rows)[new_to_old]
+
+
 def max_rel_err(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
