@@ -191,10 +191,19 @@ def kernel_roofline(device):
         pass
     peak = float(peaks.get("bf16_tflops", 1590.0))
     achieved = flops / sec / 1e12
+    # DRAM bytes of the same call (filter prep + tcgen05 kernel) from one `ncu --set full` capture of exactly this
+    # configuration: scripts/ncu_bench_conv.py -> scripts/roofline_traffic.py -> profiles/roofline_traffic.json
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            traffic = float(json.load(f)["traffic_bytes_per_call"])
+    except Exception:
+        pass
     return {"bound": "tensor", "kernel": "lattice conv fwd 128->128 (K=1152), nv=%d, precision mode %d; per ln_conv_fwd call = filter prep + tcgen05 kernel, "
                                          "device time from a CUDA-graph replay of 20 back-to-back calls (working set stays in L2, as inside the step)" % (nv, lattice_mod.CONV_PRECISION),
             "achieved": achieved, "peak": peak, "peak_source": "measured bf16 burst (MEASURED_PEAKS.json)" if peaks else "fallback",
-            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "us_per_launch": sec * 1e6}
+            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "us_per_launch": sec * 1e6,
+            "algorithmic_bytes": 4.0 * (nv * cin + nv * F + F * cin * cout + nv * cout)}
 
 
 def run_ours(args):

@@ -137,7 +137,7 @@ def run(n, d, vals, quick, order="random"):
         lv = torch.zeros((nv, V), device=dev)
 
         def acc():
-            call("ln_splat_accumulate", ptr(x), ptr(idx), ptr(w), n, d, V, ptr(lv), stream_ptr(dev))
+            call("ln_splat_accumulate", ptr(x), ptr(idx), ptr(w), n, d, V, nv, ptr(lv), stream_ptr(dev))
         rs = None
         if ref is not None and ref.k.has(f"splatCacheNaive<{d},{V}>"):
             rvals = torch.zeros((cap, V), device=dev)
@@ -152,7 +152,7 @@ def run(n, d, vals, quick, order="random"):
         out = torch.empty((n, V), device=dev)
 
         def sl():
-            call("ln_slice_fwd", ptr(lvr), ptr(idx), ptr(w), n, d, V, ptr(out), stream_ptr(dev))
+            call("ln_slice_fwd", ptr(lvr), ptr(idx), ptr(w), n, d, V, nv, ptr(out), stream_ptr(dev))
         rs = None
         if ref is not None and ref.k.has(f"slice_with_precomputation<{d},{V}>"):
             rs = timeit(lambda: ref.slice_with_precomputation(pos, lvr, ridx, rw), reps=5)
@@ -162,7 +162,7 @@ def run(n, d, vals, quick, order="random"):
         gl = torch.zeros((nv, V), device=dev)
 
         def slb():
-            call("ln_slice_bwd", ptr(g), ptr(idx), ptr(w), n, d, V, ptr(gl), stream_ptr(dev))
+            call("ln_slice_bwd", ptr(g), ptr(idx), ptr(w), n, d, V, nv, ptr(gl), stream_ptr(dev))
         rs = None
         if ref is not None and ref.k.has(f"slice_backwards_with_precomputation_no_homogeneous<{d},{V}>"):
             rs = timeit(lambda: ref.slice_backwards(g, ridx, rw), reps=5)

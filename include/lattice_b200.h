@@ -76,9 +76,11 @@ int ln_splat_build(const float* positions_raw, const float* sigmas, int n, int p
 
 /* Replaces splatCacheNaive<d,V> (LatticeGPU.cuh:926-973):
  *   lattice_values[indices[p,r], :] += values[p, :] * weights[p,r]      (rows with index < 0 skipped)
- * lattice_values must be zero-initialised by the caller (HashTable::clear does it in the reference). */
+ * lattice_values must be zero-initialised by the caller (HashTable::clear does it in the reference).
+ * nr_vertices: rows of lattice_values (<= 0: unknown, n is assumed).  Only a tuning input: the kernels walk the
+ * channels in slabs sized so that one slab of the vertex table stays resident in the L2. */
 int ln_splat_accumulate(const float* values, const int* indices, const float* weights,
-                        int n, int pos_dim, int val_dim, float* lattice_values, void* stream);
+                        int n, int pos_dim, int val_dim, int nr_vertices, float* lattice_values, void* stream);
 
 /* Replaces distribute<d,V> (LatticeGPU.cuh:534-650) + host prep of Lattice::distribute
  * (/root/reference/src/Lattice.cu:351-410).  As ln_splat_build, plus
@@ -174,13 +176,14 @@ int ln_conv_bwd(const float* nbr_values, const int* neighbours_fwd, const float*
 int ln_filter_for_dgrad(const float* filter, int filter_extent, int c_in, int c_out, float* filter_bw, void* stream);
 
 /* ---- slice family -------------------------------------------------------------------------------
- * slice_with_precomputation<d,V> (LatticeGPU.cuh:2552-2595): out[p,:] = sum_r w[p,r]*values[idx[p,r],:] */
+ * slice_with_precomputation<d,V> (LatticeGPU.cuh:2552-2595): out[p,:] = sum_r w[p,r]*values[idx[p,r],:]
+ * nr_vertices: rows of the vertex table, a tuning input as in ln_splat_accumulate (<= 0: unknown). */
 int ln_slice_fwd(const float* lattice_values, const int* indices, const float* weights,
-                 int n, int pos_dim, int val_dim, float* out, void* stream);
+                 int n, int pos_dim, int val_dim, int nr_vertices, float* out, void* stream);
 /* slice_backwards_with_precomputation_no_homogeneous<d,V> (LatticeGPU.cuh:3540-3623):
  *   grad_values[idx[p,r], :] += grad_out[p,:] * w[p,r]      (grad_values pre-zeroed by caller) */
 int ln_slice_bwd(const float* grad_out, const int* indices, const float* weights,
-                 int n, int pos_dim, int val_dim, float* grad_values, void* stream);
+                 int n, int pos_dim, int val_dim, int nr_vertices, float* grad_values, void* stream);
 /* gather_with_precomputation<d,V> (LatticeGPU.cuh:2886-2929): out [n x (pos_dim+1)(val_dim+1)],
  * chunk r = [ w_r * values[idx_r,:] | w_r ], zeros where idx_r < 0. */
 int ln_gather_fwd(const float* lattice_values, const int* indices, const float* weights,

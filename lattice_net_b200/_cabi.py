@@ -20,7 +20,7 @@ _SIGNATURES = {
     "ln_table_clear": [_P, _P, _P, _I, _P],
     "ln_table_status": [_P, _P, _P, _P, _P],
     "ln_splat_build": [_P, _P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P],
-    "ln_splat_accumulate": [_P, _P, _P, _I, _I, _I, _P, _P],
+    "ln_splat_accumulate": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "ln_distribute": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P],
     "ln_lookup_simplex": [_P, _P, _I, _I, _P, _P, _I, _P, _P, _P],
     "ln_coarsen_keys": [_P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P],
@@ -32,8 +32,8 @@ _SIGNATURES = {
     "ln_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "ln_conv_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "ln_filter_for_dgrad": [_P, _I, _I, _I, _P, _P],
-    "ln_slice_fwd": [_P, _P, _P, _I, _I, _I, _P, _P],
-    "ln_slice_bwd": [_P, _P, _P, _I, _I, _I, _P, _P],
+    "ln_slice_fwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "ln_slice_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "ln_gather_fwd": [_P, _P, _P, _I, _I, _I, _P, _P],
     "ln_gather_bwd": [_P, _P, _P, _I, _I, _I, _P, _P],
     "ln_slice_classify_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],

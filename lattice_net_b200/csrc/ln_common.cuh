@@ -17,7 +17,7 @@ void count_launch(int n = 1);
 cudaError_t allow_max_smem(const void* kernel);   // ln_conv_tc.cu: opt a kernel into 227 KB dynamic smem, once per device
 // rows[idx[p,r], :] += src[p, :] * w[p,r]  (ln_slice.cu; shared by ln_slice_bwd and ln_splat_accumulate)
 int launch_scatter_rows(const float* src, const int* indices, const float* weights, int n, int pos_dim, int val_dim,
-                        float* rows, cudaStream_t s, const char* what);
+                        int nr_vertices, float* rows, cudaStream_t s, const char* what);
 
 #define LN_REQUIRE(cond, ...)                 \
     do {                                      \
@@ -106,8 +106,8 @@ __device__ __forceinline__ int table_insert(const TableView& t, const int* key, 
                 if (id >= t.max_vertices) atomicOr(t.status, 2);   // caller's row bound exceeded (static-shape mode)
 #pragma unroll
                 for (int i = 0; i < D; i++) t.keys[(size_t)id * D + i] = key[i];
-                __threadfence();
-                st_release(e, id);
+                st_release(e, id);   // release at gpu scope: the key stores above are visible before the id is
+                                     // (a separate __threadfence() here only doubled the membar stall, ncu r01g)
                 if (probe > 0) atomicMax(t.status + 1, probe);
                 return id;
             }

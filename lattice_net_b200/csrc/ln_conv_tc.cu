@@ -835,11 +835,15 @@ conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ n
         const int* nbr_p = neighbours + (size_t)q * F + slot;
         const float* g_p = grad_out + (size_t)q * c_out + cc * 4;
         const float* a_col = values + ci0 + cc * 4;
+        // the neighbour id of a row is needed before its copies can be issued: it is requested one chunk ahead, so
+        // its latency overlaps the wait for a free stage instead of serialising every iteration of this loop
+        // (ncu r01g: 8 % L2 throughput, 17 % tensor pipe, one dependent L2 round trip per 32 vertices)
+        int id_next = (num_chunks > 0 && q < nv_query) ? __ldg(nbr_p) : -1;
         for (int g = 0; g < num_chunks; g++) {
-            mbar_wait(issue_empty, issue_phase ^ 1u);
             const bool in_range = q < nv_query;
-            int id = -1;
-            if (in_range) id = __ldg(nbr_p);
+            const int id = id_next;
+            id_next = (g + 1 < num_chunks && q + kWgRows < nv_query) ? __ldg(nbr_p + (size_t)kWgRows * F) : -1;
+            mbar_wait(issue_empty, issue_phase ^ 1u);
             const bool have = id >= 0;
             const float* arow = have ? a_col + (unsigned long long)(unsigned)id * (unsigned)c_in : values;
             const uint32_t dst = issue_addr + my_off;

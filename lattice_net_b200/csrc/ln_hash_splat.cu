@@ -26,9 +26,15 @@ __global__ void __launch_bounds__(kBlock) table_clear_kernel(int4* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// One thread per point.  The D+1 simplex vertices of spatially close points coincide most of the
-// time, so before touching the table each warp groups equal keys with __match_any_sync and only
-// the group leader probes / inserts; the vertex id is broadcast back with a shuffle.
+// One thread per point, two phases (ncu on the 1M-point sweep: the old kernel, which ran the D+1 insert-or-find chains
+// of a thread one after the other, was pure dependent-latency -- stall_long_scoreboard + stall_membar = 88 % of all
+// stalls at 19 % issue utilisation):
+//   phase 1  LOOK-UP, all D+1 keys of the thread in flight together: load the D+1 home slots, then the D+1 stored
+//            keys, compare.  Every vertex is shared by ~9 simplices, so once the table warms up most keys resolve
+//            here with two overlapped L2 round trips for the whole simplex and no atomic.
+//   phase 2  INSERT for what is left (empty / locked / colliding home slot).  The D+1 simplex vertices of spatially
+//            close points coincide most of the time, so each warp first groups equal keys with __match_any_sync and
+//            only the group leader probes / inserts; the vertex id is broadcast back with a shuffle.
 template <int D, bool kDistribute, bool kInsert>
 __global__ void __launch_bounds__(kBlock)
 splat_build_kernel(const float* __restrict__ positions_raw, const float* __restrict__ sigmas,
@@ -37,7 +43,6 @@ splat_build_kernel(const float* __restrict__ positions_raw, const float* __restr
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool valid = idx < n;
-    const unsigned valid_mask = __ballot_sync(kFull, valid);
 
     Simplex<D> s;
     float p[D];
@@ -47,32 +52,71 @@ splat_build_kernel(const float* __restrict__ positions_raw, const float* __restr
     }
 
     int ids[D + 1];
+    if (kInsert) {
+        int key[D + 1][D];
+        uint32_t hash[D + 1];
+        int cur[D + 1];
+        // ---- phase 1 ----
 #pragma unroll
-    for (int r = 0; r <= D; r++) {
-        int key[D];
+        for (int r = 0; r <= D; r++) {
 #pragma unroll
-        for (int i = 0; i < D; i++) key[i] = 0;
-        uint32_t h = 0;
-        if (valid) {
-            simplex_key<D>(s, r, key);
-            h = key_hash<D>(key);
+            for (int i = 0; i < D; i++) key[r][i] = 0;
+            hash[r] = 0;
+            cur[r] = kEmpty;
+            ids[r] = -1;
+            if (valid) {
+                simplex_key<D>(s, r, key[r]);
+                hash[r] = key_hash<D>(key[r]);
+                cur[r] = ld_relaxed(table.entries + (int)(hash[r] % (uint32_t)table.capacity));
+            }
         }
-        int id = -1;
-        if (kInsert) {
-            const unsigned peers = __match_any_sync(kFull, h) & valid_mask;
-            const int leader = valid ? (__ffs(peers) - 1) : lane;
-            bool same = valid;   // same key as the group leader (hash collisions are possible)
+        int stored[D + 1][D];
 #pragma unroll
-            for (int i = 0; i < D; i++) same &= (__shfl_sync(kFull, key[i], leader) == key[i]);
-            if (valid && (lane == leader || !same)) id = table_insert<D>(table, key, h);
+        for (int r = 0; r <= D; r++) {
+#pragma unroll
+            for (int i = 0; i < D; i++) stored[r][i] = (cur[r] >= 0) ? __ldcg(table.keys + (size_t)cur[r] * D + i) : 0;
+        }
+        bool pending[D + 1];
+#pragma unroll
+        for (int r = 0; r <= D; r++) {
+            bool same = cur[r] >= 0;
+#pragma unroll
+            for (int i = 0; i < D; i++) same &= (stored[r][i] == key[r][i]);
+            if (same) ids[r] = cur[r];
+            pending[r] = valid && !same;
+        }
+        // ---- phase 2 ----
+#pragma unroll
+        for (int r = 0; r <= D; r++) {
+            if (!__any_sync(kFull, pending[r])) continue;               // warp-uniform
+            const bool need = pending[r];
+            // group by hash; lanes with nothing left to insert are masked out of every group
+            const unsigned group = __match_any_sync(kFull, hash[r]) & __ballot_sync(kFull, need);
+            const int leader = need ? (__ffs(group) - 1) : lane;
+            bool same = need;   // same key as the group leader (hash collisions are possible)
+#pragma unroll
+            for (int i = 0; i < D; i++) same &= (__shfl_sync(kFull, key[r][i], leader) == key[r][i]);
+            int id = -1;
+            if (need && (lane == leader || !same)) id = table_insert<D>(table, key[r], hash[r]);
             const int leader_id = __shfl_sync(kFull, id, leader);
-            if (valid && same) id = leader_id;
-        } else if (valid) {
-            ConstTableView ct{table.keys, table.entries, table.capacity};
-            id = table_find<D>(ct, key);
+            if (need) ids[r] = same ? leader_id : id;
         }
-        ids[r] = (id >= table.max_vertices) ? -1 : id;   // beyond the caller's row bound: dropped + flagged
+    } else {
+#pragma unroll
+        for (int r = 0; r <= D; r++) {
+            int key[D];
+            int id = -1;
+            if (valid) {
+                simplex_key<D>(s, r, key);
+                ConstTableView ct{table.keys, table.entries, table.capacity};
+                id = table_find<D>(ct, key);
+            }
+            ids[r] = id;
+        }
     }
+#pragma unroll
+    for (int r = 0; r <= D; r++)
+        if (ids[r] >= table.max_vertices) ids[r] = -1;   // beyond the caller's row bound: dropped + flagged
     if (!valid) return;
 
     if (indices != nullptr) {
@@ -271,7 +315,7 @@ int ln_lookup_simplex(const float* positions_raw, const float* sigmas, int n, in
 }
 
 int ln_splat_accumulate(const float* values, const int* indices, const float* weights, int n, int pos_dim, int val_dim,
-                        float* lattice_values, void* stream) {
+                        int nr_vertices, float* lattice_values, void* stream) {
     LN_REQUIRE(values && indices && weights && lattice_values, "ln_splat_accumulate: null pointer");
     LN_REQUIRE(n >= 0 && pos_dim >= 1 && val_dim >= 1, "ln_splat_accumulate: bad size");
     if (n == 0) return LN_OK;
@@ -285,7 +329,7 @@ int ln_splat_accumulate(const float* values, const int* indices, const float* we
         if (val_dim == 3) splat_accumulate_small_kernel<3><<<grid, kBlock, 0, s>>>(values, indices, weights, n, spv, lattice_values);
     } else {
         // general V: the same scatter as the backward of slice (ln_slice.cu)
-        return launch_scatter_rows(values, indices, weights, n, pos_dim, val_dim, lattice_values, s, "splat_accumulate");
+        return launch_scatter_rows(values, indices, weights, n, pos_dim, val_dim, nr_vertices, lattice_values, s, "splat_accumulate");
     }
     count_launch();
     return check_launch("splat_accumulate");

@@ -68,106 +68,209 @@ __device__ __forceinline__ void load_simplex(const int* __restrict__ indices, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Work decomposition shared by slice forward and the row scatter (ncu --set full on the 1M-point sweep,
+// profiles/r01g_ops_ncu.md, is what shaped it):
+//   * CHANNEL SLABS.  The vertex table is hit (D+1)x per point in random order; once nv*V*4 bytes outgrow the L2 it
+//     is re-fetched from HBM several times (V=64, nv=463k: 118 MB table, 31 % L2 hit rate, 1.8x the compulsory DRAM
+//     traffic).  The channels are therefore processed in slabs of `slab_ch` (a multiple of 32 floats = one 128-byte
+//     line per row) sized so that one slab of the table stays L2-resident; all blocks walk the slabs in the same
+//     order.  The price is re-reading the 8(D+1) index/weight bytes per point once per slab.
+//   * PERSISTENT BLOCKS + REGISTER DOUBLE BUFFERING.  The old one-shot blocks (16 points each, 62 500 of them) lived
+//     for two dependent memory latencies and spent the second one with only the row gathers in flight; the kernels
+//     were latency bound (stall_long_scoreboard > 85 % of all stalls) at 60 % achieved occupancy.  Now a fixed grid
+//     strides over the points and every thread requests the ids / weights (and, for the scatter, the source chunk)
+//     of its NEXT point before it gathers the rows of the current one.
+// Lanes run along the channels of one point (lpp = lanes per point, a power of two covering slab_ch / VEC chunks).
+struct SlabPlan {
+    int slab_ch;     // channels per slab (== val_dim when one slab suffices)
+    int n_slabs;
+    int lpp_log2;
+    int grid;
+};
+static int blocks_per_sm(const void* kernel) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kBlock, 0) != cudaSuccess || nb <= 0) {
+        cudaGetLastError();
+        nb = 4;
+    }
+    return nb;
+}
+static int device_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+static SlabPlan plan_slabs(int n, int nr_vertices, int val_dim, int vec, int resident_blocks) {
+    constexpr long long kL2Budget = 48ll << 20;   // of the 126 MB L2 (two 63 MB halves), leaving room for the streams
+    const long long rows = nr_vertices > 0 ? nr_vertices : n;
+    SlabPlan pl;
+    pl.slab_ch = val_dim;
+    if (vec == 4 && val_dim > 32) {
+        long long fit = kL2Budget / (4 * rows) / 32 * 32;
+        fit = fit < 32 ? 32 : fit > 128 ? 128 : fit;       // 128 channels = 32 lanes x float4
+        if (fit < val_dim) pl.slab_ch = (int)fit;
+        if (val_dim > 128 && pl.slab_ch > 128) pl.slab_ch = 128;
+    }
+    pl.n_slabs = (val_dim + pl.slab_ch - 1) / pl.slab_ch;
+    const int lpp = lanes_per_point(min(pl.slab_ch / vec, 32));
+    pl.lpp_log2 = ilog2(lpp);
+    const long long want = ((long long)n * lpp + kBlock - 1) / kBlock;
+    const long long cap = (long long)device_sms() * resident_blocks;
+    pl.grid = (int)(want < cap ? want : cap);
+    return pl;
+}
+
 // SPV = simplex vertices per point (pos_dim + 1) as a compile-time constant: ids / weights stay in registers and
 // the SPV row gathers of one thread are independent loads in flight together.
 template <int VEC, int SPV>
 __global__ void __launch_bounds__(kBlock)
 slice_fwd_kernel(const float* __restrict__ lattice_values, const int* __restrict__ indices,
-                 const float* __restrict__ weights, int n, int val_dim, int lpp_log2,
+                 const float* __restrict__ weights, int n, int val_dim, int slab_ch, int n_slabs, int lpp_log2,
                  float* __restrict__ out) {
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long p = tid >> lpp_log2;
-    if (p >= n) return;
-    const int g = (int)(tid & ((1 << lpp_log2) - 1));
     const int lpp = 1 << lpp_log2;
-    const int vpr = val_dim / VEC;
+    const int g = threadIdx.x & (lpp - 1);
+    const int pts_per_block = kBlock >> lpp_log2;
+    const long long p_first = (long long)blockIdx.x * pts_per_block + (threadIdx.x >> lpp_log2);
+    const long long p_stride = (long long)gridDim.x * pts_per_block;
     const uint64_t keep = l2_policy_evict_last();
-    int id[SPV];
-    float w[SPV];
-    load_simplex<SPV>(indices, weights, p, id, w);
-    for (int c = g; c < vpr; c += lpp) {
-        float4 x[SPV];
+    for (int slab = 0; slab < n_slabs; slab++) {
+        const int ch_begin = slab * slab_ch;
+        const int ch_end = min(val_dim, ch_begin + slab_ch);
+        long long p = p_first;
+        int id[SPV], idn[SPV];
+        float w[SPV], wn[SPV];
+        if (p < n) load_simplex<SPV>(indices, weights, p, id, w);
+        while (p < n) {
+            const long long pn = p + p_stride;
+            if (pn < n) load_simplex<SPV>(indices, weights, pn, idn, wn);
+            for (int ch = ch_begin + g * VEC; ch < ch_end; ch += lpp * VEC) {
+                float4 x[SPV];
 #pragma unroll
-        for (int r = 0; r < SPV; r++) {
-            x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (id[r] >= 0) {
-                const float* src = lattice_values + (size_t)id[r] * val_dim + (size_t)c * VEC;
-                if (VEC == 4)
-                    x[r] = ldg_v4_hint(src, keep);
-                else
-                    x[r].x = ldg_f32_hint(src, keep);
-            }
-        }
-        float acc[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; k++) acc[k] = 0.0f;
-#pragma unroll
-        for (int r = 0; r < SPV; r++) {
-            if (id[r] >= 0) {   // same FMA chain, in the same order, as LatticeGPU.cuh:2575-2585
-                acc[0] = fmaf(x[r].x, w[r], acc[0]);
-                if (VEC == 4) {
-                    acc[1] = fmaf(x[r].y, w[r], acc[1]);
-                    acc[2] = fmaf(x[r].z, w[r], acc[2]);
-                    acc[3] = fmaf(x[r].w, w[r], acc[3]);
+                for (int r = 0; r < SPV; r++) {
+                    x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (id[r] >= 0) {
+                        const float* src = lattice_values + (size_t)id[r] * val_dim + ch;
+                        if (VEC == 4)
+                            x[r] = ldg_v4_hint(src, keep);
+                        else
+                            x[r].x = ldg_f32_hint(src, keep);
+                    }
                 }
+                float acc[VEC];
+#pragma unroll
+                for (int k = 0; k < VEC; k++) acc[k] = 0.0f;
+#pragma unroll
+                for (int r = 0; r < SPV; r++) {
+                    if (id[r] >= 0) {   // same FMA chain, in the same order, as LatticeGPU.cuh:2575-2585
+                        acc[0] = fmaf(x[r].x, w[r], acc[0]);
+                        if (VEC == 4) {
+                            acc[1] = fmaf(x[r].y, w[r], acc[1]);
+                            acc[2] = fmaf(x[r].z, w[r], acc[2]);
+                            acc[3] = fmaf(x[r].w, w[r], acc[3]);
+                        }
+                    }
+                }
+                float* dst = out + (size_t)p * val_dim + ch;
+                if (VEC == 4)
+                    __stcs(reinterpret_cast<float4*>(dst), make_float4(acc[0], acc[1], acc[2], acc[3]));
+                else
+                    __stcs(dst, acc[0]);
             }
+#pragma unroll
+            for (int r = 0; r < SPV; r++) {
+                id[r] = idn[r];
+                w[r] = wn[r];
+            }
+            p = pn;
         }
-        float* dst = out + (size_t)p * val_dim + (size_t)c * VEC;
-        if (VEC == 4)
-            __stcs(reinterpret_cast<float4*>(dst), make_float4(acc[0], acc[1], acc[2], acc[3]));
-        else
-            __stcs(dst, acc[0]);
     }
 }
 
 // rows[idx[p,r], :] += src[p, :] * w[p,r]: the backward of slice AND the value accumulation of splat
 // (splatCacheNaive, LatticeGPU.cuh:926-973) are this one scatter.  Lanes run along the channels of one point, so
-// every reduction instruction is a run of coalesced 16-byte vector REDs (red.global.add.v4.f32).
+// every reduction instruction is a run of coalesced 16-byte vector REDs (red.global.add.v4.f32).  The L2's reduction
+// units bound it (1 GB of RED payload per 1M points x 64 channels; ncu: lts throughput 60 %), the slabs keep the
+// read-modify-write lines of the table from bouncing to HBM.
 template <int VEC, int SPV>
 __global__ void __launch_bounds__(kBlock)
 scatter_rows_kernel(const float* __restrict__ src, const int* __restrict__ indices,
-                    const float* __restrict__ weights, int n, int val_dim, int lpp_log2,
+                    const float* __restrict__ weights, int n, int val_dim, int slab_ch, int n_slabs, int lpp_log2,
                     float* __restrict__ rows) {
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long p = tid >> lpp_log2;
-    if (p >= n) return;
-    const int g = (int)(tid & ((1 << lpp_log2) - 1));
     const int lpp = 1 << lpp_log2;
-    const int vpr = val_dim / VEC;
+    const int g = threadIdx.x & (lpp - 1);
+    const int pts_per_block = kBlock >> lpp_log2;
+    const long long p_first = (long long)blockIdx.x * pts_per_block + (threadIdx.x >> lpp_log2);
+    const long long p_stride = (long long)gridDim.x * pts_per_block;
     const uint64_t keep = l2_policy_evict_last();
-    int id[SPV];
-    float w[SPV];
-    load_simplex<SPV>(indices, weights, p, id, w);
-    for (int c = g; c < vpr; c += lpp) {
-        const float* s = src + (size_t)p * val_dim + (size_t)c * VEC;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (VEC == 4)
-            x = __ldcs(reinterpret_cast<const float4*>(s));
-        else
-            x.x = __ldcs(s);
-#pragma unroll
-        for (int r = 0; r < SPV; r++) {
-            if (id[r] < 0) continue;
-            float* dst = rows + (size_t)id[r] * val_dim + (size_t)c * VEC;
+    for (int slab = 0; slab < n_slabs; slab++) {
+        const int ch_begin = slab * slab_ch;
+        const int ch_end = min(val_dim, ch_begin + slab_ch);
+        const int ch0 = ch_begin + g * VEC;            // first chunk of this lane (the common case has exactly one)
+        auto load_src = [&](long long pp, int ch) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* s = src + (size_t)pp * val_dim + ch;
             if (VEC == 4)
-                red_v4_hint(dst, make_float4(x.x * w[r], x.y * w[r], x.z * w[r], x.w * w[r]), keep);
+                v = __ldcs(reinterpret_cast<const float4*>(s));
             else
-                red_f32_hint(dst, x.x * w[r], keep);
+                v.x = __ldcs(s);
+            return v;
+        };
+        long long p = p_first;
+        int id[SPV], idn[SPV];
+        float w[SPV], wn[SPV];
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), xn = x;
+        if (p < n) {
+            load_simplex<SPV>(indices, weights, p, id, w);
+            if (ch0 < ch_end) x = load_src(p, ch0);
+        }
+        while (p < n) {
+            const long long pn = p + p_stride;
+            if (pn < n) {
+                load_simplex<SPV>(indices, weights, pn, idn, wn);
+                if (ch0 < ch_end) xn = load_src(pn, ch0);
+            }
+            for (int ch = ch0; ch < ch_end; ch += lpp * VEC) {
+                if (ch != ch0) x = load_src(p, ch);
+#pragma unroll
+                for (int r = 0; r < SPV; r++) {
+                    if (id[r] < 0) continue;
+                    float* dst = rows + (size_t)id[r] * val_dim + ch;
+                    if (VEC == 4)
+                        red_v4_hint(dst, make_float4(x.x * w[r], x.y * w[r], x.z * w[r], x.w * w[r]), keep);
+                    else
+                        red_f32_hint(dst, x.x * w[r], keep);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < SPV; r++) {
+                id[r] = idn[r];
+                w[r] = wn[r];
+            }
+            x = xn;
+            p = pn;
         }
     }
 }
 
 int launch_scatter_rows(const float* src, const int* indices, const float* weights, int n, int pos_dim, int val_dim,
-                        float* rows, cudaStream_t s, const char* what) {
+                        int nr_vertices, float* rows, cudaStream_t s, const char* what) {
     const int vec = (val_dim % 4 == 0) ? 4 : 1;
-    const int lpp = lanes_per_point(val_dim / vec);
-    const int grid = cdiv((long long)n * lpp, kBlock);
     const int spv = pos_dim + 1;
     if (spv != 4 && spv != 6) {
         set_error("%s: pos_dim %d not built (3 and 5 are)", what, pos_dim);
         return LN_ERR_UNSUPPORTED;
     }
-#define LN_LAUNCH_SCATTER(VEC, SPV) scatter_rows_kernel<VEC, SPV><<<grid, kBlock, 0, s>>>(src, indices, weights, n, val_dim, ilog2(lpp), rows)
+#define LN_LAUNCH_SCATTER(VEC, SPV)                                                                                  \
+    do {                                                                                                             \
+        static const int resident = blocks_per_sm((const void*)scatter_rows_kernel<VEC, SPV>);                       \
+        const SlabPlan pl = plan_slabs(n, nr_vertices, val_dim, VEC, resident);                                      \
+        scatter_rows_kernel<VEC, SPV><<<pl.grid, kBlock, 0, s>>>(src, indices, weights, n, val_dim, pl.slab_ch, pl.n_slabs, pl.lpp_log2, rows); \
+    } while (0)
     if (vec == 4) {
         if (spv == 4) LN_LAUNCH_SCATTER(4, 4); else LN_LAUNCH_SCATTER(4, 6);
     } else {
@@ -435,15 +538,18 @@ using namespace ln;
 extern "C" {
 
 int ln_slice_fwd(const float* lattice_values, const int* indices, const float* weights, int n, int pos_dim,
-                 int val_dim, float* out, void* stream) {
+                 int val_dim, int nr_vertices, float* out, void* stream) {
     LN_REQUIRE(lattice_values && indices && weights && out, "ln_slice_fwd: null pointer");
     LN_SLICE_ARGS_OK("ln_slice_fwd");
     if (n == 0) return LN_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const int vec = (val_dim % 4 == 0) ? 4 : 1;
-    const int lpp = lanes_per_point(val_dim / vec);
-    const int grid = cdiv((long long)n * lpp, kBlock);
-#define LN_LAUNCH_SLICE(VEC, SPV) slice_fwd_kernel<VEC, SPV><<<grid, kBlock, 0, s>>>(lattice_values, indices, weights, n, val_dim, ilog2(lpp), out)
+#define LN_LAUNCH_SLICE(VEC, SPV)                                                                                    \
+    do {                                                                                                             \
+        static const int resident = blocks_per_sm((const void*)slice_fwd_kernel<VEC, SPV>);                          \
+        const SlabPlan pl = plan_slabs(n, nr_vertices, val_dim, VEC, resident);                                      \
+        slice_fwd_kernel<VEC, SPV><<<pl.grid, kBlock, 0, s>>>(lattice_values, indices, weights, n, val_dim, pl.slab_ch, pl.n_slabs, pl.lpp_log2, out); \
+    } while (0)
     const int spv = pos_dim + 1;
     if (spv != 4 && spv != 6) {
         set_error("ln_slice_fwd: pos_dim %d not built (3 and 5 are)", pos_dim);
@@ -460,11 +566,11 @@ int ln_slice_fwd(const float* lattice_values, const int* indices, const float* w
 }
 
 int ln_slice_bwd(const float* grad_out, const int* indices, const float* weights, int n, int pos_dim, int val_dim,
-                 float* grad_values, void* stream) {
+                 int nr_vertices, float* grad_values, void* stream) {
     LN_REQUIRE(grad_out && indices && weights && grad_values, "ln_slice_bwd: null pointer");
     LN_SLICE_ARGS_OK("ln_slice_bwd");
     if (n == 0) return LN_OK;
-    return launch_scatter_rows(grad_out, indices, weights, n, pos_dim, val_dim, grad_values, (cudaStream_t)stream, "slice_bwd");
+    return launch_scatter_rows(grad_out, indices, weights, n, pos_dim, val_dim, nr_vertices, grad_values, (cudaStream_t)stream, "slice_bwd");
 }
 
 int ln_gather_fwd(const float* lattice_values, const int* indices, const float* weights, int n, int pos_dim,

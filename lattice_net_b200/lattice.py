@@ -402,7 +402,7 @@ class Lattice:
         if n > 0:
             call("ln_splat_build", ptr(pos), ptr(self._sigmas_on(st.device)), n, d, ptr(st.keys), ptr(st.entries),
                  ptr(st.nr_filled), ptr(st.status), st.capacity, st.bound or 0, ptr(idx), ptr(w), s)
-            call("ln_splat_accumulate", ptr(val), ptr(idx), ptr(w), n, d, v, ptr(ht.m_values_tensor), s)
+            call("ln_splat_accumulate", ptr(val), ptr(idx), ptr(w), n, d, v, 0, ptr(ht.m_values_tensor), s)
         st.mark_dirty()
         return idx, w
 
@@ -668,7 +668,7 @@ class Lattice:
         n, d, idx, w = self._slice_prep(positions_raw, splatting_indices, splatting_weights)
         vals = self.values().contiguous()
         out = torch.empty((n, self.val_dim()), dtype=torch.float32, device=vals.device)
-        call("ln_slice_fwd", ptr(vals), ptr(idx), ptr(w), n, d, self.val_dim(), ptr(out), stream_ptr(vals.device))
+        call("ln_slice_fwd", ptr(vals), ptr(idx), ptr(w), n, d, self.val_dim(), int(vals.shape[0]), ptr(out), stream_ptr(vals.device))
         return out
 
     def slice_standalone_no_precomputation(self, positions_raw):
@@ -740,7 +740,7 @@ class Lattice:
         st = self._structure()
         v = int(grad_sliced_values.shape[1])
         grad = torch.zeros((st.nr_vertices(), v), dtype=torch.float32, device=st.device)
-        call("ln_slice_bwd", ptr(grad_sliced_values), ptr(idx), ptr(w), n, d, v, ptr(grad), stream_ptr(st.device))
+        call("ln_slice_bwd", ptr(grad_sliced_values), ptr(idx), ptr(w), n, d, v, int(grad.shape[0]), ptr(grad), stream_ptr(st.device))
         self.m_hash_table.m_values_tensor = grad
 
     def gather_backwards_standalone_with_precomputation(self, positions_raw, grad_sliced_values, splatting_indices, splatting_weights):
