@@ -282,7 +282,7 @@ def run_ours(args):
     if rank != 0:
         return
     roof = kernel_roofline(device)
-    cpu = cpu_baseline(model)
+    cpu = cpu_baseline(model) if not args.no_cpu_baseline else None
     scans = args.steps * world
     h2d = NR_POINTS * (3 * 4 + 1 * 4 + 8)
     line = {
@@ -335,6 +335,7 @@ def main():
     ap.add_argument("--capture-collective", action="store_true", help="N>1: capture the NCCL all-reduce inside the step graph")
     ap.add_argument("--conv-precision", type=int, default=1, choices=[0, 1, 2],
                     help="0 fp32 CUDA cores, 1 tcgen05 3xTF32 (fp32-equivalent, default), 2 tcgen05 TF32")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s CPU leg (profiler passes only; never for a reported line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
