@@ -278,11 +278,20 @@ def run_ours(args):
     ms_e2e = timed_region(step_e2e, args.steps, world, device, flush_buf)
     clocks = sampler.stop() if rank == 0 else None
     overflowed = step.overflowed_steps() if graphed else 0
+    in_sync = None
+    if world > 1:
+        # every rank applied the same all-reduced gradients to the same broadcast parameters: the replicas must be bit-identical
+        import torch.distributed as dist
+        flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+        digest = torch.stack([flat.double().sum(), flat.double().abs().sum()])
+        digests = [torch.empty_like(digest) for _ in range(world)]
+        dist.all_gather(digests, digest)
+        in_sync = all(bool(torch.equal(d, digests[0])) for d in digests)
 
     if rank != 0:
         return
     roof = kernel_roofline(device)
-    cpu = cpu_baseline(model) if not args.no_cpu_baseline else None
+    cpu = cpu_baseline(model) if (world == 1 and not args.no_cpu_baseline) else None     # reported at N=1 only
     scans = args.steps * world
     h2d = NR_POINTS * (3 * 4 + 1 * 4 + 8)
     line = {
@@ -292,6 +301,7 @@ def run_ours(args):
         "config": {"workload": "LatticeNet ShapeNet-part segmentation fwd+bwd+AdamW (lnn_train_shapenet.cfg arch), 2048-pt synthetic clouds, 1 scene/step/GPU",
                    "nr_points": NR_POINTS, "nr_classes": NR_CLASSES, "sigma": SIGMA, "hash_table_capacity": CAPACITY,
                    "parallelism": f"scene-parallel dp{world}, one flat NCCL all-reduce of {bucket.nbytes} grad bytes/step",
+                   "replicas_bit_identical_after_run": in_sync,
                    "execution": ("one CUDA graph per step (static-shape lattice, rows per level %s; %d step(s) skipped for exceeding them)" % (bounds, overflowed))
                                 if graphed else "eager launches (dynamic-shape lattice)",
                    "l2": f"flushed between steps by a {L2_FLUSH_BYTES >> 20} MiB write (inside the timed region)",

@@ -143,7 +143,8 @@ int ln_row2im(const float* rowified, const int* neighbours, int nv, int filter_e
  * -- the transpose/view/contiguous re-layout of lattice_funcs.py:304-311 without materialising it.
  * precision: 0 = exact fp32 FMA on the CUDA cores; 1 = tcgen05 tensor cores, 3xTF32 split (fp32-equivalent,
  * ~1e-6 relative); 2 = tcgen05 single-pass TF32 (~1e-3 relative).  The tensor-core path needs
- * c_in % 32 == 0 and c_out <= 256; other shapes run the fp32 kernel whatever `precision` says.
+ * c_in % 32 == 0 and c_out <= 1024 (layers wider than 256 run as 256-column chunks); other shapes run the fp32 kernel
+ * whatever `precision` says.
  * workspace: device scratch of ln_conv_workspace_bytes() bytes for precision 1/2 (re-laid-out filter),
  * may be NULL for precision 0.  bias may be NULL. */
 int ln_conv_fwd(const float* nbr_values, const int* neighbours, const float* filter, const float* bias,
@@ -155,7 +156,7 @@ long long ln_conv_workspace_bytes(int filter_extent, int c_in, int c_out, int pr
  *   grad_filter[slot*c_in + ci, co] = sum_q nbr_values[neighbours[q, slot], ci] * grad_out[q, co]
  * grad_filter [F*c_in x c_out] is overwritten (zeroed, then accumulated with fp32 reductions).
  * precision as in ln_conv_fwd: 1 / 2 run the gathered-A^T . G product on tcgen05 (MN-major operands, the
- * reduction runs over the vertices) when c_in % 32 == 0 and c_out % 4 == 0, c_out <= 256; else fp32 FMA. */
+ * reduction runs over the vertices) when c_in % 32 == 0 and c_out % 4 == 0, c_out <= 1024 (256-column chunks); else fp32 FMA. */
 int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* grad_out,
                   int nv_query, int filter_extent, int c_in, int c_out, int precision,
                   float* grad_filter, void* stream);

@@ -166,7 +166,7 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
 // B^T (n-major rows, 32 k-values each) already in the 128B-swizzled order the UMMA descriptor expects:
 // 16-byte chunk j of row n sits at chunk position j ^ (n % 8).  hi = tf32(W), lo = tf32(W - hi).
 __global__ void __launch_bounds__(256)
-filter_prep_kernel(const float* __restrict__ filter, int k_total, int c_in, int c_out, int n_pad, int split,
+filter_prep_kernel(const float* __restrict__ filter, int k_total, int c_in, int c_out, int ld_n, int n_off, int n_pad, int split,
                    int transposed, float* __restrict__ b_hi, float* __restrict__ b_lo,
                    float* __restrict__ zero_a, long long n_a, float* __restrict__ zero_b, long long n_b) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,15 +182,16 @@ filter_prep_kernel(const float* __restrict__ filter, int k_total, int c_in, int 
     const int n = (int)(rest % n_pad);
     const int kb = (int)(rest / n_pad);
     const int k = kb * kBlockK + kk;
-    // transposed: `filter` is the forward bank [F*c_out x c_in] of the convolution whose data gradient this is
-    // (element (slot, k, n) lives at [(slot*c_out + n), k]), lattice_funcs.py:304-311 without the copy
+    // transposed: `filter` is the forward bank [F*ld_n x c_in] of the convolution whose data gradient this is
+    // (element (slot, k, n) lives at [(slot*ld_n + n), k]), lattice_funcs.py:304-311 without the copy.
+    // This launch prepares output channels [n_off, n_off + c_out) of a bank that is ld_n channels wide (N chunking).
     float w = 0.0f;
     if (n < c_out) {
         if (transposed) {
             const int slot = k / c_in, ci = k - slot * c_in;
-            w = __ldg(filter + ((size_t)slot * c_out + n) * c_in + ci);
+            w = __ldg(filter + ((size_t)slot * ld_n + n_off + n) * c_in + ci);
         } else {
-            w = __ldg(filter + (size_t)k * c_out + n);
+            w = __ldg(filter + (size_t)k * ld_n + n_off + n);
         }
     }
     const int chunk = kk >> 2, within = kk & 3;
@@ -389,7 +390,7 @@ template <int kSplit>   // 1: 3xTF32, 0: single pass
 __global__ void __launch_bounds__(kTc2Threads, 1)
 conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighbours,
                 const float* __restrict__ b_hi, const float* __restrict__ b_lo, const float* __restrict__ bias,
-                int nv_query, int F, int c_in, int c_out, int n_pad, int flip, int stages, int lookahead,
+                int nv_query, int F, int c_in, int c_out, int ld_out, int n_pad, int flip, int stages, int lookahead,
                 int m_tiles, int n_items, int kb_per_split, int truncating_operand, float* __restrict__ out) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t b_tile_bytes = (uint32_t)n_pad * kRowBytes;
@@ -620,7 +621,7 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
             tc_fence_after();
             const int q = w.q0 + quad * 32 + lane;
             const bool live = q < nv_query;
-            float* orow = out + (size_t)q * c_out;
+            float* orow = out + (size_t)q * ld_out;     // `out` / `bias` already point at this launch's first channel
             const bool add_bias = bias != nullptr && w.split == 0;
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * n_pad);
             for (int n0 = 0; n0 < n_pad; n0 += 32) {
@@ -633,7 +634,7 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
                     for (int k = 16; k < 32; k++) acc[k] = 0.0f;
                 }
                 if (!live) continue;
-                if ((c_out & 3) == 0) {
+                if (((c_out | ld_out) & 3) == 0) {      // 16-byte aligned rows and whole float4 groups
 #pragma unroll
                     for (int k = 0; k < 32; k += 4) {
                         if (n0 + k < c_out) {
@@ -678,7 +679,10 @@ size_t conv_tc_workspace_bytes(int F, int c_in, int c_out) {
     return (size_t)2 * F * c_in * n_pad * sizeof(float);
 }
 
-bool conv_tc_supported(int F, int c_in, int c_out) { return c_in % kBlockK == 0 && c_out >= 1 && c_out <= 256 && F >= 3; }
+// One launch covers up to kMaxTileN output channels (UMMA N <= 256, two accumulator buffers = all 512 TMEM columns);
+// wider layers (the 384- and 512-channel levels of the SemanticKITTI architecture) run as chunks of kMaxTileN columns.
+constexpr int kMaxTileN = 256;
+constexpr int kMaxCoutTc = 1024;
 
 static int env_int(const char* name, int dflt) {   // development knobs, read on every call (cheap: a few per launch)
     const char* e = getenv(name);
@@ -691,6 +695,9 @@ static bool use_v1() {   // development switch: LN_CONV_TC_V1=1 selects the firs
         v = (e != nullptr && e[0] == '1') ? 1 : 0;
     }
     return v == 1;
+}
+bool conv_tc_supported(int F, int c_in, int c_out) {
+    return c_in % kBlockK == 0 && c_out >= 1 && c_out <= (use_v1() ? kMaxTileN : kMaxCoutTc) && F >= 3;
 }
 // Opt a kernel into the full 227 KB of dynamic shared memory ONCE per (kernel, device), not per launch: the call is
 // not free on the host, and an attribute change in the middle of a stream capture trips profilers.
@@ -748,7 +755,7 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32_mn(int m, int n) {   // as u
 template <int kSplit>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ neighbours,
-                     const float* __restrict__ grad_out, int nv_query, int F, int c_in, int c_out, int n_pad,
+                     const float* __restrict__ grad_out, int nv_query, int F, int c_in, int c_out, int ld_g, int n_pad,
                      int ci_tiles, int q_splits, int chunks_per_split, int stages, int lookahead,
                      float* __restrict__ grad_filter) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -833,7 +840,7 @@ conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ n
         };
         int q = chunk_begin * kWgRows + r;
         const int* nbr_p = neighbours + (size_t)q * F + slot;
-        const float* g_p = grad_out + (size_t)q * c_out + cc * 4;
+        const float* g_p = grad_out + (size_t)q * ld_g + cc * 4;     // ld_g: full width of grad_out / grad_filter rows (N chunking)
         const float* a_col = values + ci0 + cc * 4;
         // the neighbour id of a row is needed before its copies can be issued: it is requested one chunk ahead, so
         // its latency overlaps the wait for a free stage instead of serialising every iteration of this loop
@@ -857,7 +864,7 @@ conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ n
             in_flight++;
             q += kWgRows;
             nbr_p += (size_t)kWgRows * F;
-            g_p += (size_t)kWgRows * c_out;
+            g_p += (size_t)kWgRows * ld_g;
             issue_addr += stage_bytes;
             issue_full += 8;
             issue_empty += 8;
@@ -887,7 +894,7 @@ conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ n
             tc_fence_after();
             const int m = warp * 32 + lane;
             const bool live = m < ci_n;
-            float* orow = grad_filter + ((size_t)slot * c_in + ci0 + m) * c_out;
+            float* orow = grad_filter + ((size_t)slot * c_in + ci0 + m) * ld_g;
             for (int n0 = 0; n0 < n_pad; n0 += 16) {
                 float acc[16];
                 tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, acc);
@@ -952,12 +959,12 @@ conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ n
 }
 
 bool conv_wgrad_tc_supported(int F, int c_in, int c_out) {
-    return c_in % 32 == 0 && c_out % 4 == 0 && c_out >= 4 && c_out <= 256 && F >= 3;
+    return c_in % 32 == 0 && c_out % 4 == 0 && c_out >= 4 && c_out <= kMaxCoutTc && F >= 3;
 }
 
 // grad_filter must be zero when q_splits > 1 (the caller clears it).  Returns the number of vertex-range splits used.
-int conv_wgrad_tc(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query, int F, int c_in,
-                  int c_out, int precision, float* grad_filter, cudaStream_t s) {
+static int conv_wgrad_tc_chunk(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query, int F, int c_in,
+                               int c_out, int ld_g, int precision, float* grad_filter, cudaStream_t s) {
     const int split = precision == 1 ? 1 : 0;
     const int n_pad = (c_out + 15) / 16 * 16;
     const int n_groups = (n_pad + 31) / 32;
@@ -984,12 +991,12 @@ int conv_wgrad_tc(const float* nbr_values, const int* neighbours, const float* g
     if (split) {
         err = allow_max_smem((const void*)conv_wgrad_tc_kernel<1>);
         if (err == cudaSuccess)
-            conv_wgrad_tc_kernel<1><<<grid, kWgThreads, smem, s>>>(nbr_values, neighbours, grad_out, nv_query, F, c_in, c_out, n_pad, ci_tiles,
+            conv_wgrad_tc_kernel<1><<<grid, kWgThreads, smem, s>>>(nbr_values, neighbours, grad_out, nv_query, F, c_in, c_out, ld_g, n_pad, ci_tiles,
                                                                     q_splits, chunks_per_split, stages, lookahead, grad_filter);
     } else {
         err = allow_max_smem((const void*)conv_wgrad_tc_kernel<0>);
         if (err == cudaSuccess)
-            conv_wgrad_tc_kernel<0><<<grid, kWgThreads, smem, s>>>(nbr_values, neighbours, grad_out, nv_query, F, c_in, c_out, n_pad, ci_tiles,
+            conv_wgrad_tc_kernel<0><<<grid, kWgThreads, smem, s>>>(nbr_values, neighbours, grad_out, nv_query, F, c_in, c_out, ld_g, n_pad, ci_tiles,
                                                                     q_splits, chunks_per_split, stages, lookahead, grad_filter);
     }
     if (err != cudaSuccess) {
@@ -1000,11 +1007,24 @@ int conv_wgrad_tc(const float* nbr_values, const int* neighbours, const float* g
     return check_launch("conv_wgrad_tc");
 }
 
-// after_prep (optional): recorded on `s` once the filter-prep kernel (which also clears `also_zero`) is enqueued, so a
-// second stream can start work that depends on the clearing while this stream runs the convolution itself.
-int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
-                int F, int c_in, int c_out, int flip, int precision, int transposed, float* workspace, float* out,
-                float* also_zero, long long also_zero_n, cudaStream_t s, cudaEvent_t after_prep) {
+int conv_wgrad_tc(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query, int F, int c_in,
+                  int c_out, int precision, float* grad_filter, cudaStream_t s) {
+    // column chunks of grad_out / grad_filter (row stride c_out): each chunk is an independent GEMM over the same gathered A
+    for (int n_off = 0; n_off < c_out; n_off += kMaxTileN) {
+        const int rc = conv_wgrad_tc_chunk(nbr_values, neighbours, grad_out + n_off, nv_query, F, c_in, min(kMaxTileN, c_out - n_off),
+                                           c_out, precision, grad_filter + n_off, s);
+        if (rc != LN_OK) return rc;
+    }
+    return LN_OK;
+}
+
+// One launch pair (filter prep + convolution) for output channels [n_off, n_off + c_out) of a layer that is ld_n wide.
+// `out` / `bias` point at the layer's first channel; `workspace` at this chunk's slabs.  zero_out: clear ALL of `out`
+// (nv_query x ld_n) in the prep kernel when K is split across CTAs (done by the first chunk only).
+static int conv_fwd_tc_chunk(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
+                             int F, int c_in, int c_out, int ld_n, int n_off, bool zero_out, int flip, int precision, int transposed,
+                             float* workspace, float* out, float* also_zero, long long also_zero_n, cudaStream_t s,
+                             cudaEvent_t after_prep) {
     const int n_pad = (c_out + 15) / 16 * 16;
     const int k_total = F * c_in;
     const int split = precision == 1 ? 1 : 0;
@@ -1019,14 +1039,16 @@ int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* fil
     splits = cdiv(num_kb, kb_per_split);
     {
         const long long total = (long long)k_total * n_pad;
-        filter_prep_kernel<<<cdiv(total, 256), 256, 0, s>>>(filter, k_total, c_in, c_out, n_pad, split, transposed, b_hi, b_lo,
-                                                            out, splits > 1 ? (long long)nv_query * c_out : 0, also_zero, also_zero_n);
+        filter_prep_kernel<<<cdiv(total, 256), 256, 0, s>>>(filter, k_total, c_in, c_out, ld_n, n_off, n_pad, split, transposed, b_hi, b_lo,
+                                                            out, (splits > 1 && zero_out) ? (long long)nv_query * ld_n : 0, also_zero, also_zero_n);
         count_launch();
         if (after_prep != nullptr && cudaEventRecord(after_prep, s) != cudaSuccess) return check_launch("conv_fwd_tc event");
     }
     const size_t b_tile = (size_t)n_pad * kRowBytes;
     const size_t stage_bytes = (split ? 2 : 1) * (kATileBytes + b_tile);
     cudaError_t err;
+    float* out_chunk = out + n_off;
+    const float* bias_chunk = bias != nullptr ? bias + n_off : nullptr;
     if (!use_v1()) {
         // persistent kernel: one CTA per SM, items = (M tile, K split)
         const size_t fixed = (size_t)2 * kTileM * F * sizeof(int) + 16 + (2 * kMaxStages + 4) * 8 + 16 + 1024;
@@ -1047,13 +1069,13 @@ int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* fil
         if (split) {
             err = allow_max_smem((const void*)conv_tc2_kernel<1>);
             if (err == cudaSuccess)
-                conv_tc2_kernel<1><<<grid, kTc2Threads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias, nv_query, F, c_in, c_out, n_pad, flip,
-                                                                    stages, lookahead, m_tiles, n_items, kb_per_split, env_int("LN_CONV_TRUNC", 0), out);
+                conv_tc2_kernel<1><<<grid, kTc2Threads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias_chunk, nv_query, F, c_in, c_out, ld_n, n_pad, flip,
+                                                                    stages, lookahead, m_tiles, n_items, kb_per_split, env_int("LN_CONV_TRUNC", 0), out_chunk);
         } else {
             err = allow_max_smem((const void*)conv_tc2_kernel<0>);
             if (err == cudaSuccess)
-                conv_tc2_kernel<0><<<grid, kTc2Threads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias, nv_query, F, c_in, c_out, n_pad, flip,
-                                                                    stages, lookahead, m_tiles, n_items, kb_per_split, 0, out);
+                conv_tc2_kernel<0><<<grid, kTc2Threads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias_chunk, nv_query, F, c_in, c_out, ld_n, n_pad, flip,
+                                                                    stages, lookahead, m_tiles, n_items, kb_per_split, 0, out_chunk);
         }
         if (err != cudaSuccess) {
             set_error("conv_tc2: %s", cudaGetErrorString(err));
@@ -1061,6 +1083,10 @@ int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* fil
         }
         count_launch();
         return check_launch("conv_tc2");
+    }
+    if (ld_n != c_out) {
+        set_error("ln_conv_fwd: the first-generation kernel (LN_CONV_TC_V1) handles at most %d output channels", kMaxTileN);
+        return LN_ERR_UNSUPPORTED;
     }
     const size_t fixed = (size_t)kTileM * F * sizeof(int) + 16 + (2 * 8 + 1) * 8 + 16 + 1024;
     int stages = (int)((227 * 1024 - fixed) / stage_bytes);
@@ -1087,6 +1113,22 @@ int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* fil
     }
     count_launch();
     return check_launch("conv_fwd_tc");
+}
+
+// after_prep (optional): recorded on `s` once the first filter-prep kernel (which also clears `also_zero`) is enqueued, so a
+// second stream can start work that depends on the clearing while this stream runs the convolution itself.
+int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
+                int F, int c_in, int c_out, int flip, int precision, int transposed, float* workspace, float* out,
+                float* also_zero, long long also_zero_n, cudaStream_t s, cudaEvent_t after_prep) {
+    // workspace: chunk j's slabs follow those of the chunks before it (all kMaxTileN wide, so 2 * K * n_off floats)
+    for (int n_off = 0; n_off < c_out; n_off += kMaxTileN) {
+        const bool first = n_off == 0;
+        const int rc = conv_fwd_tc_chunk(nbr_values, neighbours, filter, bias, nv_query, F, c_in, min(kMaxTileN, c_out - n_off), c_out, n_off,
+                                         first, flip, precision, transposed, workspace + (size_t)2 * F * c_in * n_off, out,
+                                         first ? also_zero : nullptr, first ? also_zero_n : 0, s, first ? after_prep : nullptr);
+        if (rc != LN_OK) return rc;
+    }
+    return LN_OK;
 }
 
 }  // namespace ln

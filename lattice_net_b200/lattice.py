@@ -565,7 +565,7 @@ class Lattice:
 
     @staticmethod
     def _conv_ws_bytes(F, c_in, c_out):
-        if CONV_PRECISION == 0 or c_in % 32 != 0 or c_out > 256:
+        if CONV_PRECISION == 0 or c_in % 32 != 0 or c_out > 1024:     # conv_tc_supported(), ln_conv_tc.cu
             return 0
         return 2 * F * c_in * ((c_out + 15) // 16 * 16) * 4      # == ln_conv_workspace_bytes()
 

@@ -31,8 +31,8 @@ POS_DIMS = (3, 5)
 # (kernel, template-arg tuples).  V / nc lists cover the test + bench configurations.
 VALS_SMALL = (1, 3, 4, 8)
 VALS_ALL = (1, 3, 4, 8, 16, 32, 64, 128)
-VALS_CONV = (1, 3, 4, 8, 16, 32, 64, 96, 128, 192, 256)   # channel widths met by the LatticeNet architectures
-CLASSIFY = ((32, 7), (64, 16), (128, 7), (128, 20), (8, 4))
+VALS_CONV = (1, 3, 4, 8, 16, 32, 64, 96, 128, 192, 256, 384, 512)   # channel widths met by the LatticeNet architectures (ShapeNet, ScanNet, SemanticKITTI)
+CLASSIFY = ((32, 7), (64, 16), (128, 7), (128, 20), (8, 4), (256, 20), (128, 21))
 
 
 def name_expressions():

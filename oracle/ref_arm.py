@@ -248,6 +248,19 @@ def _ref_conv_module_forward(self, lattice_values, lattice_structure):
     return lv, new
 
 
+def patch_modules():
+    """Route the module layer to the reference mechanisms (no kernel of this repo stays on the path).  Process-wide:
+    the reference arm always runs in its own process."""
+    import lattice_net_b200.lattice_modules as lm
+    from lattice_net_b200 import Lattice as _L
+    RefKernels.get()
+    lm.scatter_max = lambda src, index, nv: _torch_scatter_max(src, index, nv)
+    lm.scatter_sum_count = _torch_scatter_sum_count
+    lm.ConvLatticeIm2RowModule.forward = _ref_conv_module_forward
+    lm.FUSED_NORM_MAX_ELEMS_PER_GROUP = 0      # torch GroupNorm + ReLU, as in the reference
+    _L.m_expected_position_dimensions = 3            # static pos-dim the module constructors read
+
+
 def run(args, cloud_fn, cfg):
     import lattice_net_b200.lattice_modules as lm
     from lattice_net_b200 import ModelParams
@@ -258,13 +271,7 @@ def run(args, cloud_fn, cfg):
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     torch.manual_seed(0)
-    RefKernels.get()
-    # route the module layer to the reference mechanisms (no kernel of this repo stays on the path)
-    lm.scatter_max = lambda src, index, nv: _torch_scatter_max(src, index, nv)
-    lm.scatter_sum_count = _torch_scatter_sum_count
-    lm.ConvLatticeIm2RowModule.forward = _ref_conv_module_forward
-    lm.FUSED_NORM_MAX_ELEMS_PER_GROUP = 0      # torch GroupNorm + ReLU, as in the reference
-    _L.m_expected_position_dimensions = 3            # static pos-dim the module constructors read
+    patch_modules()
     model = LNN(cfg["nr_classes"], ModelParams(), device=dev)
     pool = 16
     clouds = [cloud_fn(i) for i in range(pool)]

@@ -464,6 +464,37 @@ def test_conv_tensor_core(built, Cin, Cout, precision, tol):
         lattice_mod.set_conv_precision(0)
 
 
+@pytest.mark.parametrize("Cin,Cout", [(64, 512), (512, 64), (384, 384)])
+def test_conv_tensor_core_wide_layers(built, Cin, Cout):
+    """Layers wider than one UMMA tile (the 384 / 512-channel levels of the SemanticKITTI architecture) run on the
+    tensor cores as 256-column chunks: forward (+bias), weight gradient and the transposed-filter data gradient of
+    ln_conv_bwd must all match the oracle inside the fp32 parity tolerance (3xTF32; 5e-5 of the output scale at K up to 13*512)."""
+    from lattice_net_b200 import lattice as lattice_mod
+    b = built
+    if b["name"] not in ("shapenet", "d5"):
+        pytest.skip("one 3-D and one 5-D lattice cover the chunking")
+    F = 2 * (b["d"] + 1) + 1
+    lv = cases.randn((b["nv"], Cin), 170 + Cin)
+    fb = (cases.randn((F * Cin, Cout), 161) * 0.05).astype(np.float32)
+    bias = cases.randn((Cout,), 162)
+    g = cases.randn((b["nv"], Cout), 190 + Cout)
+    ours = b["ours"].clone_lattice()
+    ours.set_values(cuda(lv[b["o2n"]]))
+    table = lo.neighbour_table(b["ks"], b["ks"], 0, 1)
+    try:
+        lattice_mod.set_conv_precision(1)
+        out = ours.convolve_im2row_standalone(cuda(fb), 1, ours, False, bias=cuda(bias))
+        got = out.values().cpu().numpy()[b["n2o"]]
+        assert_close(got, lo.conv_fwd(lv, table, fb) + bias, 5e-5, "wide tensor-core conv forward")
+        query = ours.clone_lattice()
+        grad_in, grad_filter = query.conv_backward(ours, cuda(g[b["o2n"]]), cuda(fb), 1)
+    finally:
+        lattice_mod.set_conv_precision(0)
+    assert_close(grad_filter.cpu().numpy(), lo.conv_wgrad(lv, table, g), 5e-5, "wide tensor-core weight gradient")
+    exp_dg = lo.conv_fwd(g, table, lo.filter_for_dgrad(fb, F, Cin, Cout), flip=True)
+    assert_close(grad_in.cpu().numpy()[b["n2o"]], exp_dg, 5e-5, "wide tensor-core data gradient")
+
+
 def test_conv_tensor_core_cross_level(built):
     from lattice_net_b200 import lattice as lattice_mod
     b = built
