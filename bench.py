@@ -302,7 +302,9 @@ def run_ours(args):
                    "nr_points": NR_POINTS, "nr_classes": NR_CLASSES, "sigma": SIGMA, "hash_table_capacity": CAPACITY,
                    "parallelism": f"scene-parallel dp{world}, one flat NCCL all-reduce of {bucket.nbytes} grad bytes/step",
                    "replicas_bit_identical_after_run": in_sync,
-                   "execution": ("one CUDA graph per step (static-shape lattice, rows per level %s; %d step(s) skipped for exceeding them)" % (bounds, overflowed))
+                   "execution": ("%s (static-shape lattice, rows per level %s; %d step(s) skipped for exceeding them)"
+                                 % ("one CUDA graph per step" + (", NCCL all-reduce captured inside it" if world > 1 else "") if len(step.graphs) == 1
+                                    else "two CUDA graphs per step with an eager NCCL all-reduce between them", bounds, overflowed))
                                 if graphed else "eager launches (dynamic-shape lattice)",
                    "l2": f"flushed between steps by a {L2_FLUSH_BYTES >> 20} MiB write (inside the timed region)",
                    "conv_precision": {0: "fp32 FMA on CUDA cores", 1: "tcgen05 3xTF32 split, fp32 accumulate (fp32-equivalent)", 2: "tcgen05 TF32"}[args.conv_precision]},
@@ -342,7 +344,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="graph: static-shape lattice + one CUDA graph per step (default); eager: dynamic-shape launches")
-    ap.add_argument("--capture-collective", action="store_true", help="N>1: capture the NCCL all-reduce inside the step graph")
+    ap.add_argument("--capture-collective", dest="capture_collective", action="store_true", default=True,
+                    help="N>1: capture the NCCL all-reduce inside the step graph (default; one graph launch per step)")
+    ap.add_argument("--no-capture-collective", dest="capture_collective", action="store_false",
+                    help="N>1: two graphs per step with an eager NCCL all-reduce between them")
     ap.add_argument("--conv-precision", type=int, default=1, choices=[0, 1, 2],
                     help="0 fp32 CUDA cores, 1 tcgen05 3xTF32 (fp32-equivalent, default), 2 tcgen05 TF32")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s CPU leg (profiler passes only; never for a reported line)")

@@ -223,13 +223,18 @@ int ln_scatter_sum_count(const float* src, const int* index, int m, int c, int n
  * [1, c, nv] view the reference builds with unsqueeze/transpose
  * (/root/reference/latticenet_py/lattice/lattice_modules.py:585-614).  stats [groups x 2] = (mean, rstd).
  * nv_dev (device int32, may be NULL): static-shape mode, only the first min(nv, *nv_dev) rows are vertices;
- * the others are excluded from the statistics and written as zeros. */
+ * the others are excluded from the statistics and written as zeros.
+ * workspace: device scratch of ln_group_norm_workspace_bytes(nv, c, groups) bytes (0 for lattices small enough for
+ * the one-CTA-per-group kernels; then it may be NULL).  With it, scene-sized lattices run the row-tiled kernels
+ * (stats partial -> finalize -> apply on all SMs, coalesced, no atomics); without it they fall back to one CTA
+ * per group.  The same size serves forward and backward. */
+long long ln_group_norm_workspace_bytes(int nv, int c, int groups);
 int ln_group_norm_fwd(const float* x, const float* gamma, const float* beta, int nv, const int* nv_dev, int c, int groups,
-                      float eps, int relu, float* y, float* stats, void* stream);
+                      float eps, int relu, float* y, float* stats, float* workspace, void* stream);
 /* y = forward output (needed for the ReLU mask when relu != 0).  dgamma/dbeta [c] are overwritten. */
 int ln_group_norm_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* stats,
                       int nv, const int* nv_dev, int c, int groups, int relu, float* dx, float* dgamma, float* dbeta,
-                      void* stream);
+                      float* workspace, void* stream);
 
 #ifdef __cplusplus
 }

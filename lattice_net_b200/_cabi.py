@@ -40,14 +40,15 @@ _SIGNATURES = {
     "ln_slice_classify_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "ln_scatter_max": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "ln_scatter_sum_count": [_P, _P, _I, _I, _I, _P, _P, _P],
-    "ln_group_norm_fwd": [_P, _P, _P, _I, _P, _I, _I, ctypes.c_float, _I, _P, _P, _P],
-    "ln_group_norm_bwd": [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P],
+    "ln_group_norm_fwd": [_P, _P, _P, _I, _P, _I, _I, ctypes.c_float, _I, _P, _P, _P, _P],
+    "ln_group_norm_bwd": [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P],
 }
 _SPECIAL = {
     "ln_version": (ctypes.c_char_p, []),
     "ln_last_error": (ctypes.c_char_p, []),
     "ln_launch_count": (ctypes.c_longlong, []),
     "ln_conv_workspace_bytes": (ctypes.c_longlong, [_I, _I, _I, _I]),
+    "ln_group_norm_workspace_bytes": (ctypes.c_longlong, [_I, _I, _I]),
     "ln_reset_launch_count": (None, []),
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + list(_SPECIAL))

@@ -322,6 +322,294 @@ group_norm_bwd_small_kernel(const float* __restrict__ dy, const float* __restric
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Row-tiled variants for scene-sized lattices (SemanticKITTI / ScanNet: 10^4..10^5 vertices per level).  The
+// one-CTA-per-group kernels above put 32 CTAs on a 148-SM machine and walk a group's channels at stride C; on a
+// KITTI-sized pass they were 31 % of all kernel time (profiles/r01i_launches_kitti_pass.md).  Here every CTA owns a
+// block of consecutive ROWS and all C channels: loads are whole 16-byte-vectorised rows (coalesced), the grid
+// covers the machine, and the statistics are combined from per-CTA partials in a fixed order (no atomics:
+// results are reproducible run to run).
+//   forward : stats partial (per CTA and group: local mean, centred M2 -- rows cached in registers between the
+//             two passes)  ->  finalize (Chan's parallel combination, one CTA per group)  ->  apply
+//   backward: per-channel partial sums of dy' xhat and dy'  ->  finalize (dgamma, dbeta, per-group ds / db)  ->  apply
+// Thread layout: tpr = C/4 threads per row (one float4 each), rpp = 256 / tpr rows per pass, kGtIter passes.
+constexpr int kGtIter = 8;
+constexpr int kGtMaxThreads = 256;
+
+struct GtPlan {
+    int tpr, rpp, threads, rows_per_cta, ctas;
+};
+static bool gt_plan(int nv_rows, int c, GtPlan* p) {
+    if (c % 4 != 0 || c / 4 > kGtMaxThreads) return false;
+    p->tpr = c / 4;
+    p->rpp = kGtMaxThreads / p->tpr;
+    p->threads = p->tpr * p->rpp;
+    p->rows_per_cta = p->rpp * kGtIter;
+    p->ctas = (nv_rows + p->rows_per_cta - 1) / p->rows_per_cta;
+    return true;
+}
+static size_t gt_workspace_floats(const GtPlan& p, int c, int groups) { return (size_t)p.ctas * 2 * c + 2 * (size_t)groups; }
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// partial [ctas][G][2] = (local mean, local centred sum of squares) of the CTA's rows, per group
+__global__ void __launch_bounds__(kGtMaxThreads)
+gn_tiled_stats_kernel(const float* __restrict__ x, int nv_rows, const int* __restrict__ nv_dev, int c, int cpg, int tpr,
+                      int rows_per_cta, float* __restrict__ partial) {
+    extern __shared__ __align__(16) float sh[];   // [rpp][c] per-row-slot channel sums, [c] channel sums, [G] group means
+    const int rpp = blockDim.x / tpr;
+    float* part = sh;
+    float* ch_sum = sh + (size_t)rpp * c;
+    float* g_mean = ch_sum + c;
+    const int G = c / cpg;
+    const int nv = nv_dev ? min(nv_rows, __ldg(nv_dev)) : nv_rows;
+    const int col = threadIdx.x % tpr, rsub = threadIdx.x / tpr;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int rows_here = max(0, min(rows_per_cta, nv - r0));
+    const int ch = col * 4;
+    float4 xr[kGtIter];
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kGtIter; i++) {
+        const int r = rsub + i * rpp;
+        xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows_here) {
+            xr[i] = ld4(x + (size_t)(r0 + r) * c + ch);
+            s.x += xr[i].x; s.y += xr[i].y; s.z += xr[i].z; s.w += xr[i].w;
+        }
+    }
+    *reinterpret_cast<float4*>(part + (size_t)rsub * c + ch) = s;
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        float t = 0.0f;
+        for (int rs = 0; rs < rpp; rs++) t += part[(size_t)rs * c + i];
+        ch_sum[i] = t;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        float t = 0.0f;
+        for (int j = 0; j < cpg; j++) t += ch_sum[g * cpg + j];
+        g_mean[g] = rows_here > 0 ? t / ((float)rows_here * (float)cpg) : 0.0f;
+    }
+    __syncthreads();
+    const float m0 = g_mean[ch / cpg], m1 = g_mean[(ch + 1) / cpg], m2 = g_mean[(ch + 2) / cpg], m3 = g_mean[(ch + 3) / cpg];
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kGtIter; i++) {
+        const int r = rsub + i * rpp;
+        if (r < rows_here) {
+            float d = xr[i].x - m0; q.x = fmaf(d, d, q.x);
+            d = xr[i].y - m1; q.y = fmaf(d, d, q.y);
+            d = xr[i].z - m2; q.z = fmaf(d, d, q.z);
+            d = xr[i].w - m3; q.w = fmaf(d, d, q.w);
+        }
+    }
+    *reinterpret_cast<float4*>(part + (size_t)rsub * c + ch) = q;     // every thread rewrites only its own slot
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        float t = 0.0f;
+        for (int rs = 0; rs < rpp; rs++) t += part[(size_t)rs * c + i];
+        ch_sum[i] = t;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        float t = 0.0f;
+        for (int j = 0; j < cpg; j++) t += ch_sum[g * cpg + j];
+        partial[((size_t)blockIdx.x * G + g) * 2] = g_mean[g];
+        partial[((size_t)blockIdx.x * G + g) * 2 + 1] = t;
+    }
+}
+
+// Chan et al.: mean = sum n_i mean_i / N,  M2 = sum (M2_i + n_i (mean_i - mean)^2); one CTA per group
+__global__ void __launch_bounds__(128)
+gn_tiled_finalize_kernel(const float* __restrict__ partial, int ctas, int G, int rows_per_cta, int nv_rows,
+                         const int* __restrict__ nv_dev, int cpg, float eps, float* __restrict__ stats) {
+    __shared__ float red[32];
+    const int g = blockIdx.x;
+    const int nv = nv_dev ? min(nv_rows, __ldg(nv_dev)) : nv_rows;
+    float a = 0.0f;
+    for (int i = threadIdx.x; i < ctas; i += blockDim.x) {
+        const float n_i = (float)max(0, min(rows_per_cta, nv - i * rows_per_cta)) * (float)cpg;
+        a = fmaf(n_i, partial[((size_t)i * G + g) * 2], a);
+    }
+    const float m = (float)nv * (float)cpg;
+    const float mean = block_sum(a, red) / m;
+    float b = 0.0f;
+    for (int i = threadIdx.x; i < ctas; i += blockDim.x) {
+        const float n_i = (float)max(0, min(rows_per_cta, nv - i * rows_per_cta)) * (float)cpg;
+        const float d = partial[((size_t)i * G + g) * 2] - mean;
+        b += partial[((size_t)i * G + g) * 2 + 1] + n_i * d * d;
+    }
+    const float var = block_sum(b, red) / m;
+    if (threadIdx.x == 0) {
+        stats[2 * g] = mean;
+        stats[2 * g + 1] = rsqrtf(var + eps);
+    }
+}
+
+__global__ void __launch_bounds__(kGtMaxThreads)
+gn_tiled_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const float* __restrict__ stats, int nv_rows, const int* __restrict__ nv_dev, int c, int cpg, int tpr,
+                      int rows_per_cta, int relu, float* __restrict__ y) {
+    const int rpp = blockDim.x / tpr;
+    const int nv = nv_dev ? min(nv_rows, __ldg(nv_dev)) : nv_rows;
+    const int col = threadIdx.x % tpr, rsub = threadIdx.x / tpr;
+    const int ch = col * 4;
+    const float4 gm = ld4(gamma + ch), bt = ld4(beta + ch);
+    float mean[4], rstd[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int g = (ch + k) / cpg;
+        mean[k] = __ldg(stats + 2 * g);
+        rstd[k] = __ldg(stats + 2 * g + 1);
+    }
+    const int r0 = blockIdx.x * rows_per_cta;
+#pragma unroll
+    for (int i = 0; i < kGtIter; i++) {
+        const int r = r0 + rsub + i * rpp;
+        if (r >= nv_rows) break;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);          // padding rows (static-shape mode) come out as zeros
+        if (r < nv) {
+            const float4 v = ld4(x + (size_t)r * c + ch);
+            o.x = fmaf((v.x - mean[0]) * rstd[0], gm.x, bt.x);
+            o.y = fmaf((v.y - mean[1]) * rstd[1], gm.y, bt.y);
+            o.z = fmaf((v.z - mean[2]) * rstd[2], gm.z, bt.z);
+            o.w = fmaf((v.w - mean[3]) * rstd[3], gm.w, bt.w);
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        }
+        *reinterpret_cast<float4*>(y + (size_t)r * c + ch) = o;
+    }
+}
+
+// partial_ab [ctas][2c]: per channel sum dy' xhat (first c) and sum dy' (second c) over the CTA's rows
+__global__ void __launch_bounds__(kGtMaxThreads)
+gn_tiled_bwd_partial_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
+                            const float* __restrict__ stats, int nv_rows, const int* __restrict__ nv_dev, int c, int cpg,
+                            int tpr, int rows_per_cta, int relu, float* __restrict__ partial_ab) {
+    extern __shared__ __align__(16) float sh[];   // [rpp][2c]
+    const int rpp = blockDim.x / tpr;
+    const int nv = nv_dev ? min(nv_rows, __ldg(nv_dev)) : nv_rows;
+    const int col = threadIdx.x % tpr, rsub = threadIdx.x / tpr;
+    const int ch = col * 4;
+    float mean[4], rstd[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int g = (ch + k) / cpg;
+        mean[k] = __ldg(stats + 2 * g);
+        rstd[k] = __ldg(stats + 2 * g + 1);
+    }
+    const int r0 = blockIdx.x * rows_per_cta;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kGtIter; i++) {
+        const int r = r0 + rsub + i * rpp;
+        if (r < nv) {
+            const size_t o = (size_t)r * c + ch;
+            float4 d = ld4(dy + o);
+            const float4 v = ld4(x + o);
+            if (relu) {
+                const float4 yy = ld4(y + o);
+                if (!(yy.x > 0.f)) d.x = 0.f;
+                if (!(yy.y > 0.f)) d.y = 0.f;
+                if (!(yy.z > 0.f)) d.z = 0.f;
+                if (!(yy.w > 0.f)) d.w = 0.f;
+            }
+            a.x = fmaf(d.x, (v.x - mean[0]) * rstd[0], a.x); b.x += d.x;
+            a.y = fmaf(d.y, (v.y - mean[1]) * rstd[1], a.y); b.y += d.y;
+            a.z = fmaf(d.z, (v.z - mean[2]) * rstd[2], a.z); b.z += d.z;
+            a.w = fmaf(d.w, (v.w - mean[3]) * rstd[3], a.w); b.w += d.w;
+        }
+    }
+    *reinterpret_cast<float4*>(sh + (size_t)rsub * 2 * c + ch) = a;
+    *reinterpret_cast<float4*>(sh + (size_t)rsub * 2 * c + c + ch) = b;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) {
+        float t = 0.0f;
+        for (int rs = 0; rs < rpp; rs++) t += sh[(size_t)rs * 2 * c + i];
+        partial_ab[(size_t)blockIdx.x * 2 * c + i] = t;
+    }
+}
+
+// one CTA per group: dgamma / dbeta of its channels, and gstat[g] = (ds, db) = sum_j (a_j, b_j) gamma_j
+__global__ void __launch_bounds__(128)
+gn_tiled_bwd_finalize_kernel(const float* __restrict__ partial_ab, int ctas, int c, int cpg, const float* __restrict__ gamma,
+                             float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ gstat) {
+    __shared__ float red[32];
+    const int g = blockIdx.x;
+    float ds = 0.0f, db = 0.0f;
+    for (int j = 0; j < cpg; j++) {
+        const int ch = g * cpg + j;
+        float a = 0.0f, b = 0.0f;
+        for (int i = threadIdx.x; i < ctas; i += blockDim.x) {
+            a += partial_ab[(size_t)i * 2 * c + ch];
+            b += partial_ab[(size_t)i * 2 * c + c + ch];
+        }
+        a = block_sum(a, red);
+        b = block_sum(b, red);
+        const float gm = __ldg(gamma + ch);
+        ds = fmaf(a, gm, ds);
+        db = fmaf(b, gm, db);
+        if (threadIdx.x == 0) {
+            dgamma[ch] = a;
+            dbeta[ch] = b;
+        }
+    }
+    if (threadIdx.x == 0) {
+        gstat[2 * g] = ds;
+        gstat[2 * g + 1] = db;
+    }
+}
+
+__global__ void __launch_bounds__(kGtMaxThreads)
+gn_tiled_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
+                          const float* __restrict__ gamma, const float* __restrict__ stats, const float* __restrict__ gstat,
+                          int nv_rows, const int* __restrict__ nv_dev, int c, int cpg, int tpr, int rows_per_cta, int relu,
+                          float* __restrict__ dx) {
+    const int rpp = blockDim.x / tpr;
+    const int nv = nv_dev ? min(nv_rows, __ldg(nv_dev)) : nv_rows;
+    const int col = threadIdx.x % tpr, rsub = threadIdx.x / tpr;
+    const int ch = col * 4;
+    const float4 gm4 = ld4(gamma + ch);
+    const float gm[4] = {gm4.x, gm4.y, gm4.z, gm4.w};
+    float mean[4], rstd[4], ds[4], db[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int g = (ch + k) / cpg;
+        mean[k] = __ldg(stats + 2 * g);
+        rstd[k] = __ldg(stats + 2 * g + 1);
+        ds[k] = __ldg(gstat + 2 * g);
+        db[k] = __ldg(gstat + 2 * g + 1);
+    }
+    const float inv_m = 1.0f / ((float)nv * (float)cpg);
+    const int r0 = blockIdx.x * rows_per_cta;
+#pragma unroll
+    for (int i = 0; i < kGtIter; i++) {
+        const int r = r0 + rsub + i * rpp;
+        if (r >= nv_rows) break;
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        if (r < nv) {
+            const size_t off = (size_t)r * c + ch;
+            const float4 d4 = ld4(dy + off), v4 = ld4(x + off);
+            float d[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+            if (relu) {
+                const float4 y4 = ld4(y + off);
+                const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (!(yy[k] > 0.f)) d[k] = 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float xhat = (v[k] - mean[k]) * rstd[k];
+                o[k] = rstd[k] * (d[k] * gm[k] - (xhat * ds[k] + db[k]) * inv_m);
+            }
+        }
+        *reinterpret_cast<float4*>(dx + (size_t)r * c + ch) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 static bool gn_small_ok(int nv, int cpg) {
     return nv <= kGnRows * kGnThreads && (cpg == 1 || cpg == 2 || cpg == 3 || cpg == 4 || cpg == 6 || cpg == 8);
 }
@@ -332,8 +620,15 @@ using namespace ln;
 
 extern "C" {
 
+long long ln_group_norm_workspace_bytes(int nv, int c, int groups) {
+    if (nv < 1 || c < 1 || groups < 1 || c % groups != 0) return 0;
+    GtPlan p;
+    if (gn_small_ok(nv, c / groups) || !gt_plan(nv, c, &p)) return 0;
+    return (long long)(gt_workspace_floats(p, c, groups) * sizeof(float));
+}
+
 int ln_group_norm_fwd(const float* x, const float* gamma, const float* beta, int nv, const int* nv_dev, int c, int groups,
-                      float eps, int relu, float* y, float* stats, void* stream) {
+                      float eps, int relu, float* y, float* stats, float* workspace, void* stream) {
     LN_REQUIRE(x && gamma && beta && y && stats, "ln_group_norm_fwd: null pointer");
     LN_REQUIRE(nv >= 1 && c >= 1 && groups >= 1 && c % groups == 0, "ln_group_norm_fwd: bad size nv=%d c=%d groups=%d", nv, c, groups);
     const int cpg = c / groups;
@@ -349,6 +644,13 @@ int ln_group_norm_fwd(const float* x, const float* gamma, const float* beta, int
             default: LN_GN_FWD(8); break;
         }
 #undef LN_GN_FWD
+    } else if (GtPlan p; workspace != nullptr && gt_plan(nv, c, &p)) {
+        const size_t smem = ((size_t)p.rpp * c + c + groups) * sizeof(float);
+        gn_tiled_stats_kernel<<<p.ctas, p.threads, smem, s>>>(x, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, workspace);
+        gn_tiled_finalize_kernel<<<groups, 128, 0, s>>>(workspace, p.ctas, groups, p.rows_per_cta, nv, nv_dev, cpg, eps, stats);
+        gn_tiled_apply_kernel<<<p.ctas, p.threads, 0, s>>>(x, gamma, beta, stats, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, relu, y);
+        count_launch();
+        count_launch();
     } else {
         group_norm_fwd_kernel<<<groups, kGnThreads, 0, s>>>(x, gamma, beta, nv, nv_dev, c, cpg, eps, relu, y, stats);
     }
@@ -357,7 +659,8 @@ int ln_group_norm_fwd(const float* x, const float* gamma, const float* beta, int
 }
 
 int ln_group_norm_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* stats, int nv,
-                      const int* nv_dev, int c, int groups, int relu, float* dx, float* dgamma, float* dbeta, void* stream) {
+                      const int* nv_dev, int c, int groups, int relu, float* dx, float* dgamma, float* dbeta, float* workspace,
+                      void* stream) {
     LN_REQUIRE(dy && x && gamma && stats && dx && dgamma && dbeta, "ln_group_norm_bwd: null pointer");
     LN_REQUIRE(!relu || y, "ln_group_norm_bwd: the forward output is needed for the ReLU mask");
     LN_REQUIRE(nv >= 1 && c >= 1 && groups >= 1 && c % groups == 0, "ln_group_norm_bwd: bad size");
@@ -374,6 +677,15 @@ int ln_group_norm_bwd(const float* dy, const float* x, const float* y, const flo
             default: LN_GN_BWD(8); break;
         }
 #undef LN_GN_BWD
+    } else if (GtPlan p; workspace != nullptr && gt_plan(nv, c, &p)) {
+        float* partial_ab = workspace;
+        float* gstat = workspace + (size_t)p.ctas * 2 * c;
+        const size_t smem = (size_t)p.rpp * 2 * c * sizeof(float);
+        gn_tiled_bwd_partial_kernel<<<p.ctas, p.threads, smem, s>>>(dy, x, y, stats, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, relu, partial_ab);
+        gn_tiled_bwd_finalize_kernel<<<groups, 128, 0, s>>>(partial_ab, p.ctas, c, cpg, gamma, dgamma, dbeta, gstat);
+        gn_tiled_bwd_apply_kernel<<<p.ctas, p.threads, 0, s>>>(dy, x, y, gamma, stats, gstat, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, relu, dx);
+        count_launch();
+        count_launch();
     } else {
         group_norm_bwd_kernel<<<groups, kGnThreads, 0, s>>>(dy, x, y, gamma, stats, nv, nv_dev, c, cpg, relu, dx, dgamma, dbeta);
     }

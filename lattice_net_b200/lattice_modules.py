@@ -68,6 +68,19 @@ def scatter_sum_count(src, index, nv):
     return out, cnt
 
 
+_GN_SMALL_ROWS = 2048     # lattices up to this many rows run the one-CTA-per-group kernels (ln_norm.cu: kGnRows * kGnThreads)
+
+
+def _gn_workspace(nv, c, groups, device):
+    """Scratch for the row-tiled GroupNorm kernels of scene-sized lattices (None when the library needs none).  A
+    fresh tensor per call: the caching allocator recycles it in stream order, and it stays valid inside a CUDA graph."""
+    if nv <= _GN_SMALL_ROWS and (c // groups) in (1, 2, 3, 4, 6, 8):
+        return None
+    from ._cabi import load
+    nbytes = int(load().ln_group_norm_workspace_bytes(int(nv), int(c), int(groups)))
+    return torch.empty((nbytes // 4,), dtype=torch.float32, device=device) if nbytes > 0 else None
+
+
 class _GroupNormReLU(torch.autograd.Function):
     """GroupNorm (+ReLU) on vertex-major values [nv x C] in one kernel each way (ln_group_norm_fwd/bwd)."""
 
@@ -79,7 +92,7 @@ class _GroupNormReLU(torch.autograd.Function):
         y = torch.empty_like(x)
         stats = torch.empty((groups, 2), dtype=torch.float32, device=x.device)
         call("ln_group_norm_fwd", ptr(x), ptr(gamma.contiguous()), ptr(beta.contiguous()), nv, ptr(nv_dev), c, groups, float(eps),
-             1 if relu else 0, ptr(y), ptr(stats), stream_ptr(x.device))
+             1 if relu else 0, ptr(y), ptr(stats), ptr(_gn_workspace(nv, c, groups, x.device)), stream_ptr(x.device))
         ctx.save_for_backward(x, y, gamma, stats)
         ctx.groups, ctx.relu, ctx.nv_dev = groups, relu, nv_dev
         return y
@@ -92,12 +105,15 @@ class _GroupNormReLU(torch.autograd.Function):
         dgamma = torch.empty_like(gamma)
         dbeta = torch.empty_like(gamma)
         call("ln_group_norm_bwd", ptr(dy.contiguous()), ptr(x), ptr(y), ptr(gamma.contiguous()), ptr(stats), nv, ptr(ctx.nv_dev), c,
-             ctx.groups, 1 if ctx.relu else 0, ptr(dx), ptr(dgamma), ptr(dbeta), stream_ptr(x.device))
+             ctx.groups, 1 if ctx.relu else 0, ptr(dx), ptr(dgamma), ptr(dbeta), ptr(_gn_workspace(nv, c, ctx.groups, x.device)),
+             stream_ptr(x.device))
         return dx, dgamma, dbeta, None, None, None, None
 
 
-# one CTA per group: meant for the lattice sizes where launch count, not bandwidth, is the cost
-FUSED_NORM_MAX_ELEMS_PER_GROUP = 1 << 17
+# None: GroupNorm(+ReLU) always runs the kernels of ln_norm.cu (one CTA per group for ShapeNet-sized lattices, row-tiled
+# over all SMs for scene-sized ones).  An integer restores torch.nn.GroupNorm above that many elements per group
+# (0 = always torch: what bench.py's reference arm sets).
+FUSED_NORM_MAX_ELEMS_PER_GROUP = None
 
 # The reference treats lattice vertex 0 as the "invalid" row: points whose index was clamped from -1 land there,
 # so its mean / features are zeroed (lattice_modules.py:72-94, 683, 712).  Which real vertex gets id 0 is a race
@@ -379,7 +395,8 @@ class GroupNormLatticeModule(torch.nn.Module):
         ht = getattr(lattice_py, "m_hash_table", None)      # (bench.py's reference arm passes its own handle type)
         st = ht.structure if ht is not None else None
         nv_dev = st.nr_filled if (st is not None and st.bound is not None) else None
-        if lattice_values.is_cuda and (nv_dev is not None or nv * (c // gn.num_groups) <= FUSED_NORM_MAX_ELEMS_PER_GROUP):
+        if lattice_values.is_cuda and (nv_dev is not None or FUSED_NORM_MAX_ELEMS_PER_GROUP is None
+                                       or nv * (c // gn.num_groups) <= FUSED_NORM_MAX_ELEMS_PER_GROUP):
             lv = _GroupNormReLU.apply(lattice_values, gn.weight, gn.bias, gn.num_groups, gn.eps, relu, nv_dev)
         else:
             lv = gn(lattice_values.t().unsqueeze(0)).squeeze(0).t()

@@ -308,12 +308,13 @@ def run(args, cloud_fn, cfg):
     ms = e0.elapsed_time(e1)
     value = args.steps / (ms * 1e-3)
     return {
-        "impl": "reference", "metric": "scans/sec fwd+bwd", "value": value, "unit": "scans/s", "n_gpus": 1, "steps": args.steps,
+        "impl": "reference", "metric": "scans/sec fwd+bwd", "value": value, "unit": "scans/s", "n_gpus": int(getattr(args, "gpus", 1) or 1), "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "LatticeNet ShapeNet-part segmentation fwd+bwd+AdamW (lnn_train_shapenet.cfg arch), 2048-pt synthetic clouds, 1 scene/step/GPU",
                    "arm": "the reference's own CUDA kernels (NVRTC build of the unmodified LatticeGPU.cuh, driver-JITed on this GPU) + its host algorithm (im2row buffer + fp32 mm, C-sized clears, per-handle D2H syncs); the reference has no CPU implementation",
-                   "l2": "flushed between steps by a 256 MiB write (inside the timed region)"},
+                   "l2": "flushed between steps by a 256 MiB write (inside the timed region)",
+                   "ranks_used": "1 (the reference is single-process / single-GPU; under torchrun rank 0 alone runs it)"},
         "cpu_baseline": {"value": value, "unit": "scans/s", "cores": 0, "kind": "reference",
                          "sample": f"{args.steps} full training steps on the B200 (the reference is CUDA-only, README.md:20; no host-core implementation exists)"},
         "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -23,5 +23,3 @@ tail -4 $O/r01j_bench_2gpu.log | grep -v '^{' | cut -c1-300
 run2 r01j_bench_2gpu_captured_allreduce --no-cpu-baseline --capture-collective
 tail -4 $O/r01j_bench_2gpu_captured_allreduce.log | grep -v '^{' | cut -c1-300
 run2 r01j_bench_2gpu_reference --impl reference --steps 10 --warmup 3
-timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > $O/r01j_bench_1gpu.log 2>&1; echo "1gpu rc=$?"
-grep '^{' $O/r01j_bench_1gpu.log | tail -1 > $O/r01j_bench_1gpu.json; cut -c1-160 $O/r01j_bench_1gpu.json

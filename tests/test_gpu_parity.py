@@ -516,7 +516,10 @@ def test_conv_tensor_core_cross_level(built):
     assert_close(got, lo.conv_fwd(lv, up, fb), 2e-5, "tensor-core coarsen conv")
 
 
-@pytest.mark.parametrize("nv,C", [(983, 32), (1231, 128), (77, 192), (25, 256), (300, 8), (5000, 96)])
+# nv <= 2048 with 1..8 channels per group: one CTA per group; everything else (scene-sized levels, the 512-channel KITTI
+# bottleneck with 16 channels per group, widths that are not a multiple of 32) runs the row-tiled kernels
+@pytest.mark.parametrize("nv,C", [(983, 32), (1231, 128), (77, 192), (25, 256), (300, 8), (5000, 96), (34809, 64), (2773, 256),
+                                  (673, 512), (57169, 32), (10501, 384), (3001, 48)])
 @pytest.mark.parametrize("relu", [False, True])
 def test_fused_group_norm(nv, C, relu):
     """ln_group_norm_fwd/bwd vs torch.nn.GroupNorm on the [1, C, nv] view the reference uses."""
@@ -620,10 +623,11 @@ def test_static_shape_bound_exceeded_is_flagged():
 
 
 @pytest.mark.parametrize("relu", [False, True])
-def test_group_norm_ignores_padding_rows(relu):
+@pytest.mark.parametrize("nv,rows,C", [(700, 1024, 64), (9000, 12032, 128)])
+def test_group_norm_ignores_padding_rows(relu, nv, rows, C):
     from lattice_net_b200.lattice_modules import _GroupNormReLU
     torch.manual_seed(5)
-    nv, rows, C, groups = 700, 1024, 64, 32
+    groups = 32
     x = torch.randn((rows, C), device="cuda") * 3 + 1          # padding rows hold garbage on purpose
     g = torch.randn((rows, C), device="cuda")
     g[nv:] = 0                                                   # upstream gradients of padding rows are zero
