@@ -3,7 +3,8 @@
 //   out[q, :] = sum_slot  values[nbr[q, slot'], :] . W[slot*c_in : (slot+1)*c_in, :]      (+ bias)
 //
 // is a GEMM whose A rows are GATHERED through the neighbour table: M = query vertices (tile 128),
-// N = c_out (<= 256, one tile), K = F * c_in walked in blocks of 32 floats (one 128-byte swizzle row).
+// N = c_out (one tile of up to 256 columns; wider layers run as 256-column chunks), K = F * c_in walked in blocks of
+// 32 floats (one 128-byte swizzle row).
 // No im2row buffer exists anywhere (the reference writes nv*F*c_in floats and reads them back through
 // cuBLAS SGEMM, /root/reference/src/Lattice.cu:454-462).
 //

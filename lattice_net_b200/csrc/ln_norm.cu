@@ -5,9 +5,12 @@
 // Statistics of group g run over (channels of g) x (all vertices), biased variance, like
 // torch.nn.GroupNorm on a [1, C, nv] tensor.
 //
-// One CTA per group: mean, variance and the normalised output in a single launch (the group's slice is
-// nv * C/G floats and stays in L1/L2 between the passes); the backward pass likewise produces dx,
-// dgamma and dbeta in one launch without atomics (every channel belongs to exactly one group).
+// Three families, chosen by size (ln_group_norm_fwd / _bwd):
+//   * <= 2048 rows, 1..8 channels per group: one CTA per group with the rows cached in registers, one launch each way
+//     (the ShapeNet-sized lattices, where launch count and latency are the cost);
+//   * scene-sized lattices: row-tiled kernels over all SMs (stats partial -> finalize -> apply), see gn_tiled_*;
+//   * anything else (no workspace given, C % 4 != 0, C > 1024): the generic one-CTA-per-group kernels below --
+//     mean, variance and the normalised output in a single launch, backward without atomics.
 #include "ln_common.cuh"
 
 namespace ln {

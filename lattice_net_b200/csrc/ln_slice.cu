@@ -70,7 +70,7 @@ __device__ __forceinline__ void load_simplex(const int* __restrict__ indices, co
 
 // ---------------------------------------------------------------------------------------------
 // Work decomposition shared by slice forward and the row scatter (ncu --set full on the 1M-point sweep,
-// profiles/r01g_ops_ncu.md, is what shaped it):
+// profiles/r01i_ops_ncu.md holds the current capture, is what shaped it):
 //   * CHANNEL SLABS.  The vertex table is hit (D+1)x per point in random order; once nv*V*4 bytes outgrow the L2 it
 //     is re-fetched from HBM several times (V=64, nv=463k: 118 MB table, 31 % L2 hit rate, 1.8x the compulsory DRAM
 //     traffic).  The channels are therefore processed in slabs of `slab_ch` (a multiple of 32 floats = one 128-byte
