@@ -84,6 +84,26 @@ def uniform_cloud(n, d, seed, order="random"):
     return np.ascontiguousarray(pos)
 
 
+def bench_group_norm(nv, widths, cfg0, dev):
+    """GroupNorm + ReLU between the convolutions: this repo's kernels vs what the reference runs
+    (transpose to [1, C, nv], torch.nn.GroupNorm, ReLU, transpose back: lattice_modules.py:585-614)."""
+    from lattice_net_b200.lattice_modules import _GroupNormReLU
+    for C in widths:
+        xg = torch.randn((nv, C), device=dev)
+        gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        gy = torch.randn((nv, C), device=dev)
+        cfg = dict(cfg0, val_dim=C)
+
+        def gn_ref():
+            return torch.relu(torch.nn.functional.group_norm(xg.t().unsqueeze(0), 32, gamma, beta, 1e-5)).squeeze(0).t().contiguous()
+        emit("group_norm_relu_fwd", cfg, timeit(lambda: _GroupNormReLU.apply(xg, gamma, beta, 32, 1e-5, True), reps=5),
+             nbytes=8.0 * nv * C, ref_sec=timeit(gn_ref, reps=5), extra={"ref": "torch GroupNorm + ReLU + layout copies"})
+        xr = xg.clone().requires_grad_(True)
+        yr = _GroupNormReLU.apply(xr, gamma, beta, 32, 1e-5, True)
+        emit("group_norm_relu_bwd", cfg, timeit(lambda: torch.autograd.grad(yr, xr, gy, retain_graph=True), reps=5), nbytes=16.0 * nv * C)
+        del xg, gy, xr, yr
+
+
 def run(n, d, vals, quick, order="random"):
     from lattice_net_b200 import Lattice, lattice as lm
     from lattice_net_b200._cabi import call, ptr, stream_ptr
@@ -194,6 +214,7 @@ def run(n, d, vals, quick, order="random"):
                     lm.set_conv_precision(0)
             del fb, gout
         del lat2, lvr
+    bench_group_norm(nv, [v for v in vals if v >= 32][:2], cfg0, dev)
     # neighbour table
     lat3 = lat.clone_lattice()
     lat3.set_values(torch.zeros((nv, 1), device=dev))
@@ -211,7 +232,11 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--vals", type=int, nargs="*", default=None)
     ap.add_argument("--order", default="random", choices=["random", "morton"], help="point order of the synthetic cloud")
+    ap.add_argument("--gn-only", type=int, default=0, metavar="NV", help="only the GroupNorm entries, on an [NV x C] tensor")
     args = ap.parse_args()
+    if args.gn_only:
+        bench_group_norm(args.gn_only, args.vals or [32, 64], {"n": 0, "pos_dim": 3, "nv": args.gn_only, "point_order": "-"}, torch.device("cuda", 0))
+        return
     for n in args.n:
         run(n, 3, args.vals if args.vals else ([8, 32, 64] if args.quick else [1, 8, 32, 64, 128]), args.quick, args.order)
     if not args.quick:

@@ -343,8 +343,8 @@ constexpr int kGtMaxThreads = 256;
 struct GtPlan {
     int tpr, rpp, threads, rows_per_cta, ctas;
 };
-static bool gt_plan(int nv_rows, int c, GtPlan* p) {
-    if (c % 4 != 0 || c / 4 > kGtMaxThreads) return false;
+static bool gt_plan(int nv_rows, int c, int cpg, GtPlan* p) {
+    if (c % 4 != 0 || c / 4 > kGtMaxThreads || cpg > 128) return false;   // cpg <= 128: one finalize CTA holds whole groups
     p->tpr = c / 4;
     p->rpp = kGtMaxThreads / p->tpr;
     p->threads = p->tpr * p->rpp;
@@ -534,31 +534,51 @@ gn_tiled_bwd_partial_kernel(const float* __restrict__ dy, const float* __restric
     }
 }
 
-// one CTA per group: dgamma / dbeta of its channels, and gstat[g] = (ds, db) = sum_j (a_j, b_j) gamma_j
-__global__ void __launch_bounds__(128)
-gn_tiled_bwd_finalize_kernel(const float* __restrict__ partial_ab, int ctas, int c, int cpg, const float* __restrict__ gamma,
+// dgamma / dbeta per channel and gstat[g] = (ds, db) = sum_j (a_j, b_j) gamma_j per group.  A CTA owns `cpc` consecutive
+// channels (a whole number of groups, <= 128): lane = channel, so the loads of one partial row are coalesced; four
+// slices of CTAs are summed side by side and combined in a fixed order (deterministic).
+constexpr int kGtFinLanes = 128;
+constexpr int kGtFinSlices = 4;
+__global__ void __launch_bounds__(kGtFinLanes * kGtFinSlices)
+gn_tiled_bwd_finalize_kernel(const float* __restrict__ partial_ab, int ctas, int c, int cpg, int cpc, const float* __restrict__ gamma,
                              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ gstat) {
-    __shared__ float red[32];
-    const int g = blockIdx.x;
-    float ds = 0.0f, db = 0.0f;
-    for (int j = 0; j < cpg; j++) {
-        const int ch = g * cpg + j;
-        float a = 0.0f, b = 0.0f;
-        for (int i = threadIdx.x; i < ctas; i += blockDim.x) {
-            a += partial_ab[(size_t)i * 2 * c + ch];
-            b += partial_ab[(size_t)i * 2 * c + c + ch];
-        }
-        a = block_sum(a, red);
-        b = block_sum(b, red);
-        const float gm = __ldg(gamma + ch);
-        ds = fmaf(a, gm, ds);
-        db = fmaf(b, gm, db);
-        if (threadIdx.x == 0) {
-            dgamma[ch] = a;
-            dbeta[ch] = b;
+    __shared__ float red[kGtFinSlices][2][kGtFinLanes];
+    __shared__ float ch_a[kGtFinLanes], ch_b[kGtFinLanes];
+    const int lane = threadIdx.x % kGtFinLanes, slice = threadIdx.x / kGtFinLanes;
+    const int ch0 = blockIdx.x * cpc;
+    const int nch = min(cpc, c - ch0);                 // channels of this CTA (whole groups: c and cpc are multiples of cpg)
+    float a = 0.0f, b = 0.0f;
+    if (lane < nch) {
+        const float* p = partial_ab + ch0 + lane;
+        for (int i = slice; i < ctas; i += kGtFinSlices) {
+            a += __ldg(p + (size_t)i * 2 * c);
+            b += __ldg(p + (size_t)i * 2 * c + c);
         }
     }
-    if (threadIdx.x == 0) {
+    red[slice][0][lane] = a;
+    red[slice][1][lane] = b;
+    __syncthreads();
+    if (slice == 0 && lane < nch) {
+        float ta = 0.0f, tb = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kGtFinSlices; k++) {
+            ta += red[k][0][lane];
+            tb += red[k][1][lane];
+        }
+        dgamma[ch0 + lane] = ta;
+        dbeta[ch0 + lane] = tb;
+        const float gm = __ldg(gamma + ch0 + lane);
+        ch_a[lane] = ta * gm;
+        ch_b[lane] = tb * gm;
+    }
+    __syncthreads();
+    if (threadIdx.x < nch / cpg) {
+        float ds = 0.0f, db = 0.0f;
+        for (int j = 0; j < cpg; j++) {
+            ds += ch_a[threadIdx.x * cpg + j];
+            db += ch_b[threadIdx.x * cpg + j];
+        }
+        const int g = ch0 / cpg + threadIdx.x;
         gstat[2 * g] = ds;
         gstat[2 * g + 1] = db;
     }
@@ -626,7 +646,7 @@ extern "C" {
 long long ln_group_norm_workspace_bytes(int nv, int c, int groups) {
     if (nv < 1 || c < 1 || groups < 1 || c % groups != 0) return 0;
     GtPlan p;
-    if (gn_small_ok(nv, c / groups) || !gt_plan(nv, c, &p)) return 0;
+    if (gn_small_ok(nv, c / groups) || !gt_plan(nv, c, c / groups, &p)) return 0;
     return (long long)(gt_workspace_floats(p, c, groups) * sizeof(float));
 }
 
@@ -647,7 +667,7 @@ int ln_group_norm_fwd(const float* x, const float* gamma, const float* beta, int
             default: LN_GN_FWD(8); break;
         }
 #undef LN_GN_FWD
-    } else if (GtPlan p; workspace != nullptr && gt_plan(nv, c, &p)) {
+    } else if (GtPlan p; workspace != nullptr && gt_plan(nv, c, cpg, &p)) {
         const size_t smem = ((size_t)p.rpp * c + c + groups) * sizeof(float);
         gn_tiled_stats_kernel<<<p.ctas, p.threads, smem, s>>>(x, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, workspace);
         gn_tiled_finalize_kernel<<<groups, 128, 0, s>>>(workspace, p.ctas, groups, p.rows_per_cta, nv, nv_dev, cpg, eps, stats);
@@ -680,12 +700,13 @@ int ln_group_norm_bwd(const float* dy, const float* x, const float* y, const flo
             default: LN_GN_BWD(8); break;
         }
 #undef LN_GN_BWD
-    } else if (GtPlan p; workspace != nullptr && gt_plan(nv, c, &p)) {
+    } else if (GtPlan p; workspace != nullptr && gt_plan(nv, c, cpg, &p)) {
         float* partial_ab = workspace;
         float* gstat = workspace + (size_t)p.ctas * 2 * c;
         const size_t smem = (size_t)p.rpp * 2 * c * sizeof(float);
         gn_tiled_bwd_partial_kernel<<<p.ctas, p.threads, smem, s>>>(dy, x, y, stats, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, relu, partial_ab);
-        gn_tiled_bwd_finalize_kernel<<<groups, 128, 0, s>>>(partial_ab, p.ctas, c, cpg, gamma, dgamma, dbeta, gstat);
+        const int cpc = cpg >= kGtFinLanes ? cpg : (kGtFinLanes / cpg) * cpg;       // whole groups per CTA
+        gn_tiled_bwd_finalize_kernel<<<(c + cpc - 1) / cpc, kGtFinLanes * kGtFinSlices, 0, s>>>(partial_ab, p.ctas, c, cpg, cpc, gamma, dgamma, dbeta, gstat);
         gn_tiled_bwd_apply_kernel<<<p.ctas, p.threads, 0, s>>>(dy, x, y, gamma, stats, gstat, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, relu, dx);
         count_launch();
         count_launch();
