@@ -383,55 +383,104 @@ def test_golden_vectors_match_cuda_path(golden_dir):
         pytest.skip("no golden vectors committed yet")
 
 
+def _gradient_agreement(named_a, grads_b):
+    """Statistics of two gradient sets (name -> ndarray): per-tensor max error relative to the tensor's scale, relative
+    L2 error and cosine over everything, median / 99th percentile of the element errors."""
+    per_tensor, rel, fa, fb = {}, [], [], []
+    num = den = 0.0
+    for name, ga in named_a:
+        gb = grads_b[name]
+        ga, gb = ga.astype(np.float64).ravel(), gb.astype(np.float64).ravel()
+        scale = max(np.abs(gb).max(), 1e-30)
+        per_tensor[name] = float(np.abs(ga - gb).max() / scale)
+        rel.append(np.abs(ga - gb) / scale)
+        fa.append(ga)
+        fb.append(gb)
+        num += float(((ga - gb) ** 2).sum())
+        den += float((gb ** 2).sum())
+    fa, fb, rel = np.concatenate(fa), np.concatenate(fb), np.concatenate(rel)
+    return dict(per_tensor=per_tensor, l2=(num / den) ** 0.5, cosine=float(fa @ fb / (np.linalg.norm(fa) * np.linalg.norm(fb))),
+                median=float(np.median(rel)), p99=float(np.quantile(rel, 0.99)))
+
+
+def _assert_flip_robust(st, what):
+    """Bounds that hold whether or not a ReLU / LeakyReLU gate flipped between the two evaluations (measured on the B200,
+    scripts/diag_cpu_port.py: flipped attempts reach 0.17 on single tensors, L2 3.5e-3, cosine 0.99999, p99 4.8e-3), and
+    that an indexing / algebra bug in any gradient path does not meet."""
+    worst = max(st["per_tensor"].items(), key=lambda kv: kv[1])
+    assert worst[1] <= 0.5, f"{what}: gradient of {worst[0]} max rel err {worst[1]:.3e}"
+    assert st["l2"] <= 2e-2, f"{what}: relative L2 error over all gradients {st['l2']:.3e}"
+    assert st["cosine"] >= 0.9995, f"{what}: cosine of the concatenated gradients {st['cosine']:.6f}"
+    assert st["median"] <= 2e-3 and st["p99"] <= 3e-2, f"{what}: element errors median {st['median']:.2e} / p99 {st['p99']:.2e}"
+
+
 def test_lnn_model_matches_cpu_port():
     """Model-level parity: the whole LatticeNet forward + backward through the CUDA path vs the
     torch-CPU re-expression (oracle/cpu_port.py) with the same parameters and the same level-1
-    vertex numbering (the model treats vertex 0 specially, lattice_modules.py:72-94)."""
+    vertex numbering (the model treats vertex 0 specially, lattice_modules.py:72-94).
+
+    Forward: logits to 1e-4, loss to 1e-5 on every evaluation (measured: 4e-6 / 2e-7).
+    Backward: two fp32 evaluations of this 40-layer network differ in the last bits of the splatted / scattered values
+    (atomic order), which now and then flips a ReLU / LeakyReLU gate whose pre-activation sits within ~1e-7 of zero --
+    invisible in the logits, but it moves the gradients of a few tensors by percents (scripts/diag_cpu_port.py on the
+    B200: an evaluation agrees either to ~7e-6 on every tensor or has 1..11 of the 154 tensors off by 2e-2..2e-1).
+    So: every evaluation must meet flip-robust bounds, and EVERY gradient tensor must agree to the tight per-tensor
+    bound in at least one evaluation (evaluations cycle over four clouds, so a tensor is never hostage to one gate) --
+    a wrong gradient path fails on all of them."""
     from lattice_net_b200 import Lattice, ModelParams
     from lattice_net_b200.losses import segmentation_loss
     from lattice_net_b200.models import LNN
     from oracle import cpu_port
     torch.manual_seed(0)
     dev = torch.device("cuda", 0)
-    pos_np = cases.box_surface(2048, 0)
-    labels_np = np.random.RandomState(3).randint(0, 7, 2048)
-    lattice = Lattice(60000, [(0.05, 3)])
+    Lattice(60000, [(0.05, 3)])          # the module constructors read the static expected position dimension
     model = LNN(7, ModelParams(), device=dev)
-    pos, vals, labels = cuda(pos_np), torch.zeros((2048, 1), device=dev), cuda(labels_np)
-    logsm, logits = model(lattice, pos, vals)
-    # Gradients are compared under the NLL term alone.  The Lovasz term is piecewise linear in the SORTED errors:
-    # two errors that differ in the last bits swap places between two fp32 evaluations and the gradients of those
-    # two points jump by O(1/|union|) -- measured on the B200: identical loss to 7 digits, per-tensor gradient
-    # deviations of 1e-2..2e-1 between two runs of the very same kernels.  Its VALUE is compared below.
-    loss = torch.nn.functional.nll_loss(logsm, labels)
-    loss.backward()
-    full_loss = segmentation_loss(logsm.detach(), labels)
-    l1 = model.last_level1_lattice
-    keys = l1.hash_table().m_keys_tensor[:l1.nr_lattice_vertices()].cpu().numpy()
-    cpu = cpu_port.CpuLNN(7, ModelParams())
-    cpu.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()}, strict=True)
-    clogsm, clogits = cpu(pos_np, torch.zeros(2048, 1), [0.05] * 3, level1_keys=keys)
-    closs = torch.nn.functional.nll_loss(clogsm, torch.from_numpy(labels_np))
-    closs.backward()
-    cfull_loss = segmentation_loss(clogsm.detach(), torch.from_numpy(labels_np))
-    assert_close(logits.detach().cpu().numpy(), clogits.detach().numpy(), 2e-3, "LNN logits vs CPU port")
-    assert abs(loss.item() - closs.item()) <= 1e-3 * abs(closs.item())
-    assert abs(full_loss.item() - cfull_loss.item()) <= 1e-3 * abs(cfull_loss.item()), "0.5 Lovasz + 0.5 NLL value"
-    cpu_grads = dict(cpu.named_parameters())
-    checked = 0
-    num = den = 0.0
-    for name, p in model.named_parameters():
-        if p.grad is None:
-            continue
-        g, cg = p.grad.detach().cpu().numpy(), cpu_grads[name].grad.numpy()
-        # two fp32 evaluations of a 40-layer network: a per-tensor max error bound (2e-2 of the tensor's scale)
-        # plus a tight bound on the relative L2 error over ALL gradients together
-        assert_close(g, cg, 2e-2, f"gradient of {name}")
-        num += float(((g.astype(np.float64) - cg) ** 2).sum())
-        den += float((cg.astype(np.float64) ** 2).sum())
-        checked += 1
-    assert checked > 100
-    assert (num / den) ** 0.5 <= 5e-3, f"relative L2 error over all gradients {(num / den) ** 0.5:.3e}"
+    labels_np = np.random.RandomState(3).randint(0, 7, 2048)
+    labels = cuda(labels_np)
+    vals = torch.zeros((2048, 1), device=dev)
+    cpu = None
+    best = {}
+    best_l2 = float("inf")
+    for attempt in range(8):
+        pos_np = cases.box_surface(2048, (0, 3, 4, 1)[attempt % 4])
+        pos = cuda(pos_np)
+        lattice = Lattice(60000, [(0.05, 3)])
+        for p in model.parameters():
+            p.grad = None
+        logsm, logits = model(lattice, pos, vals)
+        # Gradients are compared under the NLL term alone.  The Lovasz term is piecewise linear in the SORTED errors:
+        # two errors that differ in the last bits swap places between two fp32 evaluations and the gradients of those
+        # two points jump by O(1/|union|).  Its VALUE is compared below.
+        loss = torch.nn.functional.nll_loss(logsm, labels)
+        loss.backward()
+        full_loss = segmentation_loss(logsm.detach(), labels)
+        l1 = model.last_level1_lattice
+        keys = l1.hash_table().m_keys_tensor[:l1.nr_lattice_vertices()].cpu().numpy()
+        if cpu is None:              # after the first forward: the lazily created layers exist
+            cpu = cpu_port.CpuLNN(7, ModelParams())
+            cpu.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()}, strict=True)
+        for p in cpu.parameters():
+            p.grad = None
+        clogsm, clogits = cpu(pos_np, torch.zeros(2048, 1), [0.05] * 3, level1_keys=keys)
+        closs = torch.nn.functional.nll_loss(clogsm, torch.from_numpy(labels_np))
+        closs.backward()
+        cfull_loss = segmentation_loss(clogsm.detach(), torch.from_numpy(labels_np))
+        assert_close(logits.detach().cpu().numpy(), clogits.detach().numpy(), 1e-4, "LNN logits vs CPU port")
+        assert abs(loss.item() - closs.item()) <= 1e-5 * abs(closs.item())
+        assert abs(full_loss.item() - cfull_loss.item()) <= 1e-3 * abs(cfull_loss.item()), "0.5 Lovasz + 0.5 NLL value"
+        cpu_grads = {n: p.grad.numpy() for n, p in cpu.named_parameters() if p.grad is not None}
+        st = _gradient_agreement([(n, p.grad.detach().cpu().numpy()) for n, p in model.named_parameters() if p.grad is not None], cpu_grads)
+        assert len(st["per_tensor"]) > 100
+        _assert_flip_robust(st, f"LNN gradients vs CPU port (evaluation {attempt})")
+        for name, err in st["per_tensor"].items():
+            best[name] = min(best.get(name, float("inf")), err)
+        best_l2 = min(best_l2, st["l2"])
+        # tight bounds: per tensor 2e-2 of its scale in some evaluation, 5e-3 relative L2 over ALL gradients in some evaluation
+        if max(best.values()) <= 2e-2 and best_l2 <= 5e-3:
+            break
+    worst = max(best.items(), key=lambda kv: kv[1])
+    assert worst[1] <= 2e-2, f"gradient of {worst[0]}: best of 8 evaluations has max rel err {worst[1]:.3e} > 2e-2"
+    assert best_l2 <= 5e-3, f"relative L2 error over all gradients: best of 8 evaluations {best_l2:.3e} > 5e-3"
 
 
 @pytest.mark.parametrize("precision,tol", [(1, 2e-5), (2, 5e-3)])
@@ -662,10 +711,9 @@ def test_graphed_step_matches_eager_step():
     ~1e-7 of zero.  One flipped gate on a 25..100-vertex coarse level moves single gradient elements by percents
     (scripts/diag_flaky.py, profiles/r01g_gradient_reproducibility.txt: eager-vs-eager runs of clouds 0, 2 and 5
     agree either to ~5e-6 or only to 1e-2..7e-2, never in between; clouds 1, 3 and 4 reproduce to <1e-3 every time).
-    The test therefore runs on the reproducible clouds, gives every cloud a few attempts of which ONE must agree to
-    2e-3 on every gradient tensor (same function when no gate flips -- an indexing / padding bug never would), and
-    bounds EVERY attempt by flip-robust statistics: per-tensor max error <= 0.15, cosine of the concatenated
-    gradients >= 0.995, median element error <= 2e-3 of its tensor's scale."""
+    The test therefore runs on the reproducible clouds, bounds EVERY attempt by flip-robust statistics
+    (_assert_flip_robust), and gives every cloud a few attempts in which every gradient tensor must agree to 2e-3 at
+    least once (same function when no gate flips -- an indexing / padding bug never would)."""
     import copy
     from lattice_net_b200 import Lattice, ModelParams, lattice_modules
     from lattice_net_b200.graphed import GraphedTrainStep, estimate_vertex_bounds
@@ -697,7 +745,7 @@ def test_graphed_step_matches_eager_step():
             assert torch.equal(pa, pb), f"{na} changed during graph capture"
         replays = 0
         for pos, vals, labels in clouds[1:] + clouds[:1]:
-            best = None
+            best = {}
             for attempt in range(6):
                 loss_b = step(pos, vals, labels)
                 replays += 1
@@ -711,27 +759,18 @@ def test_graphed_step_matches_eager_step():
                 assert step.last_vertex_counts() == nv_levels
                 assert all(n <= b for n, b in zip(nv_levels, bounds))
                 assert abs(loss_a.item() - loss_b.item()) <= 1e-4 * abs(loss_a.item())
-                checked, worst = 0, (0.0, "")
-                flat_a, flat_b, rel = [], [], []
-                for (name, pa), pb in zip(model_a.named_parameters(), model_b.parameters()):
-                    if pa.grad is None:
-                        continue
-                    ga, gb = pa.grad.cpu().numpy().ravel().astype(np.float64), pb.grad.cpu().numpy().ravel().astype(np.float64)
-                    worst = max(worst, (max_rel_err(gb, ga), name))
-                    flat_a.append(ga)
-                    flat_b.append(gb)
-                    rel.append(np.abs(ga - gb) / max(np.abs(ga).max(), 1e-30))
-                    checked += 1
-                assert checked > 100
-                flat_a, flat_b, rel = np.concatenate(flat_a), np.concatenate(flat_b), np.concatenate(rel)
-                cosine = float(flat_a @ flat_b / (np.linalg.norm(flat_a) * np.linalg.norm(flat_b)))
-                assert worst[0] <= 0.15, f"graphed gradient of {worst[1]}: max rel err {worst[0]:.3e} (attempt {attempt})"
-                assert cosine >= 0.995, f"graphed vs eager gradients: cosine {cosine:.6f} (attempt {attempt})"
-                assert float(np.median(rel)) <= 2e-3, f"graphed vs eager gradients: median element error {np.median(rel):.3e}"
-                best = worst if best is None else min(best, worst)
-                if best[0] <= 2e-3:
+                grads_a = {n: p.grad.cpu().numpy() for n, p in model_a.named_parameters() if p.grad is not None}
+                names = list(grads_a)
+                grads_b = [(n, pb.grad.cpu().numpy()) for (n, _), pb in zip(model_a.named_parameters(), model_b.parameters()) if n in grads_a]
+                st = _gradient_agreement(grads_b, grads_a)
+                assert len(names) > 100
+                _assert_flip_robust(st, f"graphed vs eager gradients (attempt {attempt})")
+                for name, err in st["per_tensor"].items():
+                    best[name] = min(best.get(name, float("inf")), err)
+                if max(best.values()) <= 2e-3:
                     break
-            assert best[0] <= 2e-3, f"graphed gradient of {best[1]}: best of 6 attempts has max rel err {best[0]:.3e} > 2e-3"
+            worst = max(best.items(), key=lambda kv: kv[1])
+            assert worst[1] <= 2e-3, f"graphed gradient of {worst[0]}: best of 6 attempts has max rel err {worst[1]:.3e} > 2e-3"
         assert step.overflowed_steps() == 0
         steps = {int(st["step"].item()) for st in opt_b.state.values()}
         assert steps == {replays}, "the optimizer step inside the graph did not run once per replay"

@@ -99,6 +99,35 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert _cabi.version().endswith("sm_100a")
 
 
+def test_workspace_size_queries_are_host_only_and_consistent():
+    """ln_conv_workspace_bytes / ln_group_norm_workspace_bytes are pure host functions (callable without a GPU); the
+    Python-side copies of their rules (lattice.py:_conv_ws_bytes, lattice_modules.py:_gn_workspace) must agree."""
+    from lattice_net_b200 import _cabi, lattice as lattice_mod
+    from lattice_net_b200.lattice import Lattice
+    lib = _cabi.load()
+    F = 9
+    saved = lattice_mod.CONV_PRECISION
+    try:
+        lattice_mod.CONV_PRECISION = 1
+        for c_in, c_out in [(32, 32), (64, 128), (128, 96), (256, 256), (64, 512), (512, 384), (96, 7), (3, 32), (32, 2048)]:
+            want = int(lib.ln_conv_workspace_bytes(F, c_in, c_out, 1))
+            assert Lattice._conv_ws_bytes(F, c_in, c_out) == want, (c_in, c_out)
+        # layers wider than one 256-column tile are chunked, not sent to the fp32 kernel
+        assert int(lib.ln_conv_workspace_bytes(F, 64, 512, 1)) == 2 * F * 64 * 512 * 4
+        assert int(lib.ln_conv_workspace_bytes(F, 3, 32, 1)) == 0          # c_in % 32 != 0: fp32 kernel, no workspace
+        assert int(lib.ln_conv_workspace_bytes(F, 64, 64, 0)) == 0         # precision 0
+    finally:
+        lattice_mod.CONV_PRECISION = saved
+    gn = lib.ln_group_norm_workspace_bytes
+    assert int(gn(1000, 128, 32)) == 0                       # ShapeNet-sized level: one CTA per group, no scratch
+    assert int(gn(673, 512, 32)) > 0                         # 16 channels per group: row-tiled even when small
+    big = int(gn(34809, 64, 32))
+    rows_per_cta = (256 // (64 // 4)) * 8
+    ctas = -(-34809 // rows_per_cta)
+    assert big == (ctas * 2 * 64 + 2 * 32) * 4
+    assert int(gn(34809, 66, 33)) == 0                       # C % 4 != 0: generic kernel
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from lattice_net_b200 import _cabi
     monkeypatch.setattr(_cabi, "_lib", None)
