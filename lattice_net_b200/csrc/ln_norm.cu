@@ -338,6 +338,7 @@ group_norm_bwd_small_kernel(const float* __restrict__ dy, const float* __restric
 //   backward: per-channel partial sums of dy' xhat and dy'  ->  finalize (dgamma, dbeta, per-group ds / db)  ->  apply
 // Thread layout: tpr = C/4 threads per row (one float4 each), rpp = 256 / tpr rows per pass, kGtIter passes.
 constexpr int kGtIter = 8;
+constexpr int kGtRedRows = 148;      // rows the backward partials are pre-reduced to on very large lattices
 constexpr int kGtMaxThreads = 256;
 
 struct GtPlan {
@@ -352,7 +353,9 @@ static bool gt_plan(int nv_rows, int c, int cpg, GtPlan* p) {
     p->ctas = (nv_rows + p->rows_per_cta - 1) / p->rows_per_cta;
     return true;
 }
-static size_t gt_workspace_floats(const GtPlan& p, int c, int groups) { return (size_t)p.ctas * 2 * c + 2 * (size_t)groups; }
+static size_t gt_workspace_floats(const GtPlan& p, int c, int groups) {   // partials, pre-reduced partials, per-group (ds, db)
+    return (size_t)p.ctas * 2 * c + (size_t)kGtRedRows * 2 * c + 2 * (size_t)groups;
+}
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -534,6 +537,18 @@ gn_tiled_bwd_partial_kernel(const float* __restrict__ dy, const float* __restric
     }
 }
 
+// Pre-reduction of the per-CTA partial rows when there are many of them (lattices beyond ~10^5 vertices): out[s][col] =
+// sum over rows r = s, s + S, s + 2S, ... of in[r][col], lane = column (coalesced), fixed order (deterministic).  The
+// finalize kernel then walks S rows instead of thousands with a single CTA per 128 channels.
+__global__ void __launch_bounds__(128)
+gn_tiled_reduce_rows_kernel(const float* __restrict__ in, int rows, int width, float* __restrict__ out) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= width) return;
+    float acc = 0.0f;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) acc += __ldg(in + (size_t)r * width + col);
+    out[(size_t)blockIdx.y * width + col] = acc;
+}
+
 // dgamma / dbeta per channel and gstat[g] = (ds, db) = sum_j (a_j, b_j) gamma_j per group.  A CTA owns `cpc` consecutive
 // channels (a whole number of groups, <= 128): lane = channel, so the loads of one partial row are coalesced; four
 // slices of CTAs are summed side by side and combined in a fixed order (deterministic).
@@ -702,11 +717,20 @@ int ln_group_norm_bwd(const float* dy, const float* x, const float* y, const flo
 #undef LN_GN_BWD
     } else if (GtPlan p; workspace != nullptr && gt_plan(nv, c, cpg, &p)) {
         float* partial_ab = workspace;
-        float* gstat = workspace + (size_t)p.ctas * 2 * c;
+        float* reduced_ab = workspace + (size_t)p.ctas * 2 * c;
+        float* gstat = reduced_ab + (size_t)kGtRedRows * 2 * c;
         const size_t smem = (size_t)p.rpp * 2 * c * sizeof(float);
         gn_tiled_bwd_partial_kernel<<<p.ctas, p.threads, smem, s>>>(dy, x, y, stats, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, relu, partial_ab);
+        const float* fin_in = partial_ab;
+        int fin_rows = p.ctas;
+        if (p.ctas > 4 * kGtRedRows) {
+            gn_tiled_reduce_rows_kernel<<<dim3((2 * c + 127) / 128, kGtRedRows), 128, 0, s>>>(partial_ab, p.ctas, 2 * c, reduced_ab);
+            count_launch();
+            fin_in = reduced_ab;
+            fin_rows = kGtRedRows;
+        }
         const int cpc = cpg >= kGtFinLanes ? cpg : (kGtFinLanes / cpg) * cpg;       // whole groups per CTA
-        gn_tiled_bwd_finalize_kernel<<<(c + cpc - 1) / cpc, kGtFinLanes * kGtFinSlices, 0, s>>>(partial_ab, p.ctas, c, cpg, cpc, gamma, dgamma, dbeta, gstat);
+        gn_tiled_bwd_finalize_kernel<<<(c + cpc - 1) / cpc, kGtFinLanes * kGtFinSlices, 0, s>>>(fin_in, fin_rows, c, cpg, cpc, gamma, dgamma, dbeta, gstat);
         gn_tiled_bwd_apply_kernel<<<p.ctas, p.threads, 0, s>>>(dy, x, y, gamma, stats, gstat, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, relu, dx);
         count_launch();
         count_launch();

@@ -568,7 +568,7 @@ def test_conv_tensor_core_cross_level(built):
 # nv <= 2048 with 1..8 channels per group: one CTA per group; everything else (scene-sized levels, the 512-channel KITTI
 # bottleneck with 16 channels per group, widths that are not a multiple of 32) runs the row-tiled kernels
 @pytest.mark.parametrize("nv,C", [(983, 32), (1231, 128), (77, 192), (25, 256), (300, 8), (5000, 96), (34809, 64), (2773, 256),
-                                  (673, 512), (57169, 32), (10501, 384), (3001, 48)])
+                                  (673, 512), (57169, 32), (10501, 384), (3001, 48), (20000, 256)])   # the last two of 384 / 256: > 592 row blocks -> pre-reduced partials
 @pytest.mark.parametrize("relu", [False, True])
 def test_fused_group_norm(nv, C, relu):
     """ln_group_norm_fwd/bwd vs torch.nn.GroupNorm on the [1, C, nv] view the reference uses."""

@@ -124,7 +124,7 @@ def test_workspace_size_queries_are_host_only_and_consistent():
     big = int(gn(34809, 64, 32))
     rows_per_cta = (256 // (64 // 4)) * 8
     ctas = -(-34809 // rows_per_cta)
-    assert big == (ctas * 2 * 64 + 2 * 32) * 4
+    assert big == (ctas * 2 * 64 + 148 * 2 * 64 + 2 * 32) * 4  # per-CTA partials + pre-reduced partials + per-group (ds, db)
     assert int(gn(34809, 66, 33)) == 0                       # C % 4 != 0: generic kernel
 
 
