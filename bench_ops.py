@@ -215,6 +215,30 @@ def run(n, d, vals, quick, order="random"):
             del fb, gout
         del lat2, lvr
     bench_group_norm(nv, [v for v in vals if v >= 32][:2], cfg0, dev)
+    # fused slice + classify, widths for which the reference instantiation is built
+    for V, nc in [(v, c) for v, c in ((32, 7), (64, 16), (128, 20)) if v in vals]:
+        cfg = dict(cfg0, val_dim=V, nr_classes=nc)
+        lvc = torch.randn((nv, V), device=dev)
+        dw = torch.randn((n, d + 1), device=dev) * 0.05
+        cw, cb = torch.randn((nc, V), device=dev) * 0.2, torch.zeros((nc,), device=dev)
+        gl = torch.randn((n, nc), device=dev)
+        latc = lat.clone_lattice()
+        latc.set_values(lvc)
+        nbytes = 12.0 * n * (d + 1) + 4.0 * nv * V + 4.0 * n * nc + 4.0 * nc * V
+        rs_f = rs_b = None
+        if ref is not None and ref.k.has(f"slice_classify_with_precomputation<{d},{V},{nc}>"):
+            try:
+                lvr_c = torch.randn((ref.nv(), V), device=dev)
+                rs_f = timeit(lambda: ref.slice_classify_with_precomputation(pos, lvr_c, dw, cw, cb, ridx, rw), reps=3)
+                rs_b = timeit(lambda: ref.slice_classify_backwards(gl, lvr_c, dw, cw, cb, ridx, rw), reps=3)
+            except Exception as exc:      # the sweep goes on without the reference column
+                print(f"# reference slice_classify<{d},{V},{nc}> not timed: {exc}", file=sys.stderr)
+        emit("slice_classify_fwd", cfg, timeit(lambda: latc.slice_classify_with_precomputation(pos, dw, cw, cb, nc, idx, w), reps=5),
+             nbytes=nbytes, ref_sec=rs_f)
+        g_lv, g_dw, g_w, g_b = torch.zeros_like(lvc), torch.zeros_like(dw), torch.zeros_like(cw), torch.zeros_like(cb)
+        emit("slice_classify_bwd", cfg, timeit(lambda: latc.slice_classify_backwards_with_precomputation(gl, pos, lvc, dw, cw, cb, nc, g_lv, g_dw, g_w, g_b, idx, w), reps=5),
+             nbytes=nbytes + 4.0 * nv * V + 4.0 * n * (d + 1), ref_sec=rs_b)
+        del lvc, dw, gl, g_lv, g_dw, latc
     # neighbour table
     lat3 = lat.clone_lattice()
     lat3.set_values(torch.zeros((nv, 1), device=dev))

@@ -5,6 +5,7 @@
 // Layout rule used throughout: lanes run along the channel dimension of one vertex row, so every
 // global access is a contiguous (vectorised where val_dim % 4 == 0) run -- the reference maps one
 // thread to one point and walks channels serially (stride-V across the warp).
+#include <cstdlib>
 #include "ln_common.cuh"
 
 namespace ln {
@@ -95,6 +96,14 @@ static int blocks_per_sm(const void* kernel) {
         nb = 4;
     }
     return nb;
+}
+static bool slice_classify_v1() {   // development switch: LN_SLICE_CLASSIFY_V1=1 selects the warp-per-point scalar kernels
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LN_SLICE_CLASSIFY_V1");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
 }
 static int device_sms() {
     static int n = 0;
@@ -364,6 +373,87 @@ slice_classify_fwd_kernel(const float* __restrict__ lattice_values, const int* _
     }
 }
 
+// Tiled forward (val_dim % 4 == 0).  ncu on the 10^6-point sweep showed the warp-per-point kernel above issue-bound
+// (74 % issue slots, one 5-step butterfly reduction per class and point).  Here a CTA walks tiles of kScfPoints points:
+//   phase A  thread = (point, float4 column): the SPV ids / weights are read first, then all SPV row loads are issued
+//            together and folded into s_p = sum_r (w_r + dw_r) values[idx_r]; the tile of s rows is parked in smem;
+//   phase B  thread = (point, group of 8 classes): logits[p, c] = <s_p, W_c> + b_c as a register-tiled mini GEMM --
+//            one float4 of s_p and one broadcast float4 of W_c per four FMAs, no cross-lane reduction at all.
+// Row stride of the s tile is V + 4 floats: the float4 reads of 8 consecutive points fall into 32 distinct banks.
+constexpr int kScfPoints = 64;
+template <int SPV>
+__global__ void __launch_bounds__(kBlock)
+slice_classify_fwd_tiled_kernel(const float* __restrict__ lattice_values, const int* __restrict__ indices,
+                                const float* __restrict__ weights, const float* __restrict__ delta_weights,
+                                const float* __restrict__ cls_weight, const float* __restrict__ cls_bias, int n,
+                                int val_dim, int nr_classes, float* __restrict__ logits) {
+    extern __shared__ __align__(16) float smem_t[];
+    const int lds = val_dim + 4;
+    float* w_sh = smem_t;                            // [nc][V]
+    float* s_sh = w_sh + nr_classes * val_dim;       // [kScfPoints][V + 4]
+    for (int i = threadIdx.x; i < nr_classes * val_dim; i += blockDim.x) w_sh[i] = __ldg(cls_weight + i);
+    const int cv = val_dim >> 2;
+    const int n_tiles = (n + kScfPoints - 1) / kScfPoints;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();                             // w_sh ready / phase B of the previous tile done
+        const long long p0 = (long long)tile * kScfPoints;
+        for (int e = threadIdx.x; e < kScfPoints * cv; e += blockDim.x) {
+            const int pl = e / cv, j = e - pl * cv;
+            const long long p = p0 + pl;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p < n) {
+                int id[SPV];
+                float w[SPV];
+#pragma unroll
+                for (int r = 0; r < SPV; r++) {
+                    id[r] = __ldg(indices + p * SPV + r);
+                    w[r] = __ldg(weights + p * SPV + r) + __ldg(delta_weights + p * SPV + r);
+                }
+                float4 x[SPV];
+#pragma unroll
+                for (int r = 0; r < SPV; r++)
+                    x[r] = id[r] >= 0 ? __ldg(reinterpret_cast<const float4*>(lattice_values + (size_t)id[r] * val_dim) + j)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int r = 0; r < SPV; r++) {
+                    acc.x = fmaf(x[r].x, w[r], acc.x);
+                    acc.y = fmaf(x[r].y, w[r], acc.y);
+                    acc.z = fmaf(x[r].z, w[r], acc.z);
+                    acc.w = fmaf(x[r].w, w[r], acc.w);
+                }
+            }
+            *reinterpret_cast<float4*>(s_sh + pl * lds + 4 * j) = acc;
+        }
+        __syncthreads();
+        const int pl = threadIdx.x & (kScfPoints - 1);
+        const long long p = p0 + pl;
+        const float* srow = s_sh + pl * lds;
+        for (int c0 = (threadIdx.x / kScfPoints) * 8; c0 < nr_classes; c0 += (kBlock / kScfPoints) * 8) {
+            float acc[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] = 0.0f;
+            for (int v = 0; v < val_dim; v += 4) {
+                const float4 s4 = *reinterpret_cast<const float4*>(srow + v);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (c0 + k < nr_classes) {       // uniform across the warp: no divergence
+                        const float4 w4 = *reinterpret_cast<const float4*>(w_sh + (c0 + k) * val_dim + v);
+                        acc[k] = fmaf(s4.x, w4.x, acc[k]);
+                        acc[k] = fmaf(s4.y, w4.y, acc[k]);
+                        acc[k] = fmaf(s4.z, w4.z, acc[k]);
+                        acc[k] = fmaf(s4.w, w4.w, acc[k]);
+                    }
+                }
+            }
+            if (p < n) {
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (c0 + k < nr_classes) logits[p * nr_classes + c0 + k] = acc[k] + __ldg(cls_bias + c0 + k);
+            }
+        }
+    }
+}
+
 // slice_classify backward.  Persistent blocks walk tiles of kTile points:
 //   phase A (warp per point): s_p = sum_r (w+dw) values[idx_r], t_p = g_p * W, scatter
 //            (w+dw)*t_p into the lattice gradient, grad_dw[p,r] = <values[idx_r], t_p>;
@@ -450,6 +540,150 @@ slice_classify_bwd_kernel(const float* __restrict__ grad_logits, const float* __
             for (int k = 0; k < KV; k++) {
                 const int v = lane + 32 * k;
                 if (v < val_dim) s_row[v] = s[k];
+            }
+        }
+        __syncthreads();
+        // phase B: grad_W[c][v] += sum_p G[p][c] * S[p][v]
+#pragma unroll
+        for (int i = 0; i < kMaxAcc; i++) {
+            const int o = threadIdx.x + i * kBlock;
+            if (o < n_out) {
+                const int c = o / val_dim, v = o - c * val_dim;
+                float acc = gw_acc[i];
+#pragma unroll 8
+                for (int pl = 0; pl < kTile; pl++) acc = fmaf(g_sh[pl * nr_classes + c], s_sh[pl * val_dim + v], acc);
+                gw_acc[i] = acc;
+            }
+        }
+        if (threadIdx.x < nr_classes) {
+            for (int pl = 0; pl < kTile; pl++) gb_acc += g_sh[pl * nr_classes + threadIdx.x];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxAcc; i++) {
+        const int o = threadIdx.x + i * kBlock;
+        if (o < n_out) atomicAdd(grad_cls_weight + o, gw_acc[i]);
+    }
+    if (threadIdx.x < nr_classes) atomicAdd(grad_cls_bias + threadIdx.x, gb_acc);
+}
+
+// Vectorised backward (val_dim % 4 == 0, SPV known at compile time).  The kernel above is latency-bound (ncu, 10^6
+// points: 25 % occupancy, 5.5 % L2 throughput, one dependent index -> row -> atomic chain per simplex vertex, 4-byte
+// reductions).  Same tiling and phase B, but in phase A a lane owns float4 column(s) of the row: the SPV ids /
+// weights are fetched by SPV lanes and broadcast, ALL row loads of the simplex are issued before anything consumes
+// them (t_p = g_p W is computed while they are in flight), and the lattice gradient receives 16-byte reductions
+// (red.global.add.v4.f32, evict_last like the row scatter) -- a quarter of the L2 atomic operations.
+template <int KV4, int SPV>   // KV4 float4 columns per lane: val_dim <= 128 * KV4
+__global__ void __launch_bounds__(kBlock)
+slice_classify_bwd_vec_kernel(const float* __restrict__ grad_logits, const float* __restrict__ lattice_values,
+                              const int* __restrict__ indices, const float* __restrict__ weights,
+                              const float* __restrict__ delta_weights, const float* __restrict__ cls_weight, int n,
+                              int val_dim, int nr_classes, float* __restrict__ grad_lattice_values,
+                              float* __restrict__ grad_delta_weights, float* __restrict__ grad_cls_weight,
+                              float* __restrict__ grad_cls_bias) {
+    extern __shared__ __align__(16) float smem_v[];
+    float* w_sh = smem_v;                               // [nc][V]
+    float* s_sh = w_sh + nr_classes * val_dim;          // [kTile][V]
+    float* g_sh = s_sh + kTile * val_dim;               // [kTile][nc]
+    for (int i = threadIdx.x; i < nr_classes * val_dim; i += blockDim.x) w_sh[i] = __ldg(cls_weight + i);
+
+    constexpr int kMaxAcc = 24;                         // nc*V <= kMaxAcc*kBlock  (checked on the host)
+    float gw_acc[kMaxAcc];
+#pragma unroll
+    for (int i = 0; i < kMaxAcc; i++) gw_acc[i] = 0.0f;
+    float gb_acc = 0.0f;
+    const int n_out = nr_classes * val_dim;
+    const int cv = val_dim >> 2;
+    const uint64_t keep = l2_policy_evict_last();
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const int n_tiles = (n + kTile - 1) / kTile;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();   // w_sh ready / previous tile's phase B done
+        const int p0 = tile * kTile;
+        const int tile_n = min(kTile, n - p0);
+        for (int pl = warp; pl < kTile; pl += warps_per_block) {
+            float* s_row = s_sh + pl * val_dim;
+            float* g_row = g_sh + pl * nr_classes;
+            if (pl >= tile_n) {   // pad the tile with zeros so phase B needs no bounds
+                for (int v = lane; v < val_dim; v += 32) s_row[v] = 0.0f;
+                for (int c = lane; c < nr_classes; c += 32) g_row[c] = 0.0f;
+                continue;
+            }
+            const long long p = p0 + pl;
+            int my_id = -1;
+            float my_w = 0.0f;
+            if (lane < SPV) {
+                my_id = __ldg(indices + p * SPV + lane);
+                my_w = __ldg(weights + p * SPV + lane) + __ldg(delta_weights + p * SPV + lane);
+            }
+            for (int c = lane; c < nr_classes; c += 32) g_row[c] = __ldg(grad_logits + p * nr_classes + c);
+            int id[SPV];
+            float w[SPV];
+#pragma unroll
+            for (int r = 0; r < SPV; r++) {
+                id[r] = __shfl_sync(0xffffffffu, my_id, r);
+                w[r] = __shfl_sync(0xffffffffu, my_w, r);
+            }
+            float4 x[SPV][KV4];
+#pragma unroll
+            for (int r = 0; r < SPV; r++)
+#pragma unroll
+                for (int k = 0; k < KV4; k++) {
+                    const int j = lane + 32 * k;
+                    x[r][k] = (id[r] >= 0 && j < cv) ? __ldg(reinterpret_cast<const float4*>(lattice_values + (size_t)id[r] * val_dim) + j)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            __syncwarp();   // g_row written by all lanes
+            float4 t[KV4], sacc[KV4];
+#pragma unroll
+            for (int k = 0; k < KV4; k++) {
+                t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                sacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            for (int c = 0; c < nr_classes; c++) {
+                const float g = g_row[c];
+#pragma unroll
+                for (int k = 0; k < KV4; k++) {
+                    const int j = lane + 32 * k;
+                    if (j < cv) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(w_sh + c * val_dim + 4 * j);
+                        t[k].x = fmaf(g, w4.x, t[k].x);
+                        t[k].y = fmaf(g, w4.y, t[k].y);
+                        t[k].z = fmaf(g, w4.z, t[k].z);
+                        t[k].w = fmaf(g, w4.w, t[k].w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < SPV; r++) {
+                float dot = 0.0f;
+#pragma unroll
+                for (int k = 0; k < KV4; k++) {
+                    const int j = lane + 32 * k;
+                    const float4 xv = x[r][k];
+                    sacc[k].x = fmaf(xv.x, w[r], sacc[k].x);
+                    sacc[k].y = fmaf(xv.y, w[r], sacc[k].y);
+                    sacc[k].z = fmaf(xv.z, w[r], sacc[k].z);
+                    sacc[k].w = fmaf(xv.w, w[r], sacc[k].w);
+                    dot = fmaf(xv.x, t[k].x, dot);
+                    dot = fmaf(xv.y, t[k].y, dot);
+                    dot = fmaf(xv.z, t[k].z, dot);
+                    dot = fmaf(xv.w, t[k].w, dot);
+                    if (id[r] >= 0 && j < cv)
+                        red_v4_hint(grad_lattice_values + (size_t)id[r] * val_dim + 4 * j,
+                                    make_float4(t[k].x * w[r], t[k].y * w[r], t[k].z * w[r], t[k].w * w[r]), keep);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                if (lane == 0) grad_delta_weights[p * SPV + r] += dot;   // (p,r) is owned by this warp
+            }
+#pragma unroll
+            for (int k = 0; k < KV4; k++) {
+                const int j = lane + 32 * k;
+                if (j < cv) *reinterpret_cast<float4*>(s_row + 4 * j) = sacc[k];
             }
         }
         __syncthreads();
@@ -608,6 +842,28 @@ int ln_slice_classify_fwd(const float* lattice_values, const int* indices, const
         return LN_ERR_UNSUPPORTED;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        const size_t smem_t = ((size_t)nr_classes * val_dim + (size_t)kScfPoints * (val_dim + 4)) * sizeof(float);
+        if (val_dim % 4 == 0 && (pos_dim == 3 || pos_dim == 5) && smem_t <= 200 * 1024 && !slice_classify_v1()) {
+            const int grid_t = min(cdiv(n, kScfPoints), 148 * 2);
+            cudaError_t err = cudaSuccess;
+            if (pos_dim == 3) {
+                if (smem_t > 48 * 1024) err = allow_max_smem((const void*)slice_classify_fwd_tiled_kernel<4>);
+                if (err == cudaSuccess)
+                    slice_classify_fwd_tiled_kernel<4><<<grid_t, kBlock, smem_t, s>>>(lattice_values, indices, weights, delta_weights, cls_weight, cls_bias, n, val_dim, nr_classes, logits);
+            } else {
+                if (smem_t > 48 * 1024) err = allow_max_smem((const void*)slice_classify_fwd_tiled_kernel<6>);
+                if (err == cudaSuccess)
+                    slice_classify_fwd_tiled_kernel<6><<<grid_t, kBlock, smem_t, s>>>(lattice_values, indices, weights, delta_weights, cls_weight, cls_bias, n, val_dim, nr_classes, logits);
+            }
+            if (err != cudaSuccess) {
+                set_error("ln_slice_classify_fwd: %s", cudaGetErrorString(err));
+                return LN_ERR_CUDA;
+            }
+            count_launch();
+            return check_launch("slice_classify_fwd_tiled");
+        }
+    }
     const size_t smem = (size_t)nr_classes * val_dim * sizeof(float);
     const int grid = min(cdiv(n, kBlock / 32), 148 * 8);
     const int kv = cdiv(val_dim, 32);
@@ -642,6 +898,25 @@ int ln_slice_classify_bwd(const float* grad_logits, const float* lattice_values,
     cudaStream_t s = (cudaStream_t)stream;
     const size_t smem = ((size_t)nr_classes * val_dim + (size_t)kTile * val_dim + (size_t)kTile * nr_classes) * sizeof(float);
     const int grid = min(cdiv(n, kTile), 148 * 2);
+    if (val_dim % 4 == 0 && (pos_dim == 3 || pos_dim == 5) && !slice_classify_v1()) {
+#define LN_LAUNCH_SCBV(KV4, SPV)                                                                                   \
+    do {                                                                                                           \
+        cudaError_t err = smem > 48 * 1024 ? allow_max_smem((const void*)slice_classify_bwd_vec_kernel<KV4, SPV>) : cudaSuccess; \
+        if (err != cudaSuccess) {                                                                                  \
+            set_error("ln_slice_classify_bwd: %s", cudaGetErrorString(err));                                       \
+            return LN_ERR_CUDA;                                                                                    \
+        }                                                                                                          \
+        slice_classify_bwd_vec_kernel<KV4, SPV><<<grid, kBlock, smem, s>>>(grad_logits, lattice_values, indices, weights, delta_weights, cls_weight, n, val_dim, nr_classes, grad_lattice_values, grad_delta_weights, grad_cls_weight, grad_cls_bias); \
+    } while (0)
+        if (val_dim <= 128) {
+            if (pos_dim == 3) LN_LAUNCH_SCBV(1, 4); else LN_LAUNCH_SCBV(1, 6);
+        } else {
+            if (pos_dim == 3) LN_LAUNCH_SCBV(2, 4); else LN_LAUNCH_SCBV(2, 6);
+        }
+#undef LN_LAUNCH_SCBV
+        count_launch();
+        return check_launch("slice_classify_bwd_vec");
+    }
     const int kv = cdiv(val_dim, 32);
 #define LN_LAUNCH_SCB(KV)                                                                                          \
     do {                                                                                                           \

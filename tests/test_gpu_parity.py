@@ -172,7 +172,7 @@ def test_gather_fwd_bwd(built):
     assert_close(grad, lo.gather_bwd(gg, b["cpu"]["indices"], b["cpu"]["weights"], b["nv"], V), TOL_GRADS, "gather backward vs oracle")
 
 
-@pytest.mark.parametrize("V,nc", [(32, 7), (128, 20), (8, 4)])
+@pytest.mark.parametrize("V,nc", [(32, 7), (128, 20), (8, 4), (64, 16), (256, 20)])
 def test_slice_classify(built, V, nc):
     b = built
     if b["d"] != 3:
