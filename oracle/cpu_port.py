@@ -293,7 +293,7 @@ def time_training_step(gpu_model, cloud_fn, nr_classes, sigma, budget_s=20.0):
             done += 1
             t_total += dt
         i += 1
-        if (time.time() - t_start > budget_s and done >= 2) or done >= 20:
+        if (time.time() - t_start > budget_s and done >= 2) or done >= 80:     # ~15-20 s of host work either way
             break
     return {"value": done / t_total, "unit": "scans/s", "cores": cores, "kind": "port",
             "sample": f"{done} scans of the same workload (2048-pt clouds, fwd+bwd+AdamW), torch-CPU gather/index_add/mm port incl. lattice construction on 1 core (C oracle)",
