@@ -352,6 +352,40 @@ def test_empty_and_tiny_inputs():
     assert abs(float(lat.values()[:4].sum()) - 2.0) < 1e-5
 
 
+def test_duplicate_points_and_crowded_table():
+    """Collisions and contention: 1000 copies of one point (every insert after the first finds its key present, the
+    accumulation hits four rows 1000 times) mixed with random points, in a table sized for an 85 % load factor (long
+    linear probes).  Structure must still equal the oracle's exactly, values within the fp32 tolerance."""
+    from lattice_net_b200 import Lattice
+    rng = np.random.RandomState(11)
+    pos_np = np.concatenate([np.tile(np.array([[0.123, -0.456, 0.789]], np.float32), (1000, 1)),
+                             (rng.rand(1000, 3).astype(np.float32) - 0.5)], 0)
+    pos_np = np.ascontiguousarray(pos_np[rng.permutation(len(pos_np))])
+    sig = [0.05] * 3
+    cpu = lo.build_lattice(pos_np, sig)
+    capacity = int(cpu["nv"] / 0.85) + 1
+    vals_np = cases.randn((len(pos_np), 4), 12)
+    lat = Lattice(capacity, [(0.05, 3)])
+    lat.begin_splat()
+    idx, w = lat.splat_standalone(cuda(pos_np), cuda(vals_np))
+    nv = lat.nr_lattice_vertices()                      # raises if the table overflowed
+    assert nv == cpu["nv"]
+    ks, o2n, n2o = canonical(lat.hash_table().m_keys_tensor[:nv].cpu().numpy())
+    assert np.array_equal(ks, cpu["keys"])
+    assert len(np.unique(ks, axis=0)) == nv             # no key stored twice
+    assert np.array_equal(lo.relabel(idx.cpu().numpy(), o2n), cpu["indices"])
+    assert bits_equal(w.cpu().numpy(), cpu["weights"]) == 0
+    exp = lo.splat_accumulate(vals_np, cpu["indices"], cpu["weights"], nv)
+    assert_close(lat.values()[:nv].cpu().numpy()[n2o], exp, TOL_VALUES, "splat values with 1000 coincident points")
+    # the same table answers look-ups for the slice without precomputation
+    l2 = lat.clone_lattice()
+    lv = cases.randn((nv, 8), 13)
+    l2.set_values(cuda(lv[o2n]))
+    s, i2, w2 = l2.slice_standalone_no_precomputation(cuda(pos_np))
+    assert np.array_equal(lo.relabel(i2.cpu().numpy(), o2n), cpu["indices"])
+    assert_close(s.cpu().numpy(), lo.slice_fwd(lv, cpu["indices"], cpu["weights"], len(pos_np)), 1e-6, "slice through a crowded table")
+
+
 def test_golden_vectors_match_cuda_path(golden_dir):
     """Committed reference outputs (made by oracle/make_golden.py from the reference kernels)."""
     from lattice_net_b200 import Lattice
