@@ -85,6 +85,64 @@ def test_conv_dgrad_is_adjoint_and_wgrad_matches_finite_difference():
     assert abs(fd - gw[7, 2]) < 2e-2 * max(abs(fd), 1.0)
 
 
+def test_splat_slice_gather_backwards_are_the_adjoints_of_their_forwards():
+    """The oracle's backward restatements against its forward ones: splat / slice backward is the transpose of
+    slice forward, gather backward the transpose of gather forward on the value columns."""
+    pos = cases.box_surface(300, 9)
+    L = lo.build_lattice(pos, [0.05] * 3)
+    n, nv = len(pos), L["nv"]
+    rng = np.random.RandomState(2)
+    V = 5
+    lv = rng.randn(nv, V).astype(np.float32)
+    g = rng.randn(n, V).astype(np.float32)
+    lhs = float((lo.slice_fwd(lv, L["indices"], L["weights"], n).astype(np.float64) * g).sum())
+    rhs = float((lv.astype(np.float64) * lo.slice_bwd(g, L["indices"], L["weights"], nv)).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
+    assert np.array_equal(lo.slice_bwd(g, L["indices"], L["weights"], nv), lo.splat_accumulate(g, L["indices"], L["weights"], nv))
+    gg = rng.randn(n, 4 * (V + 1)).astype(np.float32)
+    gathered = lo.gather_fwd(lv, L["indices"], L["weights"], n)
+    gv = gg.reshape(n, 4, V + 1).copy()
+    gv[:, :, V] = 0.0                                  # the weight column carries no gradient to the values
+    lhs = float((gathered.astype(np.float64) * gv.reshape(n, -1)).sum())
+    rhs = float((lv.astype(np.float64) * lo.gather_bwd(gg, L["indices"], L["weights"], nv, V)).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
+    # the weight column of the gather is the barycentric weight itself
+    assert np.array_equal(gathered.reshape(n, 4, V + 1)[:, :, V].ravel(), L["weights"])
+
+
+def test_slice_classify_backward_matches_finite_differences():
+    """slice_classify_bwd (LatticeGPU.cuh:3628-3756 restated) against central differences of slice_classify_fwd in all
+    four of its differentiable inputs: lattice values, delta weights, classifier weight and bias."""
+    pos = cases.box_surface(200, 10)
+    L = lo.build_lattice(pos, [0.05] * 3)
+    n, nv = len(pos), L["nv"]
+    rng = np.random.RandomState(4)
+    V, nc = 6, 5
+    lv = rng.randn(nv, V).astype(np.float32)
+    dw = (rng.randn(n, 4) * 0.05).astype(np.float32)
+    cw = (rng.randn(nc, V) * 0.3).astype(np.float32)
+    cb = rng.randn(nc).astype(np.float32)
+    g = rng.randn(n, nc).astype(np.float32)
+
+    def objective(lv_, dw_, cw_, cb_):
+        # float64 pre-rounding value: the second return of slice_classify_fwd is the sliced row in float64
+        _, s = lo.slice_classify_fwd(lv_, L["indices"], L["weights"], dw_, cw_, cb_, n)
+        return float(((s @ np.asarray(cw_, np.float64).T + np.asarray(cb_, np.float64)) * g).sum())
+
+    g_lv, g_dw, g_w, g_b = lo.slice_classify_bwd(g, lv, L["indices"], L["weights"], dw, cw, n)
+    eps = 1e-2                                           # exact up to rounding: the objective is bilinear in each input
+    for arr, grad, picks in ((lv, g_lv, [(0, 0), (nv // 2, 3), (nv - 1, V - 1)]), (dw, g_dw, [(0, 0), (n // 3, 2), (n - 1, 3)]),
+                             (cw, g_w, [(0, 0), (nc - 1, V - 1)]), (cb, g_b, [(0,), (nc - 1,)])):
+        for pick in picks:
+            plus, minus = arr.copy(), arr.copy()
+            plus[pick] += eps
+            minus[pick] -= eps
+            args_p = [plus if a is arr else a for a in (lv, dw, cw, cb)]
+            args_m = [minus if a is arr else a for a in (lv, dw, cw, cb)]
+            fd = (objective(*args_p) - objective(*args_m)) / (float(plus[pick]) - float(minus[pick]))
+            assert abs(fd - float(grad[pick])) <= 1e-3 * max(abs(fd), 1.0), (pick, fd, float(grad[pick]))
+
+
 def test_cross_level_tables():
     pos = cases.box_surface(1024, 7)
     fine = lo.build_lattice(pos, [0.05] * 3)
