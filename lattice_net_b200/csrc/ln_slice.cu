@@ -845,8 +845,23 @@ int ln_slice_classify_fwd(const float* lattice_values, const int* indices, const
     {
         const size_t smem_t = ((size_t)nr_classes * val_dim + (size_t)kScfPoints * (val_dim + 4)) * sizeof(float);
         if (val_dim % 4 == 0 && (pos_dim == 3 || pos_dim == 5) && smem_t <= 200 * 1024 && !slice_classify_v1()) {
-            const int grid_t = min(cdiv(n, kScfPoints), 148 * 2);
-            cudaError_t err = cudaSuccess;
+            // as many CTAs as stay resident (ncu r01s: with 2 per SM the kernel sat at 25 % occupancy, latency-bound);
+            // the tile loop is grid-stride, so the grid size only affects scheduling
+            const void* kern = pos_dim == 3 ? (const void*)slice_classify_fwd_tiled_kernel<4> : (const void*)slice_classify_fwd_tiled_kernel<6>;
+            cudaError_t err = smem_t > 48 * 1024 ? allow_max_smem(kern) : cudaSuccess;
+            static int cached_resident[2] = {0, 0};          // per kernel variant; queried once per shared-memory size
+            static size_t cached_smem[2] = {0, 0};
+            const int slot = pos_dim == 3 ? 0 : 1;
+            int resident = cached_smem[slot] == smem_t ? cached_resident[slot] : 0;
+            if (resident < 1) {
+                if (err != cudaSuccess || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kBlock, smem_t) != cudaSuccess || resident < 1) {
+                    cudaGetLastError();
+                    resident = 2;
+                }
+                cached_resident[slot] = resident;
+                cached_smem[slot] = smem_t;
+            }
+            const int grid_t = min(cdiv(n, kScfPoints), device_sms() * min(resident, 8));
             if (pos_dim == 3) {
                 if (smem_t > 48 * 1024) err = allow_max_smem((const void*)slice_classify_fwd_tiled_kernel<4>);
                 if (err == cudaSuccess)
