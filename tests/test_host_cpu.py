@@ -158,3 +158,99 @@ def test_batched_lovasz_equals_per_class_loop():
     gb, = torch.autograd.grad(b, logits)
     assert torch.allclose(ga, gb, atol=1e-6)
     assert torch.isfinite(segmentation_loss(torch.log_softmax(logits, 1), labels))
+
+
+# Names the reference binds to Python (live `.def` / `.def_static` / `.def_readonly` lines of
+# /root/reference/src/PyBridge.cxx:27-154, extracted once; the test does not read the reference tree).
+REFERENCE_PYTHON_SURFACE = {
+    "HashTable": [
+        "m_keys_tensor",
+        "m_nr_filled_tensor"
+    ],
+    "Lattice": [
+        "begin_splat",
+        "capacity",
+        "clone_lattice",
+        "convolve_im2row_standalone",
+        "create",
+        "create_coarse_verts",
+        "create_coarse_verts_naive",
+        "distribute",
+        "expand",
+        "gather_backwards_standalone_with_precomputation",
+        "gather_standalone_no_precomputation",
+        "gather_standalone_with_precomputation",
+        "get_expected_filter_extent",
+        "get_filter_extent",
+        "hash_table",
+        "im2row",
+        "im2rowindices",
+        "increase_sigmas",
+        "just_create_verts",
+        "name",
+        "nr_lattice_vertices",
+        "pos_dim",
+        "positions",
+        "row2im",
+        "set_positions",
+        "set_sigma",
+        "set_values",
+        "sigmas_tensor",
+        "slice_backwards_standalone_with_precomputation",
+        "slice_backwards_standalone_with_precomputation_no_homogeneous",
+        "slice_classify_backwards_with_precomputation",
+        "slice_classify_no_precomputation",
+        "slice_classify_with_precomputation",
+        "slice_standalone_no_precomputation",
+        "slice_standalone_with_precomputation",
+        "splat_standalone",
+        "val_dim",
+        "values"
+    ],
+    "TrainParams": [
+        "checkpoint_path",
+        "create",
+        "dataset_name",
+        "lr",
+        "save_checkpoint",
+        "weight_decay",
+        "with_tensorboard",
+        "with_viewer",
+        "with_visdom"
+    ],
+    "EvalParams": [
+        "checkpoint_path",
+        "create",
+        "dataset_name",
+        "do_write_predictions",
+        "output_predictions_path",
+        "with_viewer"
+    ],
+    "ModelParams": [
+        "compression_factor",
+        "create",
+        "dropout_last_layer",
+        "nr_blocks_bottleneck",
+        "nr_blocks_down_stage",
+        "nr_blocks_up_stage",
+        "nr_downsamples",
+        "nr_levels_down_with_normal_resnet",
+        "nr_levels_up_with_normal_resnet",
+        "pointnet_channels_per_layer",
+        "pointnet_start_nr_channels",
+        "positions_mode",
+        "values_mode"
+    ]
+}
+
+
+def test_python_surface_of_the_reference_is_kept():
+    """Drop-in boundary: every class / method / attribute name the reference's pybind module exposes exists here."""
+    import lattice_net_b200 as pkg
+    lattice = pkg.Lattice(60000, [(0.05, 3)])
+    for cls_name, names in REFERENCE_PYTHON_SURFACE.items():
+        cls = getattr(pkg, cls_name, None)
+        assert cls is not None, f"class {cls_name} is missing"
+        obj = lattice if cls_name == "Lattice" else cls
+        missing = [n for n in names if not hasattr(obj, n)]
+        assert not missing, f"{cls_name} lacks {missing}"
