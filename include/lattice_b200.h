@@ -93,8 +93,9 @@ int ln_distribute(const float* positions_raw, const float* sigmas, const float* 
 
 /* Structure part of slice_no_precomputation<d,V> (LatticeGPU.cuh:2598-2750): recompute the simplex
  * of every position and *retrieve* (never insert) its vertices; not-found -> index -1, weight -1. */
+/* max_vertices: row bound of the caller's per-vertex tensors (0 = capacity); ids at or past it are returned as -1. */
 int ln_lookup_simplex(const float* positions_raw, const float* sigmas, int n, int pos_dim,
-                      const int* keys, const int* entries, int capacity,
+                      const int* keys, const int* entries, int capacity, int max_vertices,
                       int* indices, float* weights, void* stream);
 
 /* Replaces coarsen<d> (LatticeGPU.cuh:2314-2514) used by Lattice::create_coarse_verts
@@ -135,30 +136,52 @@ int ln_row2im(const float* rowified, const int* neighbours, int nv, int filter_e
 /* ---- lattice convolution (implicit GEMM, no im2row buffer) -------------------------------------
  * Replaces im2row + `lattice_rowified.mm(filter_bank)` in Lattice::convolve_im2row_standalone
  * (/root/reference/src/Lattice.cu:424-474):
- *   out[q, co] = sum_slot sum_ci nbr_values[neighbours[q, slot'], ci] * filter[slot*c_in + ci, co] (+ bias[co])
+ *   out[q, co] = sum_slot sum_ci nbr_values[neighbours[q, slot'], ci] * filter[slot*c_in + ci, co]
+ *                (+ bias[co]) (+ residual[q, co])
  * slot' = slot^1 for slot < F-1 when flip != 0 (the data-gradient convolution of
  * /root/reference/latticenet_py/lattice/lattice_funcs.py:307-313), else slot.
+ * filter_extent = 1 with neighbours[q, 0] = q is a plain row-major GEMM: the 1x1 layers of the bottleneck blocks and of
+ * the slice head (torch.nn.Linear in lattice_modules.py:806-832) run through the same kernels.
  * transposed_filter != 0: `filter` is the FORWARD bank [F*c_out x c_in] of the convolution whose data
  * gradient is being computed, read as filter_bw[(slot*c_in + ci), co] = filter[(slot*c_out + co), ci]
  * -- the transpose/view/contiguous re-layout of lattice_funcs.py:304-311 without materialising it.
+ * residual (may be NULL): [nv_query x c_out] added in the epilogue (the skip connection of a residual block,
+ * lattice_modules.py:1255-1358, without its own kernel).  bias may be NULL.
  * precision: 0 = exact fp32 FMA on the CUDA cores; 1 = tcgen05 tensor cores, 3xTF32 split (fp32-equivalent,
  * ~1e-6 relative); 2 = tcgen05 single-pass TF32 (~1e-3 relative).  The tensor-core path needs
  * c_in % 32 == 0 and c_out <= 1024 (layers wider than 256 run as 256-column chunks); other shapes run the fp32 kernel
  * whatever `precision` says.
- * workspace: device scratch of ln_conv_workspace_bytes() bytes for precision 1/2 (re-laid-out filter),
- * may be NULL for precision 0.  bias may be NULL. */
-int ln_conv_fwd(const float* nbr_values, const int* neighbours, const float* filter, const float* bias,
+ * slabs: for precision 1/2 a device buffer of ln_conv_workspace_bytes() bytes holding the PREPARED filter of this
+ * reading (pre-swizzled B tiles, TF32 high / low parts).  slabs_prepared != 0: it already does (ln_filter_prepare /
+ * ln_filter_prepare_batch ran after the last change of `filter`); 0: this call prepares it first.  NULL for precision 0.
+ * out_is_zero != 0: the caller hands over a zeroed `out`; otherwise the call clears it itself when
+ * ln_conv_needs_zero() says the kernel accumulates (K split across CTAs on small lattices). */
+int ln_conv_fwd(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, const float* residual,
                 int nv_query, int filter_extent, int c_in, int c_out, int flip, int transposed_filter, int precision,
-                float* workspace, float* out, void* stream);
+                float* slabs, int slabs_prepared, int out_is_zero, float* out, void* stream);
 long long ln_conv_workspace_bytes(int filter_extent, int c_in, int c_out, int precision);
+int ln_conv_needs_zero(int nv_query, int filter_extent, int c_in, int c_out, int precision);
+
+/* Filter preparation for the tensor-core convolution, hoisted out of the per-call path: weights change once per
+ * optimizer step, so every bank is prepared once per step for both of its readings (forward; transposed for the data
+ * gradient) instead of once per convolution call.  ln_filter_prepare: one bank, one launch.
+ * ln_filter_prepare_batch: n_jobs banks in ONE launch; jobs_device = device array of 48-byte records
+ *   { const float* src; float* dst; int k_total (= F*c_in of the reading); int c_in; int c_out; int transposed;
+ *     int split (1 = write the low parts, precision 1); int pad; long long first_thread; }
+ * with first_thread the running sum of k_total * n_pad_sum(c_out) over the preceding jobs (n_pad_sum = c_out rounded up
+ * to 16 within every 256-column chunk) and total_threads that sum over all jobs. */
+int ln_filter_prepare(const float* filter, int filter_extent, int c_in, int c_out, int transposed_filter, int precision,
+                      float* slabs, void* stream);
+int ln_filter_prepare_batch(const void* jobs_device, int n_jobs, long long total_threads, void* stream);
 
 /* Weight gradient, replaces `lattice_rowified.transpose(0,1).mm(grad)` (lattice_funcs.py:302,378,443):
  *   grad_filter[slot*c_in + ci, co] = sum_q nbr_values[neighbours[q, slot], ci] * grad_out[q, co]
- * grad_filter [F*c_in x c_out] is overwritten (zeroed, then accumulated with fp32 reductions).
+ * grad_filter [F*c_in x c_out]: grad_is_zero != 0 = the caller hands over a zeroed buffer (e.g. a slice of a gradient
+ * bucket cleared once per step); 0 = the call clears it when its kernel accumulates with reductions.
  * precision as in ln_conv_fwd: 1 / 2 run the gathered-A^T . G product on tcgen05 (MN-major operands, the
  * reduction runs over the vertices) when c_in % 32 == 0 and c_out % 4 == 0, c_out <= 1024 (256-column chunks); else fp32 FMA. */
 int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* grad_out,
-                  int nv_query, int filter_extent, int c_in, int c_out, int precision,
+                  int nv_query, int filter_extent, int c_in, int c_out, int precision, int grad_is_zero,
                   float* grad_filter, void* stream);
 
 /* Whole backward pass of one lattice convolution out = conv(query <- neighbours) in one call
@@ -167,10 +190,13 @@ int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* g
  *                                     lattice's vertices (neighbours_bwd [nv_nbr x F] = table neighbour -> query),
  *                                     forward filter bank read transposed;            NULL = not wanted
  *   grad_filter [F*c_in x c_out]    = im2row(nbr_values)^T . grad_out                 NULL = not wanted
- * precision / workspace as in ln_conv_fwd (workspace size: ln_conv_workspace_bytes(F, c_out, c_in, precision)). */
+ * The two run side by side (the weight gradient on an internal second stream, joined before returning).
+ * slabs_bwd / slabs_prepared: prepared TRANSPOSED reading of `filter` (ln_conv_workspace_bytes(F, c_out, c_in, precision)
+ * bytes), as in ln_conv_fwd.  *_is_zero: as in ln_conv_fwd / ln_conv_wgrad. */
 int ln_conv_bwd(const float* nbr_values, const int* neighbours_fwd, const float* grad_out, const int* neighbours_bwd,
                 const float* filter, int nv_query, int nv_nbr, int filter_extent, int c_in, int c_out, int precision,
-                float* workspace, float* grad_nbr_values, float* grad_filter, void* stream);
+                float* slabs_bwd, int slabs_prepared, float* grad_nbr_values, int grad_nbr_is_zero, float* grad_filter,
+                int grad_filter_is_zero, void* stream);
 
 /* filter_bw[(slot*c_out + co), ci] = filter[(slot*c_in + ci), co]: the re-layout done with
  * transpose/view/contiguous in lattice_funcs.py:304-311. */
@@ -231,10 +257,12 @@ int ln_scatter_sum_count(const float* src, const int* index, int m, int c, int n
 long long ln_group_norm_workspace_bytes(int nv, int c, int groups);
 int ln_group_norm_fwd(const float* x, const float* gamma, const float* beta, int nv, const int* nv_dev, int c, int groups,
                       float eps, int relu, float* y, float* stats, float* workspace, void* stream);
-/* y = forward output (needed for the ReLU mask when relu != 0).  dgamma/dbeta [c] are overwritten. */
+/* y = forward output (needed for the ReLU mask when relu != 0).  dgamma/dbeta [c] are overwritten.
+ * dx_add (may be NULL): [nv x c] added to dx in the same pass -- the gradient of the skip connection that forked off x
+ * in a residual block (lattice_modules.py:1255-1358), which autograd would otherwise add with a kernel of its own. */
 int ln_group_norm_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* stats,
-                      int nv, const int* nv_dev, int c, int groups, int relu, float* dx, float* dgamma, float* dbeta,
-                      float* workspace, void* stream);
+                      const float* dx_add, int nv, const int* nv_dev, int c, int groups, int relu, float* dx, float* dgamma,
+                      float* dbeta, float* workspace, void* stream);
 
 #ifdef __cplusplus
 }

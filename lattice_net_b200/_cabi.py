@@ -22,15 +22,17 @@ _SIGNATURES = {
     "ln_splat_build": [_P, _P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P],
     "ln_splat_accumulate": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "ln_distribute": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P],
-    "ln_lookup_simplex": [_P, _P, _I, _I, _P, _P, _I, _P, _P, _P],
+    "ln_lookup_simplex": [_P, _P, _I, _I, _P, _P, _I, _I, _P, _P, _P],
     "ln_coarsen_keys": [_P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "ln_neighbour_table": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P],
     "ln_im2row": [_P, _P, _I, _I, _I, _I, _P, _P],
     "ln_im2rowindices": [_P, _I, _I, _I, _I, _P, _P],
     "ln_row2im": [_P, _P, _I, _I, _I, _P, _P],
-    "ln_conv_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
-    "ln_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
-    "ln_conv_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "ln_conv_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P],
+    "ln_filter_prepare": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "ln_filter_prepare_batch": [_P, _I, ctypes.c_longlong, _P],
+    "ln_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "ln_conv_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P],
     "ln_filter_for_dgrad": [_P, _I, _I, _I, _P, _P],
     "ln_slice_fwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "ln_slice_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
@@ -41,13 +43,14 @@ _SIGNATURES = {
     "ln_scatter_max": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "ln_scatter_sum_count": [_P, _P, _I, _I, _I, _P, _P, _P],
     "ln_group_norm_fwd": [_P, _P, _P, _I, _P, _I, _I, ctypes.c_float, _I, _P, _P, _P, _P],
-    "ln_group_norm_bwd": [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P],
+    "ln_group_norm_bwd": [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P],
 }
 _SPECIAL = {
     "ln_version": (ctypes.c_char_p, []),
     "ln_last_error": (ctypes.c_char_p, []),
     "ln_launch_count": (ctypes.c_longlong, []),
     "ln_conv_workspace_bytes": (ctypes.c_longlong, [_I, _I, _I, _I]),
+    "ln_conv_needs_zero": (ctypes.c_int, [_I, _I, _I, _I, _I]),
     "ln_group_norm_workspace_bytes": (ctypes.c_longlong, [_I, _I, _I]),
     "ln_reset_launch_count": (None, []),
 }

@@ -4,6 +4,7 @@
 // floating-point operation whose rounding matters for lattice keys is an explicit intrinsic.
 #pragma once
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 #include "../../include/lattice_b200.h"
 
@@ -37,6 +38,13 @@ constexpr int kLocked = -2;
 __device__ __forceinline__ int ld_relaxed(const int* p) {
     int v;
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// entries[] loads that are FOLLOWED by a read of keys[id]: acquire pairs with the writer's st.release, so the key
+// words are ordered after the id by the memory model and not merely by the address dependency
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release(int* p, int v) {
@@ -90,19 +98,17 @@ __device__ __forceinline__ int table_insert(const TableView& t, const int* key, 
     int h = (int)(hash % (uint32_t)t.capacity);
     for (int probe = 0; probe < t.capacity; probe++) {
         int* e = t.entries + h;
-        int cur = ld_relaxed(e);
+        int cur = ld_acquire(e);
         if (cur == kEmpty) {
             cur = atomicCAS(e, kEmpty, kLocked);
             if (cur == kEmpty) {   // we own the slot: allocate the vertex, publish its key
                 // the vertex counter is ONE address for the whole grid: lanes of this warp that won a slot in the
-                // same probe step share a single atomic (warp-aggregated allocation)
-                const unsigned winners = __activemask();
-                const int lane = threadIdx.x & 31;
-                const int first = __ffs(winners) - 1;
+                // same probe step share a single atomic (warp-aggregated allocation over the coalesced group)
+                const cooperative_groups::coalesced_group winners = cooperative_groups::coalesced_threads();
                 int base = 0;
-                if (lane == first) base = atomicAdd(t.nr_filled, __popc(winners));
-                base = __shfl_sync(winners, base, first);
-                const int id = base + __popc(winners & ((1u << lane) - 1u));
+                if (winners.thread_rank() == 0) base = atomicAdd(t.nr_filled, (int)winners.size());
+                base = winners.shfl(base, 0);
+                const int id = base + (int)winners.thread_rank();
                 if (id >= t.max_vertices) atomicOr(t.status, 2);   // caller's row bound exceeded (static-shape mode)
 #pragma unroll
                 for (int i = 0; i < D; i++) t.keys[(size_t)id * D + i] = key[i];
@@ -112,7 +118,7 @@ __device__ __forceinline__ int table_insert(const TableView& t, const int* key, 
                 return id;
             }
         }
-        while (cur == kLocked) cur = ld_relaxed(e);   // another thread is publishing; short wait
+        while (cur == kLocked) cur = ld_acquire(e);   // another thread is publishing; short wait
         if (key_equal_at<D>(t.keys, cur, key)) return cur;
         h = (h + 1 == t.capacity) ? 0 : h + 1;   // linear probing
     }

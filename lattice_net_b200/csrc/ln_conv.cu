@@ -5,19 +5,21 @@
 // Reference: Lattice::convolve_im2row_standalone (/root/reference/src/Lattice.cu:424-474) =
 // im2row kernel (LatticeGPU.cuh:1464-1688) + cuBLAS SGEMM; backward algebra in
 // /root/reference/latticenet_py/lattice/lattice_funcs.py:294-313.
-#include <cstdlib>
 #include <mutex>
 #include "ln_common.cuh"
 
 namespace ln {
 
 // ln_conv_tc.cu
-int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
-                int F, int c_in, int c_out, int flip, int precision, int transposed, float* workspace, float* out,
-                float* also_zero, long long also_zero_n, cudaStream_t s, cudaEvent_t after_prep);
+int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* slabs, const float* bias, const float* residual, int nv_query,
+                int F, int c_in, int c_out, int flip, int precision, float* out, cudaStream_t s);
+int filter_prepare(const float* filter, int F, int c_in, int c_out, int transposed, int precision, float* slabs, cudaStream_t s);
+int filter_prepare_batch(const void* jobs_device, int n_jobs, long long total_threads, cudaStream_t s);
 size_t conv_tc_workspace_bytes(int F, int c_in, int c_out);
 bool conv_tc_supported(int F, int c_in, int c_out);
+bool conv_tc_needs_zero(int nv_query, int F, int c_in);
 bool conv_wgrad_tc_supported(int F, int c_in, int c_out);
+bool conv_wgrad_tc_needs_zero(int nv_query, int F, int c_in);
 int conv_wgrad_tc(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query, int F, int c_in,
                   int c_out, int precision, float* grad_filter, cudaStream_t s);
 
@@ -27,8 +29,8 @@ constexpr int BM = 64, BN = 64, BK = 16;
 // out[q0:q0+64, n0:n0+64] tile per block, 4x4 outputs per thread, K walked slot by slot.
 __global__ void __launch_bounds__(kThreads)
 conv_fwd_simt_kernel(const float* __restrict__ values, const int* __restrict__ neighbours,
-                     const float* __restrict__ filter, const float* __restrict__ bias, int nv_query, int F, int c_in,
-                     int c_out, int flip, int transposed, float* __restrict__ out) {
+                     const float* __restrict__ filter, const float* __restrict__ bias, const float* __restrict__ residual,
+                     int nv_query, int F, int c_in, int c_out, int flip, int transposed, float* __restrict__ out) {
     __shared__ float a_sh[BK][BM + 4];
     __shared__ float b_sh[BK][BN + 4];
     __shared__ int nbr_sh[BM];
@@ -101,7 +103,8 @@ conv_fwd_simt_kernel(const float* __restrict__ values, const int* __restrict__ n
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int n = n0 + tx * 4 + j;
-            if (n < c_out) out[(size_t)q * c_out + n] = acc[i][j] + (bias ? __ldg(bias + n) : 0.0f);
+            if (n < c_out)
+                out[(size_t)q * c_out + n] = acc[i][j] + (bias ? __ldg(bias + n) : 0.0f) + (residual ? __ldg(residual + (size_t)q * c_out + n) : 0.0f);
         }
     }
 }
@@ -189,67 +192,15 @@ filter_for_dgrad_kernel(const float* __restrict__ filter, int c_in, int c_out, f
 
 using namespace ln;
 
-extern "C" {
-
-long long ln_conv_workspace_bytes(int filter_extent, int c_in, int c_out, int precision) {
-    if (precision == 0 || !conv_tc_supported(filter_extent, c_in, c_out)) return 0;
-    return (long long)conv_tc_workspace_bytes(filter_extent, c_in, c_out);
-}
-
-int ln_conv_fwd(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
-                int filter_extent, int c_in, int c_out, int flip, int transposed_filter, int precision, float* workspace,
-                float* out, void* stream) {
-    LN_REQUIRE(nbr_values && neighbours && filter && out, "ln_conv_fwd: null pointer");
-    LN_REQUIRE(nv_query >= 0 && filter_extent >= 3 && (filter_extent & 1) && c_in >= 1 && c_out >= 1, "ln_conv_fwd: bad size");
-    LN_REQUIRE(precision >= 0 && precision <= 2, "ln_conv_fwd: precision must be 0 (fp32), 1 (3xTF32) or 2 (TF32)");
-    if (nv_query == 0) return LN_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (precision != 0 && conv_tc_supported(filter_extent, c_in, c_out)) {
-        LN_REQUIRE(workspace != nullptr, "ln_conv_fwd: precision %d needs a workspace of ln_conv_workspace_bytes() bytes", precision);
-        return conv_fwd_tc(nbr_values, neighbours, filter, bias, nv_query, filter_extent, c_in, c_out, flip, precision, transposed_filter, workspace, out, nullptr, 0, s, nullptr);
-    }
-    dim3 grid(cdiv(nv_query, BM), cdiv(c_out, BN));
-    conv_fwd_simt_kernel<<<grid, kThreads, 0, s>>>(nbr_values, neighbours, filter, bias, nv_query, filter_extent, c_in, c_out, flip, transposed_filter, out);
-    count_launch();
-    return check_launch("conv_fwd_simt");
-}
-
-static int conv_wgrad_launch(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query,
-                             int filter_extent, int c_in, int c_out, int precision, float* grad_filter, bool already_zero,
-                             cudaStream_t s) {
-    const size_t bytes = (size_t)filter_extent * c_in * c_out * sizeof(float);
-    if (!already_zero && cudaMemsetAsync(grad_filter, 0, bytes, s) != cudaSuccess) return check_launch("conv_wgrad memset");
-    if (nv_query == 0) return LN_OK;
-    if (precision != 0 && conv_wgrad_tc_supported(filter_extent, c_in, c_out))
-        return conv_wgrad_tc(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, precision, grad_filter, s);
-    const int ci_tiles = cdiv(c_in, BM), co_tiles = cdiv(c_out, BN);
-    // enough q-chunks to fill the machine (~4 waves of 148 SMs), at least 256 rows each
-    const int tiles = ci_tiles * co_tiles * filter_extent;
-    int chunks = max(1, min(cdiv(nv_query, 256), cdiv(148 * 4, tiles)));
-    int q_chunk = cdiv(cdiv(nv_query, chunks), BK) * BK;
-    chunks = cdiv(nv_query, q_chunk);
-    dim3 grid(chunks, ci_tiles * co_tiles, filter_extent);
-    conv_wgrad_simt_kernel<<<grid, kThreads, 0, s>>>(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, q_chunk, co_tiles, grad_filter);
-    count_launch();
-    return check_launch("conv_wgrad_simt");
-}
-
-int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query,
-                  int filter_extent, int c_in, int c_out, int precision, float* grad_filter, void* stream) {
-    LN_REQUIRE(nbr_values && neighbours && grad_out && grad_filter, "ln_conv_wgrad: null pointer");
-    LN_REQUIRE(nv_query >= 0 && filter_extent >= 3 && c_in >= 1 && c_out >= 1, "ln_conv_wgrad: bad size");
-    LN_REQUIRE(precision >= 0 && precision <= 2, "ln_conv_wgrad: precision must be 0 (fp32), 1 (3xTF32) or 2 (TF32)");
-    return conv_wgrad_launch(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, precision, grad_filter, false, (cudaStream_t)stream);
-}
-
 // Second stream for the weight gradient: it depends on grad_out and the forward inputs only, never on the data
-// gradient, so ln_conv_bwd runs the two kernels side by side (fork after the filter-prep kernel that clears
-// grad_filter, join before returning).  Inside a CUDA-graph capture the fork/join become graph edges.
+// gradient, so ln_conv_bwd runs the two kernels side by side (fork at entry, join before returning).  Inside a
+// CUDA-graph capture the fork / join become graph edges.
+namespace {
 struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
 };
-static SideStream* side_stream() {
+SideStream* side_stream() {
     static SideStream per_device[64];
     static std::mutex mu;
     int dev = 0;
@@ -267,53 +218,123 @@ static SideStream* side_stream() {
     }
     return &ss;
 }
-static bool fork_enabled() {   // LN_CONV_BWD_FORK=0 keeps both gradients on the caller's stream
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("LN_CONV_BWD_FORK");
-        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+
+int conv_wgrad_launch(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query,
+                      int filter_extent, int c_in, int c_out, int precision, float* grad_filter, bool already_zero,
+                      cudaStream_t s) {
+    const size_t bytes = (size_t)filter_extent * c_in * c_out * sizeof(float);
+    const bool tc = precision != 0 && conv_wgrad_tc_supported(filter_extent, c_in, c_out);
+    const bool needs_zero = nv_query == 0 || !tc || conv_wgrad_tc_needs_zero(nv_query, filter_extent, c_in);
+    if (needs_zero && !already_zero && cudaMemsetAsync(grad_filter, 0, bytes, s) != cudaSuccess) return check_launch("conv_wgrad memset");
+    if (nv_query == 0) return LN_OK;
+    if (tc) return conv_wgrad_tc(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, precision, grad_filter, s);
+    const int ci_tiles = cdiv(c_in, BM), co_tiles = cdiv(c_out, BN);
+    // enough q-chunks to fill the machine (~4 waves of 148 SMs), at least 256 rows each
+    const int tiles = ci_tiles * co_tiles * filter_extent;
+    int chunks = max(1, min(cdiv(nv_query, 256), cdiv(148 * 4, tiles)));
+    int q_chunk = cdiv(cdiv(nv_query, chunks), BK) * BK;
+    chunks = cdiv(nv_query, q_chunk);
+    dim3 grid(chunks, ci_tiles * co_tiles, filter_extent);
+    conv_wgrad_simt_kernel<<<grid, kThreads, 0, s>>>(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, q_chunk, co_tiles, grad_filter);
+    count_launch();
+    return check_launch("conv_wgrad_simt");
+}
+
+// out = conv(values through `neighbours`) [+ bias] [+ residual]; tensor cores when the shape allows and precision != 0
+int conv_launch(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, const float* residual, int nv_query,
+                int filter_extent, int c_in, int c_out, int flip, int transposed_filter, int precision, float* slabs, int slabs_prepared,
+                int out_is_zero, float* out, cudaStream_t s, const char* what) {
+    if (precision != 0 && conv_tc_supported(filter_extent, c_in, c_out)) {
+        if (slabs == nullptr) {
+            set_error("%s: precision %d needs a slab buffer of ln_conv_workspace_bytes() bytes", what, precision);
+            return LN_ERR_BAD_ARG;
+        }
+        if (!slabs_prepared) {
+            const int rc = filter_prepare(filter, filter_extent, c_in, c_out, transposed_filter, precision, slabs, s);
+            if (rc != LN_OK) return rc;
+        }
+        if (!out_is_zero && conv_tc_needs_zero(nv_query, filter_extent, c_in) &&
+            cudaMemsetAsync(out, 0, (size_t)nv_query * c_out * sizeof(float), s) != cudaSuccess)
+            return check_launch("conv memset");
+        return conv_fwd_tc(nbr_values, neighbours, slabs, bias, residual, nv_query, filter_extent, c_in, c_out, flip, precision, out, s);
     }
-    return v == 1;
+    dim3 grid(cdiv(nv_query, BM), cdiv(c_out, BN));
+    conv_fwd_simt_kernel<<<grid, kThreads, 0, s>>>(nbr_values, neighbours, filter, bias, residual, nv_query, filter_extent, c_in, c_out, flip,
+                                                   transposed_filter, out);
+    count_launch();
+    return check_launch(what);
+}
+}  // namespace
+
+extern "C" {
+
+long long ln_conv_workspace_bytes(int filter_extent, int c_in, int c_out, int precision) {
+    if (precision == 0 || !conv_tc_supported(filter_extent, c_in, c_out)) return 0;
+    return (long long)conv_tc_workspace_bytes(filter_extent, c_in, c_out);
+}
+
+int ln_conv_needs_zero(int nv_query, int filter_extent, int c_in, int c_out, int precision) {
+    return (precision != 0 && conv_tc_supported(filter_extent, c_in, c_out) && conv_tc_needs_zero(nv_query, filter_extent, c_in)) ? 1 : 0;
+}
+
+int ln_filter_prepare(const float* filter, int filter_extent, int c_in, int c_out, int transposed_filter, int precision, float* slabs,
+                      void* stream) {
+    LN_REQUIRE(filter && slabs, "ln_filter_prepare: null pointer");
+    LN_REQUIRE(precision == 1 || precision == 2, "ln_filter_prepare: precision must be 1 (3xTF32) or 2 (TF32)");
+    LN_REQUIRE(conv_tc_supported(filter_extent, c_in, c_out), "ln_filter_prepare: shape F=%d c_in=%d c_out=%d does not run on the tensor cores",
+               filter_extent, c_in, c_out);
+    return filter_prepare(filter, filter_extent, c_in, c_out, transposed_filter, precision, slabs, (cudaStream_t)stream);
+}
+
+int ln_filter_prepare_batch(const void* jobs_device, int n_jobs, long long total_threads, void* stream) {
+    LN_REQUIRE(jobs_device != nullptr || n_jobs == 0, "ln_filter_prepare_batch: null pointer");
+    return filter_prepare_batch(jobs_device, n_jobs, total_threads, (cudaStream_t)stream);
+}
+
+int ln_conv_fwd(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, const float* residual,
+                int nv_query, int filter_extent, int c_in, int c_out, int flip, int transposed_filter, int precision, float* slabs,
+                int slabs_prepared, int out_is_zero, float* out, void* stream) {
+    LN_REQUIRE(nbr_values && neighbours && filter && out, "ln_conv_fwd: null pointer");
+    LN_REQUIRE(nv_query >= 0 && filter_extent >= 1 && (filter_extent & 1) && c_in >= 1 && c_out >= 1, "ln_conv_fwd: bad size");
+    LN_REQUIRE(precision >= 0 && precision <= 2, "ln_conv_fwd: precision must be 0 (fp32), 1 (3xTF32) or 2 (TF32)");
+    if (nv_query == 0) return LN_OK;
+    return conv_launch(nbr_values, neighbours, filter, bias, residual, nv_query, filter_extent, c_in, c_out, flip, transposed_filter, precision,
+                       slabs, slabs_prepared, out_is_zero, out, (cudaStream_t)stream, "conv_fwd_simt");
+}
+
+int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query,
+                  int filter_extent, int c_in, int c_out, int precision, int grad_is_zero, float* grad_filter, void* stream) {
+    LN_REQUIRE(nbr_values && neighbours && grad_out && grad_filter, "ln_conv_wgrad: null pointer");
+    LN_REQUIRE(nv_query >= 0 && filter_extent >= 1 && c_in >= 1 && c_out >= 1, "ln_conv_wgrad: bad size");
+    LN_REQUIRE(precision >= 0 && precision <= 2, "ln_conv_wgrad: precision must be 0 (fp32), 1 (3xTF32) or 2 (TF32)");
+    return conv_wgrad_launch(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, precision, grad_filter, grad_is_zero != 0,
+                             (cudaStream_t)stream);
 }
 
 int ln_conv_bwd(const float* nbr_values, const int* neighbours_fwd, const float* grad_out, const int* neighbours_bwd,
                 const float* filter, int nv_query, int nv_nbr, int filter_extent, int c_in, int c_out, int precision,
-                float* workspace, float* grad_nbr_values, float* grad_filter, void* stream) {
+                float* slabs_bwd, int slabs_prepared, float* grad_nbr_values, int grad_nbr_is_zero, float* grad_filter,
+                int grad_filter_is_zero, void* stream) {
     LN_REQUIRE(nbr_values && neighbours_fwd && grad_out && filter, "ln_conv_bwd: null pointer");
-    LN_REQUIRE(nv_query >= 0 && nv_nbr >= 0 && filter_extent >= 3 && c_in >= 1 && c_out >= 1, "ln_conv_bwd: bad size");
+    LN_REQUIRE(nv_query >= 0 && nv_nbr >= 0 && filter_extent >= 1 && c_in >= 1 && c_out >= 1, "ln_conv_bwd: bad size");
     LN_REQUIRE(grad_nbr_values == nullptr || neighbours_bwd != nullptr, "ln_conv_bwd: the data gradient needs the reverse neighbour table");
     cudaStream_t s = (cudaStream_t)stream;
-    bool filter_zeroed = false;
-    const long long nfilt = (long long)filter_extent * c_in * c_out;
-    if (grad_nbr_values && nv_nbr > 0) {
-        // data gradient = flipped convolution of grad_out, evaluated at the neighbour lattice's vertices, with the
-        // forward bank read transposed (c_in <-> c_out)
-        if (precision != 0 && conv_tc_supported(filter_extent, c_out, c_in)) {
-            LN_REQUIRE(workspace != nullptr, "ln_conv_bwd: precision %d needs a workspace", precision);
-            SideStream* ss = (grad_filter != nullptr && nv_query > 0 && fork_enabled()) ? side_stream() : nullptr;
-            const int rc = conv_fwd_tc(grad_out, neighbours_bwd, filter, nullptr, nv_nbr, filter_extent, c_out, c_in, 1, precision, 1,
-                                       workspace, grad_nbr_values, grad_filter, grad_filter ? nfilt : 0, s, ss ? ss->fork : nullptr);
-            if (rc != LN_OK) return rc;
-            filter_zeroed = grad_filter != nullptr;
-            if (ss != nullptr) {
-                if (cudaStreamWaitEvent(ss->stream, ss->fork, 0) != cudaSuccess) return check_launch("conv_bwd fork");
-                const int rw = conv_wgrad_launch(nbr_values, neighbours_fwd, grad_out, nv_query, filter_extent, c_in, c_out, precision,
-                                                 grad_filter, true, ss->stream);
-                if (cudaEventRecord(ss->join, ss->stream) != cudaSuccess || cudaStreamWaitEvent(s, ss->join, 0) != cudaSuccess)
-                    return check_launch("conv_bwd join");
-                return rw;
-            }
-        } else {
-            dim3 grid(cdiv(nv_nbr, BM), cdiv(c_in, BN));
-            conv_fwd_simt_kernel<<<grid, kThreads, 0, s>>>(grad_out, neighbours_bwd, filter, nullptr, nv_nbr, filter_extent, c_out, c_in, 1, 1, grad_nbr_values);
-            count_launch();
-            const int rc = check_launch("conv_dgrad_simt");
-            if (rc != LN_OK) return rc;
-        }
-    }
-    if (grad_filter)
-        return conv_wgrad_launch(nbr_values, neighbours_fwd, grad_out, nv_query, filter_extent, c_in, c_out, precision, grad_filter, filter_zeroed, s);
-    return LN_OK;
+    const bool want_dgrad = grad_nbr_values != nullptr && nv_nbr > 0;
+    // weight gradient on the side stream while the data gradient runs on the caller's
+    SideStream* ss = (want_dgrad && grad_filter != nullptr && nv_query > 0) ? side_stream() : nullptr;
+    if (ss != nullptr && (cudaEventRecord(ss->fork, s) != cudaSuccess || cudaStreamWaitEvent(ss->stream, ss->fork, 0) != cudaSuccess))
+        return check_launch("conv_bwd fork");
+    int rw = LN_OK;
+    if (grad_filter != nullptr)
+        rw = conv_wgrad_launch(nbr_values, neighbours_fwd, grad_out, nv_query, filter_extent, c_in, c_out, precision, grad_filter,
+                               grad_filter_is_zero != 0, ss ? ss->stream : s);
+    int rd = LN_OK;
+    if (want_dgrad)   // flipped convolution of grad_out at the neighbour lattice's vertices, forward bank read transposed (c_in <-> c_out)
+        rd = conv_launch(grad_out, neighbours_bwd, filter, nullptr, nullptr, nv_nbr, filter_extent, c_out, c_in, 1, 1, precision, slabs_bwd,
+                         slabs_prepared, grad_nbr_is_zero, grad_nbr_values, s, "conv_dgrad_simt");
+    if (ss != nullptr && (cudaEventRecord(ss->join, ss->stream) != cudaSuccess || cudaStreamWaitEvent(s, ss->join, 0) != cudaSuccess))
+        return check_launch("conv_bwd join");
+    return rw != LN_OK ? rw : rd;
 }
 
 int ln_filter_for_dgrad(const float* filter, int filter_extent, int c_in, int c_out, float* filter_bw, void* stream) {

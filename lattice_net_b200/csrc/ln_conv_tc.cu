@@ -14,17 +14,20 @@
 //
 // Persistent CTAs (one per SM) walk work items = (M tile, K split); the smem stage ring and the two TMEM
 // accumulator buffers run straight across item boundaries, so the gathers of item i+1 overlap the MMAs of
-// item i and the epilogue of item i-1.  CTA layout (288 threads):
-//   warps 0-3  producers: neighbour rows are gathered with cp.async (LDGSTS, 16 B, zero-fill for absent
-//              neighbours) DIRECTLY into the 128B-swizzled K-major UMMA layout, kLookahead K blocks in
-//              flight per thread; when a block has landed its owner derives the TF32 low part
-//              (x - trunc_tf32(x)) into the second A tile (3xTF32 only), fences the async proxy and
-//              arrives on the stage's "full" barrier.  Thread 0 also launches the bulk-async copy
-//              (UBLKCP) of the pre-swizzled B slab of that stage.
-//   warp 4     TMEM allocation; one lane issues tcgen05.mma / tcgen05.commit
-//   warps 5-8  epilogue: tcgen05.ld (32 columns = one 128-byte line per thread) -> bias -> st.global
+// item i and the epilogue of item i-1.  CTA layout (416 threads):
+//   warps 0-7  producers: neighbour rows are gathered with cp.async (LDGSTS, 16 B, zero-fill for absent
+//              neighbours) DIRECTLY into the 128B-swizzled K-major UMMA layout, `lookahead` K blocks in
+//              flight per thread; when a block has landed its owner derives the TF32 high / low parts
+//              in place (3xTF32 only), fences the async proxy and arrives on the stage's "full" barrier.
+//              Thread 0 also launches the bulk-async copy (UBLKCP) of the pre-swizzled B slab of that stage.
+//   warp 8     TMEM allocation; one lane issues tcgen05.mma / tcgen05.commit
+//   warps 9-12 epilogue: tcgen05.ld (32 columns = one 128-byte line per thread) -> bias / residual -> st.global
 //              (vector fp32 atomics when K is split across CTAs)
-#include <cstdlib>
+//
+// The filter bank reaches the kernel as PREPARED SLABS (filter_prep kernels below): per K block a [n_pad x 128 B]
+// tile of B^T, pre-swizzled, split into TF32 high / low parts.  A bank is prepared once per optimizer step for the
+// forward AND the transposed (data-gradient) reading -- one batched launch for all banks of a model -- instead of
+// once per convolution call.
 #include <mutex>
 #include <set>
 #include <utility>
@@ -32,7 +35,6 @@
 
 namespace ln {
 
-constexpr int kTcThreads = 160;
 constexpr int kTileM = 128;
 constexpr int kBlockK = 32;                 // floats per K block = 128 bytes = one swizzle row
 constexpr int kRowBytes = kBlockK * 4;
@@ -141,11 +143,6 @@ __device__ __forceinline__ float to_tf32(float x) {   // round-to-nearest TF32, 
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-// low part of the TF32 split when the tensor core TRUNCATES the raw fp32 operand: x - (x with 13 low mantissa bits cleared)
-__device__ __forceinline__ float tf32_residual(float x) {
-    return to_tf32(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
-}
-
 // K-major, 128B-swizzled shared-memory matrix descriptor (sm_100 format: version 1, SBO = 8 rows * 128 B)
 __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
     uint64_t desc = 0;
@@ -163,211 +160,80 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
 
 
 // ---- filter preparation ----------------------------------------------------------------------------
-// W [F*c_in x c_out] (row = slot*c_in + ci) -> per K block kb a slab [n_pad rows x 128 B] holding
-// B^T (n-major rows, 32 k-values each) already in the 128B-swizzled order the UMMA descriptor expects:
-// 16-byte chunk j of row n sits at chunk position j ^ (n % 8).  hi = tf32(W), lo = tf32(W - hi).
-__global__ void __launch_bounds__(256)
-filter_prep_kernel(const float* __restrict__ filter, int k_total, int c_in, int c_out, int ld_n, int n_off, int n_pad, int split,
-                   int transposed, float* __restrict__ b_hi, float* __restrict__ b_lo,
-                   float* __restrict__ zero_a, long long n_a, float* __restrict__ zero_b, long long n_b) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    // buffers that later kernels accumulate into with atomics (split-K output, weight gradient) are
-    // cleared here instead of by separate memset launches
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = t; i < n_a; i += stride) zero_a[i] = 0.0f;
-    for (long long i = t; i < n_b; i += stride) zero_b[i] = 0.0f;
-    const long long total = (long long)(k_total / kBlockK) * n_pad * kBlockK;
-    if (t >= total) return;
+// W [F*c_in x c_out] (row = slot*c_in + ci) -> prepared slabs.  The output channels are cut into chunks of kMaxTileN
+// (one UMMA N tile); chunk j (n_off = j*kMaxTileN, n_pad = its width rounded up to 16) owns the floats
+// [2*K*n_off, 2*K*(n_off + n_pad)) of the slab buffer: first the TF32 high parts, K*n_pad floats, then the low parts.
+// Inside a chunk, K block kb is a tile [n_pad rows x 128 B] holding B^T (n-major rows, 32 k-values each) already in the
+// 128B-swizzled order the UMMA descriptor expects: 16-byte unit j of row n sits at unit position j ^ (n % 8).
+//   hi = tf32(W), lo = tf32(W - hi).
+// transposed: `filter` is the FORWARD bank of the convolution whose DATA GRADIENT is being computed, read in place
+// (lattice_funcs.py:304-311 without the copy): this GEMM's K runs over (slot, forward output channel), its N over the
+// forward input channels, so element (slot, k, n) lives at filter[(slot*N + n) * c_in + k] with c_in = this reading's
+// channels per slot (= the forward c_out) and N = this reading's c_out (= the forward c_in).
+constexpr int kMaxTileN = 256;
+
+struct FilterPrepJob {          // one bank; 48 bytes, built on the host (lattice.py packs the same layout)
+    const float* src;
+    float* dst;
+    int k_total;                // GEMM K = F * c_in (of THIS reading)
+    int c_in;                   // channels per filter slot of this reading
+    int c_out;                  // GEMM N
+    int transposed;
+    int split;                  // 1: write the low parts too (3xTF32)
+    int pad_;
+    long long first_thread;     // prefix sum of thread counts over the jobs of a batch
+};
+
+__host__ __device__ __forceinline__ int prep_n_pad_sum(int c_out) {   // padded columns over all chunks
+    const int full = c_out / kMaxTileN, rest = c_out - full * kMaxTileN;
+    return full * kMaxTileN + (rest + 15) / 16 * 16;
+}
+
+__device__ __forceinline__ void filter_prep_element(const FilterPrepJob& j, long long t) {
+    const int n_pad_sum = prep_n_pad_sum(j.c_out);
     const int kk = (int)(t % kBlockK);
     const long long rest = t / kBlockK;
-    const int n = (int)(rest % n_pad);
-    const int kb = (int)(rest / n_pad);
+    const int np = (int)(rest % n_pad_sum);
+    const int kb = (int)(rest / n_pad_sum);
+    const int n_off = np / kMaxTileN * kMaxTileN;
+    const int nl = np - n_off;
+    const int n_pad = min(kMaxTileN, n_pad_sum - n_off);
+    const int n = n_off + nl;
     const int k = kb * kBlockK + kk;
-    // transposed: `filter` is the forward bank [F*ld_n x c_in] of the convolution whose data gradient this is
-    // (element (slot, k, n) lives at [(slot*ld_n + n), k]), lattice_funcs.py:304-311 without the copy.
-    // This launch prepares output channels [n_off, n_off + c_out) of a bank that is ld_n channels wide (N chunking).
     float w = 0.0f;
-    if (n < c_out) {
-        if (transposed) {
-            const int slot = k / c_in, ci = k - slot * c_in;
-            w = __ldg(filter + ((size_t)slot * ld_n + n_off + n) * c_in + ci);
+    if (n < j.c_out) {
+        if (j.transposed) {
+            const int slot = k / j.c_in, ci = k - slot * j.c_in;
+            w = __ldg(j.src + ((size_t)slot * j.c_out + n) * j.c_in + ci);
         } else {
-            w = __ldg(filter + (size_t)k * ld_n + n_off + n);
+            w = __ldg(j.src + (size_t)k * j.c_out + n);
         }
     }
-    const int chunk = kk >> 2, within = kk & 3;
-    const size_t dst = ((size_t)kb * n_pad + n) * kBlockK + (size_t)((chunk ^ (n & 7)) << 2) + within;
+    const int unit = kk >> 2, within = kk & 3;
+    float* hi_base = j.dst + (size_t)2 * j.k_total * n_off;
+    const size_t dst = ((size_t)kb * n_pad + nl) * kBlockK + (size_t)((unit ^ (nl & 7)) << 2) + within;
     const float hi = to_tf32(w);
-    b_hi[dst] = hi;
-    if (split) b_lo[dst] = to_tf32(w - hi);
+    hi_base[dst] = hi;
+    if (j.split) hi_base[(size_t)j.k_total * n_pad + dst] = to_tf32(w - hi);
 }
 
-// ---- main kernel ----------------------------------------------------------------------------------
-template <int kSplit>   // 1: 3xTF32, 0: single pass
-__global__ void __launch_bounds__(kTcThreads, 1)
-conv_fwd_tc_kernel(const float* __restrict__ values, const int* __restrict__ neighbours,
-                   const float* __restrict__ b_hi, const float* __restrict__ b_lo, const float* __restrict__ bias,
-                   int nv_query, int F, int c_in, int c_out, int n_pad, int flip, int stages, int kb_per_split,
-                   float* __restrict__ out) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [stages] x { A_hi, (A_lo), B_hi, (B_lo) } tiles (all multiples of 1024 B), then indices, barriers
-    const uint32_t b_tile_bytes = (uint32_t)n_pad * kRowBytes;
-    const uint32_t stage_bytes = (kSplit ? 2 : 1) * (kATileBytes + b_tile_bytes);
-    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    int* nbr_sh = (int*)(base + (size_t)stages * stage_bytes);                  // [kTileM][F]
-    uint64_t* bars = (uint64_t*)(((uintptr_t)(nbr_sh + kTileM * F) + 15) & ~(uintptr_t)15);
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * stages + 1);
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int q0 = blockIdx.x * kTileM;
-    const uint32_t base_u32 = smem_u32(base);
-    const uint32_t bars_u32 = smem_u32(bars);
-    auto full_bar = [&](int s) { return bars_u32 + 8u * (uint32_t)s; };
-    auto empty_bar = [&](int s) { return bars_u32 + 8u * (uint32_t)(stages + s); };
-    const uint32_t accum_bar = bars_u32 + 8u * (uint32_t)(2 * stages);
-    auto a_hi = [&](int s) { return base_u32 + (uint32_t)s * stage_bytes; };
-    auto a_lo = [&](int s) { return a_hi(s) + kATileBytes; };
-    auto b_hi_s = [&](int s) { return a_hi(s) + (kSplit ? 2 : 1) * kATileBytes; };
-    auto b_lo_s = [&](int s) { return b_hi_s(s) + b_tile_bytes; };
-
-    // neighbour ids of this tile (all slots), coalesced
-    for (int i = tid; i < kTileM * F; i += kTcThreads) {
-        const int q = q0 + i / F;
-        nbr_sh[i] = (q < nv_query) ? __ldg(neighbours + (size_t)q0 * F + i) : -1;
-    }
-    uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < n_pad) tmem_cols <<= 1;
-    if (tid == 0) {
-        for (int s = 0; s < stages; s++) {
-            mbar_init(full_bar(s), 128 + 1);   // 128 producer threads + the expect_tx arrival for B
-            mbar_init(empty_bar(s), 1);        // one tcgen05.commit
-        }
-        mbar_init(accum_bar, 1);
-        fence_barrier_init();
-    }
-    if (warp == 4) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int cpb = c_in / kBlockK;          // K blocks per slot
-    // split-K: blockIdx.y owns K blocks [kb_begin, kb_end); partial tiles are reduced with fp32 atomics
-    // into the pre-zeroed output (small lattices: a 1000-vertex level is only 8 M tiles)
-    const int kb_begin = blockIdx.y * kb_per_split;
-    const int kb_end = min(F * cpb, kb_begin + kb_per_split);
-    const int num_kb = kb_end - kb_begin;
-    const bool split_k = gridDim.y > 1;
-
-    if (warp < 4) {
-        // ================= producers =================
-        const int chunk = tid & 7;
-        const int row0 = tid >> 3;           // rows row0 + 16*i
-        for (int it = 0; it < num_kb; it++) {
-            const int kb = kb_begin + it;
-            const int s = it % stages;
-            const uint32_t ph = (uint32_t)(it / stages) & 1u;
-            mbar_wait(empty_bar(s), ph ^ 1u);
-            if (tid == 0) {
-                mbar_arrive_expect_tx(full_bar(s), (kSplit ? 2u : 1u) * b_tile_bytes);
-                bulk_copy_g2s(b_hi_s(s), b_hi + (size_t)kb * n_pad * kBlockK, b_tile_bytes, full_bar(s));
-                if (kSplit) bulk_copy_g2s(b_lo_s(s), b_lo + (size_t)kb * n_pad * kBlockK, b_tile_bytes, full_bar(s));
-            }
-            const int slot = kb / cpb;
-            const int cb = kb - slot * cpb;
-            const int src_slot = (flip && slot < F - 1) ? (slot ^ 1) : slot;
-            float4 v[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int row = row0 + 16 * i;
-                const int id = nbr_sh[row * F + src_slot];
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (id >= 0) v[i] = __ldg(reinterpret_cast<const float4*>(values + (size_t)id * c_in + cb * kBlockK) + chunk);
-            }
-            uint8_t* a_hi_p = base + (size_t)s * stage_bytes;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int row = row0 + 16 * i;
-                const uint32_t off = (uint32_t)row * kRowBytes + (uint32_t)((chunk ^ (row & 7)) << 4);
-                float4 h = make_float4(to_tf32(v[i].x), to_tf32(v[i].y), to_tf32(v[i].z), to_tf32(v[i].w));
-                *reinterpret_cast<float4*>(a_hi_p + off) = h;
-                if (kSplit) {
-                    float4 l = make_float4(to_tf32(v[i].x - h.x), to_tf32(v[i].y - h.y), to_tf32(v[i].z - h.z), to_tf32(v[i].w - h.w));
-                    *reinterpret_cast<float4*>(a_hi_p + kATileBytes + off) = l;
-                }
-            }
-            fence_proxy_async();             // generic-proxy stores -> visible to the tensor-core (async) proxy
-            mbar_arrive(full_bar(s));
-        }
-        // ================= epilogue =================
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        const int q = q0 + warp * 32 + (tid & 31);
-        float* orow = out + (size_t)q * c_out;
-        for (int n0 = 0; n0 < n_pad; n0 += 16) {
-            float acc[16];
-            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, acc);
-            if (q < nv_query && split_k) {
-#pragma unroll
-                for (int j = 0; j < 16; j++)
-                    if (n0 + j < c_out) atomicAdd(orow + n0 + j, acc[j] + ((bias && blockIdx.y == 0) ? __ldg(bias + n0 + j) : 0.0f));
-            } else if (q < nv_query) {
-                if (n0 + 16 <= c_out && (c_out & 3) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-                        if (bias) {
-                            o.x += __ldg(bias + n0 + j); o.y += __ldg(bias + n0 + j + 1);
-                            o.z += __ldg(bias + n0 + j + 2); o.w += __ldg(bias + n0 + j + 3);
-                        }
-                        *reinterpret_cast<float4*>(orow + n0 + j) = o;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; j++)
-                        if (n0 + j < c_out) orow[n0 + j] = acc[j] + (bias ? __ldg(bias + n0 + j) : 0.0f);
-                }
-            }
-        }
-        tc_fence_before();
-    } else {
-        // ================= MMA issuer (warp 4, one lane) =================
-        if ((tid & 31) == 0) {
-            const uint32_t idesc = umma_idesc_tf32(kTileM, n_pad);
-            for (int kb = 0; kb < num_kb; kb++) {   // kb counts this CTA's K blocks from 0
-                const int s = kb % stages;
-                const uint32_t ph = (uint32_t)(kb / stages) & 1u;
-                mbar_wait(full_bar(s), ph);
-                tc_fence_after();
-                const uint64_t da_hi = umma_desc_kmajor_sw128(a_hi(s));
-                const uint64_t db_hi = umma_desc_kmajor_sw128(b_hi_s(s));
-                const uint64_t da_lo = umma_desc_kmajor_sw128(a_lo(s));
-                const uint64_t db_lo = umma_desc_kmajor_sw128(b_lo_s(s));
-#pragma unroll
-                for (int ks = 0; ks < kBlockK / 8; ks++) {   // UMMA K = 8 tf32 = 32 bytes = 2 x 16-byte units
-                    const uint64_t adv = (uint64_t)(ks * 2);
-                    if (kSplit) {                             // small cross terms first, then the main product
-                        umma_tf32(tmem_base, da_lo + adv, db_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-                        umma_tf32(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
-                        umma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, 1u);
-                    } else {
-                        umma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-                    }
-                }
-                umma_commit(empty_bar(s));   // frees the stage when these MMAs have read it
-            }
-            umma_commit(accum_bar);          // accumulator complete -> epilogue
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-    if (warp == 4) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, tmem_cols);
-    }
+__global__ void __launch_bounds__(256) filter_prep_kernel(FilterPrepJob job) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (long long)job.k_total * prep_n_pad_sum(job.c_out)) filter_prep_element(job, t);
 }
 
+// all banks of a model in ONE launch: jobs[] lives in device memory, sorted by first_thread
+__global__ void __launch_bounds__(256) filter_prep_batch_kernel(const FilterPrepJob* __restrict__ jobs, int n_jobs, long long total) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int lo = 0, hi = n_jobs - 1;              // last job whose first_thread <= t
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&jobs[mid].first_thread) <= t) lo = mid; else hi = mid - 1;
+    }
+    const FilterPrepJob j = jobs[lo];
+    filter_prep_element(j, t - j.first_thread);
+}
 
 // ---- persistent, cp.async-fed kernel (v2) -----------------------------------------------------------
 constexpr int kTc2ProducerWarps = 8;
@@ -391,8 +257,8 @@ template <int kSplit>   // 1: 3xTF32, 0: single pass
 __global__ void __launch_bounds__(kTc2Threads, 1)
 conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighbours,
                 const float* __restrict__ b_hi, const float* __restrict__ b_lo, const float* __restrict__ bias,
-                int nv_query, int F, int c_in, int c_out, int ld_out, int n_pad, int flip, int stages, int lookahead,
-                int m_tiles, int n_items, int kb_per_split, int truncating_operand, float* __restrict__ out) {
+                const float* __restrict__ residual, int nv_query, int F, int c_in, int c_out, int ld_out, int n_pad, int flip,
+                int stages, int lookahead, int m_tiles, int n_items, int kb_per_split, float* __restrict__ out) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t b_tile_bytes = (uint32_t)n_pad * kRowBytes;
     const uint32_t stage_bytes = (kSplit ? 2 : 1) * (kATileBytes + b_tile_bytes);
@@ -469,15 +335,11 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const float4 x = lds128(hi + (uint32_t)i * 32u * kRowBytes);
-                    if (truncating_operand) {     // the tensor core drops the 13 low mantissa bits of the raw fp32 operand itself
-                        sts128(lo + (uint32_t)i * 32u * kRowBytes,
-                               make_float4(tf32_residual(x.x), tf32_residual(x.y), tf32_residual(x.z), tf32_residual(x.w)));
-                    } else {                       // explicit round-to-nearest high part, independent of the operand read-out
-                        const float4 h = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
-                        sts128(hi + (uint32_t)i * 32u * kRowBytes, h);
-                        sts128(lo + (uint32_t)i * 32u * kRowBytes,
-                               make_float4(to_tf32(x.x - h.x), to_tf32(x.y - h.y), to_tf32(x.z - h.z), to_tf32(x.w - h.w)));
-                    }
+                    // explicit round-to-nearest high part, independent of how the tensor core reads a raw fp32 operand
+                    const float4 h = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
+                    sts128(hi + (uint32_t)i * 32u * kRowBytes, h);
+                    sts128(lo + (uint32_t)i * 32u * kRowBytes,
+                           make_float4(to_tf32(x.x - h.x), to_tf32(x.y - h.y), to_tf32(x.z - h.z), to_tf32(x.w - h.w)));
                 }
             }
             fence_proxy_async();             // generic-proxy writes (cp.async data, lo tile) -> visible to the tensor-core proxy
@@ -622,8 +484,9 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
             tc_fence_after();
             const int q = w.q0 + quad * 32 + lane;
             const bool live = q < nv_query;
-            float* orow = out + (size_t)q * ld_out;     // `out` / `bias` already point at this launch's first channel
+            float* orow = out + (size_t)q * ld_out;     // `out` / `bias` / `residual` already point at this launch's first channel
             const bool add_bias = bias != nullptr && w.split == 0;
+            const float* rrow = (residual != nullptr && w.split == 0) ? residual + (size_t)q * ld_out : nullptr;
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * n_pad);
             for (int n0 = 0; n0 < n_pad; n0 += 32) {
                 float acc[32];
@@ -644,6 +507,10 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
                                 o.x += __ldg(bias + n0 + k); o.y += __ldg(bias + n0 + k + 1);
                                 o.z += __ldg(bias + n0 + k + 2); o.w += __ldg(bias + n0 + k + 3);
                             }
+                            if (rrow != nullptr) {
+                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rrow + n0 + k));
+                                o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                            }
                             if (split_k)
                                 atomicAdd(reinterpret_cast<float4*>(orow + n0 + k), o);
                             else
@@ -654,7 +521,7 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
 #pragma unroll
                     for (int k = 0; k < 32; k++) {
                         if (n0 + k < c_out) {
-                            const float o = acc[k] + (add_bias ? __ldg(bias + n0 + k) : 0.0f);
+                            const float o = acc[k] + (add_bias ? __ldg(bias + n0 + k) : 0.0f) + (rrow != nullptr ? __ldg(rrow + n0 + k) : 0.0f);
                             if (split_k)
                                 atomicAdd(orow + n0 + k, o);
                             else
@@ -675,30 +542,20 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
     }
 }
 
+// floats of the prepared slabs of one bank reading (both parts are always reserved, the low half stays unused in
+// single-pass TF32 mode, so a buffer survives a precision change)
 size_t conv_tc_workspace_bytes(int F, int c_in, int c_out) {
-    const int n_pad = (c_out + 15) / 16 * 16;
-    return (size_t)2 * F * c_in * n_pad * sizeof(float);
+    return (size_t)2 * F * c_in * prep_n_pad_sum(c_out) * sizeof(float);
 }
 
 // One launch covers up to kMaxTileN output channels (UMMA N <= 256, two accumulator buffers = all 512 TMEM columns);
 // wider layers (the 384- and 512-channel levels of the SemanticKITTI architecture) run as chunks of kMaxTileN columns.
-constexpr int kMaxTileN = 256;
 constexpr int kMaxCoutTc = 1024;
 
-static int env_int(const char* name, int dflt) {   // development knobs, read on every call (cheap: a few per launch)
-    const char* e = getenv(name);
-    return (e != nullptr && e[0] != 0) ? atoi(e) : dflt;
-}
-static bool use_v1() {   // development switch: LN_CONV_TC_V1=1 selects the first-generation (non-persistent) kernel
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("LN_CONV_TC_V1");
-        v = (e != nullptr && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1;
-}
+// F = 1 with an identity "neighbour" table is a plain row-major GEMM: the 1x1 layers of the bottleneck blocks and of the
+// slice head run through the same kernels (lattice_modules.py:806-832 uses torch.nn.Linear there)
 bool conv_tc_supported(int F, int c_in, int c_out) {
-    return c_in % kBlockK == 0 && c_out >= 1 && c_out <= (use_v1() ? kMaxTileN : kMaxCoutTc) && F >= 3;
+    return c_in % kBlockK == 0 && c_out >= 1 && c_out <= kMaxCoutTc && F >= 1;
 }
 // Opt a kernel into the full 227 KB of dynamic shared memory ONCE per (kernel, device), not per launch: the call is
 // not free on the host, and an attribute change in the middle of a stream capture trips profilers.
@@ -722,6 +579,21 @@ static int sm_count() {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     }
     return n;
+}
+
+int filter_prepare(const float* filter, int F, int c_in, int c_out, int transposed, int precision, float* slabs, cudaStream_t s) {
+    FilterPrepJob job{filter, slabs, F * c_in, c_in, c_out, transposed, precision == 1 ? 1 : 0, 0, 0};
+    const long long total = (long long)job.k_total * prep_n_pad_sum(c_out);
+    filter_prep_kernel<<<cdiv(total, 256), 256, 0, s>>>(job);
+    count_launch();
+    return check_launch("filter_prep");
+}
+
+int filter_prepare_batch(const void* jobs_device, int n_jobs, long long total_threads, cudaStream_t s) {
+    if (n_jobs <= 0 || total_threads <= 0) return LN_OK;
+    filter_prep_batch_kernel<<<cdiv(total_threads, 256), 256, 0, s>>>((const FilterPrepJob*)jobs_device, n_jobs, total_threads);
+    count_launch();
+    return check_launch("filter_prep_batch");
 }
 
 
@@ -960,10 +832,25 @@ conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ n
 }
 
 bool conv_wgrad_tc_supported(int F, int c_in, int c_out) {
-    return c_in % 32 == 0 && c_out % 4 == 0 && c_out >= 4 && c_out <= kMaxCoutTc && F >= 3;
+    return c_in % 32 == 0 && c_out % 4 == 0 && c_out >= 4 && c_out <= kMaxCoutTc && F >= 1;
 }
 
-// grad_filter must be zero when q_splits > 1 (the caller clears it).  Returns the number of vertex-range splits used.
+// K blocks in flight per producer thread = half the ring: a stage published `stages - lookahead` iterations ago has had
+// that long for its MMAs to retire before the producer needs it back (lookahead = stages - 1 serialises the two).
+static inline int lookahead_for(int stages) { return max(1, min(stages - 1, stages / 2)); }
+
+// Vertex-range splits of the weight gradient: enough CTAs for the machine (two waves at most), at least 4 stages of
+// vertices per CTA.
+static int wgrad_q_splits(int nv_query, int F, int c_in) {
+    const int tiles = F * cdiv(c_in, 128);
+    const int total_chunks = cdiv(nv_query, kWgRows);
+    int q_splits = max(1, min(cdiv(total_chunks, 4), (2 * sm_count()) / tiles));
+    const int chunks_per_split = cdiv(total_chunks, q_splits);
+    return cdiv(total_chunks, chunks_per_split);
+}
+bool conv_wgrad_tc_needs_zero(int nv_query, int F, int c_in) { return wgrad_q_splits(nv_query, F, c_in) > 1; }
+
+// grad_filter must be zero when conv_wgrad_tc_needs_zero() (partial sums of vertex ranges are combined with vector atomics).
 static int conv_wgrad_tc_chunk(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query, int F, int c_in,
                                int c_out, int ld_g, int precision, float* grad_filter, cudaStream_t s) {
     const int split = precision == 1 ? 1 : 0;
@@ -972,19 +859,16 @@ static int conv_wgrad_tc_chunk(const float* nbr_values, const int* neighbours, c
     const int ci_tiles = cdiv(c_in, 128);
     const int total_chunks = cdiv(nv_query, kWgRows);
     const int tiles = F * ci_tiles;
-    // enough CTAs for the machine (two waves at most), at least 4 stages of vertices per CTA
-    int q_splits = max(1, min(cdiv(total_chunks, 4), (2 * sm_count()) / tiles));
+    const int q_splits = wgrad_q_splits(nv_query, F, c_in);
     const int chunks_per_split = cdiv(total_chunks, q_splits);
-    q_splits = cdiv(total_chunks, chunks_per_split);
     const size_t stage_bytes = (size_t)(split ? 2 : 1) * (4 + n_groups) * kWgGroupBytes;
     const size_t fixed = (2 * kMaxStages + 1) * 8 + 16 + 1024;
-    int stages = (int)min((size_t)kMaxStages, (227 * 1024 - fixed) / stage_bytes);
+    const int stages = (int)min((size_t)kMaxStages, (227 * 1024 - fixed) / stage_bytes);
     if (stages < 2) {
         set_error("conv_wgrad_tc: tile does not fit shared memory (c_out=%d)", c_out);
         return LN_ERR_UNSUPPORTED;
     }
-    stages = min(stages, max(2, env_int("LN_CONV_STAGES", kMaxStages)));
-    const int lookahead = min(stages - 1, max(1, env_int("LN_CONV_LOOKAHEAD", stages / 2)));   // see conv_fwd_tc
+    const int lookahead = lookahead_for(stages);
     // > half of the SM's shared memory: one CTA per SM (TMEM columns, see conv_tc2)
     const size_t smem = max((size_t)stages * stage_bytes + fixed, (size_t)120 * 1024);
     const int grid = tiles * q_splits;
@@ -1019,114 +903,76 @@ int conv_wgrad_tc(const float* nbr_values, const int* neighbours, const float* g
     return LN_OK;
 }
 
-// One launch pair (filter prep + convolution) for output channels [n_off, n_off + c_out) of a layer that is ld_n wide.
-// `out` / `bias` point at the layer's first channel; `workspace` at this chunk's slabs.  zero_out: clear ALL of `out`
-// (nv_query x ld_n) in the prep kernel when K is split across CTAs (done by the first chunk only).
-static int conv_fwd_tc_chunk(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
-                             int F, int c_in, int c_out, int ld_n, int n_off, bool zero_out, int flip, int precision, int transposed,
-                             float* workspace, float* out, float* also_zero, long long also_zero_n, cudaStream_t s,
-                             cudaEvent_t after_prep) {
+// K splits of the convolution: enough CTAs for the machine when there are few M tiles (148 SMs, one CTA each)
+static int conv_k_splits(int nv_query, int F, int c_in) {
+    const int num_kb = F * (c_in / kBlockK);
+    const int m_tiles = cdiv(nv_query, kTileM);
+    int splits = 1;
+    if (m_tiles < sm_count()) splits = max(1, min(num_kb, sm_count() / m_tiles));
+    const int kb_per_split = cdiv(num_kb, splits);
+    return cdiv(num_kb, kb_per_split);
+}
+// partial tiles of different K ranges are combined with vector atomics: `out` must be zero beforehand
+bool conv_tc_needs_zero(int nv_query, int F, int c_in) { return conv_k_splits(nv_query, F, c_in) > 1; }
+
+// One launch for output channels [n_off, n_off + c_out) of a layer that is ld_n wide.  `out` / `bias` / `residual` point at
+// the layer's first channel; `slabs` at this chunk's prepared filter.
+static int conv_fwd_tc_chunk(const float* nbr_values, const int* neighbours, const float* slabs, const float* bias, const float* residual,
+                             int nv_query, int F, int c_in, int c_out, int ld_n, int n_off, int flip, int precision, float* out,
+                             cudaStream_t s) {
     const int n_pad = (c_out + 15) / 16 * 16;
     const int k_total = F * c_in;
     const int split = precision == 1 ? 1 : 0;
-    float* b_hi = workspace;
-    float* b_lo = workspace + (size_t)k_total * n_pad;
+    const float* b_hi = slabs;
+    const float* b_lo = slabs + (size_t)k_total * n_pad;
     const int num_kb = F * (c_in / kBlockK);
-    // enough CTAs for the machine: split K when there are few M tiles (148 SMs, one CTA each)
     const int m_tiles = cdiv(nv_query, kTileM);
-    int splits = 1;
-    if (m_tiles < 148) splits = max(1, min(num_kb, 148 / m_tiles));
+    const int splits = conv_k_splits(nv_query, F, c_in);
     const int kb_per_split = cdiv(num_kb, splits);
-    splits = cdiv(num_kb, kb_per_split);
-    {
-        const long long total = (long long)k_total * n_pad;
-        filter_prep_kernel<<<cdiv(total, 256), 256, 0, s>>>(filter, k_total, c_in, c_out, ld_n, n_off, n_pad, split, transposed, b_hi, b_lo,
-                                                            out, (splits > 1 && zero_out) ? (long long)nv_query * ld_n : 0, also_zero, also_zero_n);
-        count_launch();
-        if (after_prep != nullptr && cudaEventRecord(after_prep, s) != cudaSuccess) return check_launch("conv_fwd_tc event");
-    }
     const size_t b_tile = (size_t)n_pad * kRowBytes;
     const size_t stage_bytes = (split ? 2 : 1) * (kATileBytes + b_tile);
-    cudaError_t err;
     float* out_chunk = out + n_off;
     const float* bias_chunk = bias != nullptr ? bias + n_off : nullptr;
-    if (!use_v1()) {
-        // persistent kernel: one CTA per SM, items = (M tile, K split)
-        const size_t fixed = (size_t)2 * kTileM * F * sizeof(int) + 16 + (2 * kMaxStages + 4) * 8 + 16 + 1024;
-        int stages = (int)((227 * 1024 - fixed) / stage_bytes);
-        stages = min(stages, kMaxStages);
-        if (stages < 2) {
-            set_error("ln_conv_fwd: tensor-core tile does not fit shared memory (c_out=%d)", c_out);
-            return LN_ERR_UNSUPPORTED;
-        }
-        // K blocks in flight per producer thread.  Half the ring: a stage published `stages - lookahead` iterations ago has
-        // had that long for its MMAs to retire before the producer needs it back (lookahead = stages - 1 serialises the two)
-        stages = min(stages, max(2, env_int("LN_CONV_STAGES", kMaxStages)));
-        const int lookahead = min(stages - 1, max(1, env_int("LN_CONV_LOOKAHEAD", stages / 2)));
-        // > half of the SM's shared memory: exactly one CTA per SM, so the 2*n_pad TMEM columns are always available
-        const size_t smem = max((size_t)stages * stage_bytes + fixed, (size_t)120 * 1024);
-        const int n_items = m_tiles * splits;
-        const int grid = min(n_items, sm_count());
-        if (split) {
-            err = allow_max_smem((const void*)conv_tc2_kernel<1>);
-            if (err == cudaSuccess)
-                conv_tc2_kernel<1><<<grid, kTc2Threads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias_chunk, nv_query, F, c_in, c_out, ld_n, n_pad, flip,
-                                                                    stages, lookahead, m_tiles, n_items, kb_per_split, env_int("LN_CONV_TRUNC", 0), out_chunk);
-        } else {
-            err = allow_max_smem((const void*)conv_tc2_kernel<0>);
-            if (err == cudaSuccess)
-                conv_tc2_kernel<0><<<grid, kTc2Threads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias_chunk, nv_query, F, c_in, c_out, ld_n, n_pad, flip,
-                                                                    stages, lookahead, m_tiles, n_items, kb_per_split, 0, out_chunk);
-        }
-        if (err != cudaSuccess) {
-            set_error("conv_tc2: %s", cudaGetErrorString(err));
-            return LN_ERR_CUDA;
-        }
-        count_launch();
-        return check_launch("conv_tc2");
-    }
-    if (ld_n != c_out) {
-        set_error("ln_conv_fwd: the first-generation kernel (LN_CONV_TC_V1) handles at most %d output channels", kMaxTileN);
-        return LN_ERR_UNSUPPORTED;
-    }
-    const size_t fixed = (size_t)kTileM * F * sizeof(int) + 16 + (2 * 8 + 1) * 8 + 16 + 1024;
-    int stages = (int)((227 * 1024 - fixed) / stage_bytes);
-    stages = min(stages, 8);
-    stages = min(stages, kb_per_split);
-    if (stages < 2 && kb_per_split >= 2) {
+    const float* res_chunk = residual != nullptr ? residual + n_off : nullptr;
+    // persistent kernel: one CTA per SM, items = (M tile, K split)
+    const size_t fixed = (size_t)2 * kTileM * F * sizeof(int) + 16 + (2 * kMaxStages + 4) * 8 + 16 + 1024;
+    const int stages = min((int)((227 * 1024 - fixed) / stage_bytes), kMaxStages);
+    if (stages < 2) {
         set_error("ln_conv_fwd: tensor-core tile does not fit shared memory (c_out=%d)", c_out);
         return LN_ERR_UNSUPPORTED;
     }
-    const size_t smem = (size_t)stages * stage_bytes + fixed;
-    const dim3 grid(m_tiles, splits);
+    const int lookahead = lookahead_for(stages);
+    // > half of the SM's shared memory: exactly one CTA per SM, so the 2*n_pad TMEM columns are always available
+    const size_t smem = max((size_t)stages * stage_bytes + fixed, (size_t)120 * 1024);
+    const int n_items = m_tiles * splits;
+    const int grid = min(n_items, sm_count());
+    cudaError_t err;
     if (split) {
-        err = allow_max_smem((const void*)conv_fwd_tc_kernel<1>);
+        err = allow_max_smem((const void*)conv_tc2_kernel<1>);
         if (err == cudaSuccess)
-            conv_fwd_tc_kernel<1><<<grid, kTcThreads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias, nv_query, F, c_in, c_out, n_pad, flip, stages, kb_per_split, out);
+            conv_tc2_kernel<1><<<grid, kTc2Threads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias_chunk, res_chunk, nv_query, F, c_in, c_out, ld_n,
+                                                                n_pad, flip, stages, lookahead, m_tiles, n_items, kb_per_split, out_chunk);
     } else {
-        err = allow_max_smem((const void*)conv_fwd_tc_kernel<0>);
+        err = allow_max_smem((const void*)conv_tc2_kernel<0>);
         if (err == cudaSuccess)
-            conv_fwd_tc_kernel<0><<<grid, kTcThreads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias, nv_query, F, c_in, c_out, n_pad, flip, stages, kb_per_split, out);
+            conv_tc2_kernel<0><<<grid, kTc2Threads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias_chunk, res_chunk, nv_query, F, c_in, c_out, ld_n,
+                                                                n_pad, flip, stages, lookahead, m_tiles, n_items, kb_per_split, out_chunk);
     }
     if (err != cudaSuccess) {
-        set_error("conv_fwd_tc: %s", cudaGetErrorString(err));
+        set_error("conv_tc2: %s", cudaGetErrorString(err));
         return LN_ERR_CUDA;
     }
     count_launch();
-    return check_launch("conv_fwd_tc");
+    return check_launch("conv_tc2");
 }
 
-// after_prep (optional): recorded on `s` once the first filter-prep kernel (which also clears `also_zero`) is enqueued, so a
-// second stream can start work that depends on the clearing while this stream runs the convolution itself.
-int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, int nv_query,
-                int F, int c_in, int c_out, int flip, int precision, int transposed, float* workspace, float* out,
-                float* also_zero, long long also_zero_n, cudaStream_t s, cudaEvent_t after_prep) {
-    // workspace: chunk j's slabs follow those of the chunks before it (all kMaxTileN wide, so 2 * K * n_off floats)
+// slabs: prepared filter of this reading (filter_prepare / filter_prepare_batch).  `out` must be zero when
+// conv_tc_needs_zero() (the caller clears it or hands over a zeroed buffer).
+int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* slabs, const float* bias, const float* residual, int nv_query,
+                int F, int c_in, int c_out, int flip, int precision, float* out, cudaStream_t s) {
     for (int n_off = 0; n_off < c_out; n_off += kMaxTileN) {
-        const bool first = n_off == 0;
-        const int rc = conv_fwd_tc_chunk(nbr_values, neighbours, filter, bias, nv_query, F, c_in, min(kMaxTileN, c_out - n_off), c_out, n_off,
-                                         first, flip, precision, transposed, workspace + (size_t)2 * F * c_in * n_off, out,
-                                         first ? also_zero : nullptr, first ? also_zero_n : 0, s, first ? after_prep : nullptr);
+        const int rc = conv_fwd_tc_chunk(nbr_values, neighbours, slabs + (size_t)2 * F * c_in * n_off, bias, residual, nv_query, F, c_in,
+                                         min(kMaxTileN, c_out - n_off), c_out, n_off, flip, precision, out, s);
         if (rc != LN_OK) return rc;
     }
     return LN_OK;

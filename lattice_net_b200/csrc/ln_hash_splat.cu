@@ -67,7 +67,7 @@ splat_build_kernel(const float* __restrict__ positions_raw, const float* __restr
             if (valid) {
                 simplex_key<D>(s, r, key[r]);
                 hash[r] = key_hash<D>(key[r]);
-                cur[r] = ld_relaxed(table.entries + (int)(hash[r] % (uint32_t)table.capacity));
+                cur[r] = ld_acquire(table.entries + (int)(hash[r] % (uint32_t)table.capacity));
             }
         }
         int stored[D + 1][D];
@@ -302,10 +302,11 @@ int ln_distribute(const float* positions_raw, const float* sigmas, const float* 
 }
 
 int ln_lookup_simplex(const float* positions_raw, const float* sigmas, int n, int pos_dim, const int* keys,
-                      const int* entries, int capacity, int* indices, float* weights, void* stream) {
+                      const int* entries, int capacity, int max_vertices, int* indices, float* weights, void* stream) {
     LN_REQUIRE(positions_raw && sigmas && keys && entries && indices && weights, "ln_lookup_simplex: null pointer");
     LN_REQUIRE(n >= 0 && capacity > 0, "ln_lookup_simplex: bad size");
-    TableView t{const_cast<int*>(keys), const_cast<int*>(entries), nullptr, nullptr, capacity, capacity};
+    // ids at or past the caller's row bound (static-shape mode after an overflow) come back as -1, never as a row to read
+    TableView t{const_cast<int*>(keys), const_cast<int*>(entries), nullptr, nullptr, capacity, vertex_bound(max_vertices, capacity)};
     switch (pos_dim) {
         case 3: return launch_splat_build<3>(positions_raw, sigmas, nullptr, n, 0, t, indices, weights, nullptr, false, (cudaStream_t)stream);
         case 5: return launch_splat_build<5>(positions_raw, sigmas, nullptr, n, 0, t, indices, weights, nullptr, false, (cudaStream_t)stream);

@@ -84,8 +84,8 @@ group_norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gam
 // dx = rstd * ( dy' gamma - (xhat * ds + db) / m ),  ds = sum dy' gamma xhat, db = sum dy' gamma  (over the group)
 __global__ void __launch_bounds__(kGnThreads)
 group_norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
-                      const float* __restrict__ gamma, const float* __restrict__ stats, int nv_rows,
-                      const int* __restrict__ nv_dev, int c, int cpg, int relu, float* __restrict__ dx,
+                      const float* __restrict__ gamma, const float* __restrict__ stats, const float* __restrict__ dx_add,
+                      int nv_rows, const int* __restrict__ nv_dev, int c, int cpg, int relu, float* __restrict__ dx,
                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
     __shared__ float red[32];
     const int g = blockIdx.x;
@@ -93,7 +93,8 @@ group_norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
     const int nv = nv_dev ? min(nv_rows, __ldg(nv_dev)) : nv_rows;
     for (long long i = (long long)nv * cpg + threadIdx.x; i < (long long)nv_rows * cpg; i += blockDim.x) {
         const long long v = i / cpg;
-        dx[v * c + c0 + (int)(i - v * cpg)] = 0.0f;
+        const long long o = v * c + c0 + (int)(i - v * cpg);
+        dx[o] = dx_add ? __ldg(dx_add + o) : 0.0f;
     }
     const float mean = stats[2 * g], rstd = stats[2 * g + 1];
     const long long m = (long long)nv * cpg;
@@ -126,7 +127,7 @@ group_norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
         float d = __ldg(dy + o);
         if (relu && !(__ldg(y + o) > 0.0f)) d = 0.0f;
         const float xhat = (__ldg(x + o) - mean) * rstd;
-        dx[o] = rstd * (d * __ldg(gamma + c0 + j) - (xhat * ds + db) * inv_m);
+        dx[o] = rstd * (d * __ldg(gamma + c0 + j) - (xhat * ds + db) * inv_m) + (dx_add ? __ldg(dx_add + o) : 0.0f);
     }
 }
 
@@ -259,8 +260,8 @@ group_norm_fwd_small_kernel(const float* __restrict__ x, const float* __restrict
 template <int CPG>
 __global__ void __launch_bounds__(kGnThreads)
 group_norm_bwd_small_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
-                            const float* __restrict__ gamma, const float* __restrict__ stats, int nv_rows,
-                            const int* __restrict__ nv_dev, int c, int relu, float* __restrict__ dx,
+                            const float* __restrict__ gamma, const float* __restrict__ stats, const float* __restrict__ dx_add,
+                            int nv_rows, const int* __restrict__ nv_dev, int c, int relu, float* __restrict__ dx,
                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
     __shared__ float red[32 * 2 * CPG];
     const int g = blockIdx.x;
@@ -316,10 +317,11 @@ group_norm_bwd_small_kernel(const float* __restrict__ dy, const float* __restric
         if (v < nv_rows) {
             float o[CPG];
 #pragma unroll
-            for (int k = 0; k < CPG; k++) {
-                o[k] = 0.0f;
-                if (v < nv) o[k] = rstd * (dr[i][k] * gm[k] - (xh[i][k] * ds + db) * inv_m);
-            }
+            for (int k = 0; k < CPG; k++) o[k] = 0.0f;
+            if (dx_add != nullptr) load_row<CPG>(dx_add + (size_t)v * c + c0, o);   // gradient of the skip connection that forked off x
+#pragma unroll
+            for (int k = 0; k < CPG; k++)
+                if (v < nv) o[k] += rstd * (dr[i][k] * gm[k] - (xh[i][k] * ds + db) * inv_m);
             store_row<CPG>(dx + (size_t)v * c + c0, o);
         }
     }
@@ -602,8 +604,8 @@ gn_tiled_bwd_finalize_kernel(const float* __restrict__ partial_ab, int ctas, int
 __global__ void __launch_bounds__(kGtMaxThreads)
 gn_tiled_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
                           const float* __restrict__ gamma, const float* __restrict__ stats, const float* __restrict__ gstat,
-                          int nv_rows, const int* __restrict__ nv_dev, int c, int cpg, int tpr, int rows_per_cta, int relu,
-                          float* __restrict__ dx) {
+                          const float* __restrict__ dx_add, int nv_rows, const int* __restrict__ nv_dev, int c, int cpg, int tpr,
+                          int rows_per_cta, int relu, float* __restrict__ dx) {
     const int rpp = blockDim.x / tpr;
     const int nv = nv_dev ? min(nv_rows, __ldg(nv_dev)) : nv_rows;
     const int col = threadIdx.x % tpr, rsub = threadIdx.x / tpr;
@@ -626,6 +628,10 @@ gn_tiled_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict_
         const int r = r0 + rsub + i * rpp;
         if (r >= nv_rows) break;
         float o[4] = {0.f, 0.f, 0.f, 0.f};
+        if (dx_add != nullptr) {
+            const float4 a4 = ld4(dx_add + (size_t)r * c + ch);
+            o[0] = a4.x; o[1] = a4.y; o[2] = a4.z; o[3] = a4.w;
+        }
         if (r < nv) {
             const size_t off = (size_t)r * c + ch;
             const float4 d4 = ld4(dy + off), v4 = ld4(x + off);
@@ -641,7 +647,7 @@ gn_tiled_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict_
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const float xhat = (v[k] - mean[k]) * rstd[k];
-                o[k] = rstd[k] * (d[k] * gm[k] - (xhat * ds[k] + db[k]) * inv_m);
+                o[k] += rstd[k] * (d[k] * gm[k] - (xhat * ds[k] + db[k]) * inv_m);
             }
         }
         *reinterpret_cast<float4*>(dx + (size_t)r * c + ch) = make_float4(o[0], o[1], o[2], o[3]);
@@ -696,16 +702,16 @@ int ln_group_norm_fwd(const float* x, const float* gamma, const float* beta, int
     return check_launch("group_norm_fwd");
 }
 
-int ln_group_norm_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* stats, int nv,
-                      const int* nv_dev, int c, int groups, int relu, float* dx, float* dgamma, float* dbeta, float* workspace,
-                      void* stream) {
+int ln_group_norm_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* stats,
+                      const float* dx_add, int nv, const int* nv_dev, int c, int groups, int relu, float* dx, float* dgamma,
+                      float* dbeta, float* workspace, void* stream) {
     LN_REQUIRE(dy && x && gamma && stats && dx && dgamma && dbeta, "ln_group_norm_bwd: null pointer");
     LN_REQUIRE(!relu || y, "ln_group_norm_bwd: the forward output is needed for the ReLU mask");
     LN_REQUIRE(nv >= 1 && c >= 1 && groups >= 1 && c % groups == 0, "ln_group_norm_bwd: bad size");
     const int cpg = c / groups;
     cudaStream_t s = (cudaStream_t)stream;
     if (gn_small_ok(nv, cpg)) {
-#define LN_GN_BWD(CPG) group_norm_bwd_small_kernel<CPG><<<groups, kGnThreads, 0, s>>>(dy, x, y, gamma, stats, nv, nv_dev, c, relu, dx, dgamma, dbeta)
+#define LN_GN_BWD(CPG) group_norm_bwd_small_kernel<CPG><<<groups, kGnThreads, 0, s>>>(dy, x, y, gamma, stats, dx_add, nv, nv_dev, c, relu, dx, dgamma, dbeta)
         switch (cpg) {
             case 1: LN_GN_BWD(1); break;
             case 2: LN_GN_BWD(2); break;
@@ -731,11 +737,11 @@ int ln_group_norm_bwd(const float* dy, const float* x, const float* y, const flo
         }
         const int cpc = cpg >= kGtFinLanes ? cpg : (kGtFinLanes / cpg) * cpg;       // whole groups per CTA
         gn_tiled_bwd_finalize_kernel<<<(c + cpc - 1) / cpc, kGtFinLanes * kGtFinSlices, 0, s>>>(fin_in, fin_rows, c, cpg, cpc, gamma, dgamma, dbeta, gstat);
-        gn_tiled_bwd_apply_kernel<<<p.ctas, p.threads, 0, s>>>(dy, x, y, gamma, stats, gstat, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, relu, dx);
+        gn_tiled_bwd_apply_kernel<<<p.ctas, p.threads, 0, s>>>(dy, x, y, gamma, stats, gstat, dx_add, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, relu, dx);
         count_launch();
         count_launch();
     } else {
-        group_norm_bwd_kernel<<<groups, kGnThreads, 0, s>>>(dy, x, y, gamma, stats, nv, nv_dev, c, cpg, relu, dx, dgamma, dbeta);
+        group_norm_bwd_kernel<<<groups, kGnThreads, 0, s>>>(dy, x, y, gamma, stats, dx_add, nv, nv_dev, c, cpg, relu, dx, dgamma, dbeta);
     }
     count_launch();
     return check_launch("group_norm_bwd");

@@ -5,7 +5,6 @@
 // Layout rule used throughout: lanes run along the channel dimension of one vertex row, so every
 // global access is a contiguous (vectorised where val_dim % 4 == 0) run -- the reference maps one
 // thread to one point and walks channels serially (stride-V across the warp).
-#include <cstdlib>
 #include "ln_common.cuh"
 
 namespace ln {
@@ -96,14 +95,6 @@ static int blocks_per_sm(const void* kernel) {
         nb = 4;
     }
     return nb;
-}
-static bool slice_classify_v1() {   // development switch: LN_SLICE_CLASSIFY_V1=1 selects the warp-per-point scalar kernels
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("LN_SLICE_CLASSIFY_V1");
-        v = (e != nullptr && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1;
 }
 static int device_sms() {
     static int n = 0;
@@ -844,7 +835,7 @@ int ln_slice_classify_fwd(const float* lattice_values, const int* indices, const
     cudaStream_t s = (cudaStream_t)stream;
     {
         const size_t smem_t = ((size_t)nr_classes * val_dim + (size_t)kScfPoints * (val_dim + 4)) * sizeof(float);
-        if (val_dim % 4 == 0 && (pos_dim == 3 || pos_dim == 5) && smem_t <= 200 * 1024 && !slice_classify_v1()) {
+        if (val_dim % 4 == 0 && (pos_dim == 3 || pos_dim == 5) && smem_t <= 200 * 1024) {
             // as many CTAs as stay resident (ncu r01s: with 2 per SM the kernel sat at 25 % occupancy, latency-bound);
             // the tile loop is grid-stride, so the grid size only affects scheduling
             const void* kern = pos_dim == 3 ? (const void*)slice_classify_fwd_tiled_kernel<4> : (const void*)slice_classify_fwd_tiled_kernel<6>;
@@ -913,7 +904,7 @@ int ln_slice_classify_bwd(const float* grad_logits, const float* lattice_values,
     cudaStream_t s = (cudaStream_t)stream;
     const size_t smem = ((size_t)nr_classes * val_dim + (size_t)kTile * val_dim + (size_t)kTile * nr_classes) * sizeof(float);
     const int grid = min(cdiv(n, kTile), 148 * 2);
-    if (val_dim % 4 == 0 && (pos_dim == 3 || pos_dim == 5) && !slice_classify_v1()) {
+    if (val_dim % 4 == 0 && (pos_dim == 3 || pos_dim == 5)) {
 #define LN_LAUNCH_SCBV(KV4, SPV)                                                                                   \
     do {                                                                                                           \
         cudaError_t err = smem > 48 * 1024 ? allow_max_smem((const void*)slice_classify_bwd_vec_kernel<KV4, SPV>) : cudaSuccess; \

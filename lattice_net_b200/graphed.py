@@ -16,6 +16,7 @@ re-run that cloud through the ordinary (dynamic-shape) path.
 import torch
 import torch.distributed as dist
 
+from . import lattice as _lattice
 from .lattice import Lattice
 
 
@@ -69,14 +70,22 @@ class GraphedTrainStep:
         self.capture_collective = capture_collective and world > 1
         self.graphs = []
         self.launches_per_step = 0
+        # zeroed outputs of the split-K convolutions: one buffer, one memset per step (sized by a dry run in _capture)
+        self.arena = _lattice.ZeroArena(0, None)
         self._capture(warmup)
 
     # -- the three phases of a step; `_allreduce` is the only part that may have to stay outside a graph
     def _forward_backward(self):
-        logsoftmax, _ = self.model(self.lattice, self.pos, self.vals)
-        loss = self.loss_fn(logsoftmax, self.labels)
-        self.bucket.zero()
-        loss.backward()
+        self.arena.reset()                       # one memset for every output a split-K convolution accumulates into
+        self.bucket.begin_direct_step()          # one memset for every weight gradient; .grad <- None
+        prev = _lattice.set_zero_arena(self.arena)
+        try:
+            logsoftmax, _ = self.model(self.lattice, self.pos, self.vals)
+            loss = self.loss_fn(logsoftmax, self.labels)
+            loss.backward()
+        finally:
+            _lattice.set_zero_arena(prev)
+            self.bucket.end_direct_step()
         self.loss.copy_(loss.detach())
         levels = self.model.last_level_lattices
         flags = torch.stack([l.m_hash_table.structure.status[0] for l in levels]).max()
@@ -124,6 +133,8 @@ class GraphedTrainStep:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
+            self._eager_step()                  # dry run of the arena: counts the floats the step asks for
+            self.arena = _lattice.ZeroArena(self.arena.requested + 1024, self.device)
             for _ in range(max(warmup, 1)):     # lazy initialisations (cuBLAS handles, workspaces, optimizer state)
                 self._eager_step()
         torch.cuda.current_stream(self.device).wait_stream(side)

@@ -26,8 +26,9 @@ from . import _cabi
 from ._cabi import call, ptr, stream_ptr
 from .params import lattice_settings, parse_cfg
 
-# conv arithmetic: 0 = exact fp32 (CUDA cores), 1 = tcgen05 3xTF32 (fp32-equivalent), 2 = tcgen05 TF32
-CONV_PRECISION = 0
+# conv arithmetic: 1 = tcgen05 3xTF32 error-compensated split (fp32-equivalent, the default), 2 = tcgen05 single-pass TF32,
+# 0 = exact fp32 FMA on the CUDA cores (opt-in; also what layers with c_in % 32 != 0 run whatever the mode)
+CONV_PRECISION = 1
 
 
 def set_conv_precision(mode):
@@ -36,21 +37,180 @@ def set_conv_precision(mode):
     CONV_PRECISION = mode
 
 
-_workspaces = {}
 _SIGMA_CACHE = {}
+_IDENTITY_TABLES = {}
 
 
-def _workspace(nbytes, device):
-    """Grow-only scratch per device for the re-laid-out filter of the tensor-core convolution.  Kernels on
-    one stream run in order, so consecutive convolutions can share it."""
-    if nbytes <= 0:
-        return None
+# ---- prepared filters --------------------------------------------------------------------------------------------
+# The tensor-core convolution reads a filter bank as PREPARED SLABS (pre-swizzled B tiles, TF32 high / low parts,
+# csrc/ln_conv_tc.cu).  Weights change once per optimizer step, so the slabs of every bank -- its forward reading and
+# its transposed reading for the data gradient -- are produced by ONE batched launch per step (`prepare_filters`)
+# instead of by one kernel per convolution call.  A reading = (tensor, filter_extent, c_in, c_out, transposed) in the
+# GEMM's own terms: K = filter_extent * c_in, N = c_out.
+class _PreparedReading:
+    __slots__ = ("slabs", "version", "precision", "dims")
+
+    def __init__(self, slabs, dims):
+        self.slabs, self.dims = slabs, dims
+        self.version, self.precision = -1, -1
+
+
+_PREPARED = {}          # (data_ptr, transposed) -> _PreparedReading
+_JOB_TABLES = {}        # signature of a batch -> (device job table, n_jobs, total_threads)
+_SCRATCH = {}           # (device index, stream) -> grow-only slab buffer for banks nobody prepared ahead of time
+
+
+def _n_pad_sum(c_out):
+    full, rest = divmod(int(c_out), 256)
+    return full * 256 + (rest + 15) // 16 * 16
+
+
+def _slab_floats(F, c_in, c_out):
+    return 2 * F * c_in * _n_pad_sum(c_out)          # == ln_conv_workspace_bytes() / 4
+
+
+def tensor_core_reading_ok(F, c_in, c_out):
+    return CONV_PRECISION != 0 and c_in % 32 == 0 and 1 <= c_out <= 1024 and F >= 1     # conv_tc_supported(), ln_conv_tc.cu
+
+
+def prepare_filters(readings):
+    """readings: iterable of (tensor, filter_extent, c_in, c_out, transposed).  Prepares the tensor-core slabs of all of
+    them in one launch (skipped entirely when every reading is current); shapes that do not run on the tensor cores are
+    ignored.  Call it after the weights changed and before the convolutions that use them (LNN.forward and
+    GraphedTrainStep do)."""
+    import struct
+    todo = []
+    stale = False
+    for t, F, c_in, c_out, transposed in readings:
+        if not tensor_core_reading_ok(F, c_in, c_out) or not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            continue
+        key = (t.data_ptr(), bool(transposed))
+        dims = (int(F), int(c_in), int(c_out))
+        entry = _PREPARED.get(key)
+        if entry is None or entry.dims != dims or entry.slabs.device != t.device:
+            entry = _PREPARED[key] = _PreparedReading(torch.empty((_slab_floats(*dims),), dtype=torch.float32, device=t.device), dims)
+        if entry.version != t._version or entry.precision != CONV_PRECISION:
+            stale = True
+        todo.append((t, entry, key))
+    if not todo or not (stale or torch.cuda.is_current_stream_capturing()):
+        return 0
+    device = todo[0][0].device
+    sig = (CONV_PRECISION,) + tuple((k, e.dims, e.slabs.data_ptr()) for _, e, k in todo)
+    table = _JOB_TABLES.get(sig)
+    if table is None:
+        blob, first = b"", 0
+        for t, e, (ptr_, transposed) in todo:
+            F, c_in, c_out = e.dims
+            blob += struct.pack("<QQiiiiiiq", t.data_ptr(), e.slabs.data_ptr(), F * c_in, c_in, c_out, 1 if transposed else 0,
+                                1 if CONV_PRECISION == 1 else 0, 0, first)
+            first += F * c_in * _n_pad_sum(c_out)
+        host = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+        if len(_JOB_TABLES) > 64:
+            _JOB_TABLES.clear()
+        table = _JOB_TABLES[sig] = (host.to(device), len(todo), first)
+    call("ln_filter_prepare_batch", ptr(table[0]), table[1], table[2], stream_ptr(device))
+    for t, e, _ in todo:
+        e.version, e.precision = t._version, CONV_PRECISION
+    return len(todo)
+
+
+def invalidate_prepared_filters():
+    """Forget every prepared bank (needed only after writing to a weight through an alias that does not bump the
+    tensor's version counter, e.g. `w.data`)."""
+    _PREPARED.clear()
+    _JOB_TABLES.clear()
+
+
+def _slabs_for(filter_bank, F, c_in, c_out, transposed):
+    """-> (slab tensor or None, prepared flag) for one convolution call."""
+    if not tensor_core_reading_ok(F, c_in, c_out):
+        return None, 0
+    entry = _PREPARED.get((filter_bank.data_ptr(), bool(transposed)))
+    if (entry is not None and entry.version == filter_bank._version and entry.precision == CONV_PRECISION
+            and entry.dims == (F, c_in, c_out) and entry.slabs.device == filter_bank.device):
+        return entry.slabs, 1
+    device = filter_bank.device
     key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr(device))
-    ws = _workspaces.get(key)
-    if ws is None or ws.numel() * 4 < nbytes:
-        ws = torch.empty((max(nbytes // 4, 1 << 20),), dtype=torch.float32, device=device)
-        _workspaces[key] = ws
-    return ws
+    ws = _SCRATCH.get(key)
+    need = _slab_floats(F, c_in, c_out)
+    if ws is None or ws.numel() < need:
+        ws = _SCRATCH[key] = torch.empty((max(need, 1 << 20),), dtype=torch.float32, device=device)
+    return ws, 0
+
+
+# ---- zeroed output arena --------------------------------------------------------------------------------------------
+# On small lattices the convolution splits K across CTAs and combines the partial tiles with vector reductions, so its
+# output must start at zero.  Inside a captured training step all such outputs are carved out of ONE buffer that a single
+# memset clears at the start of the step (instead of one clearing launch per convolution).
+class ZeroArena:
+    def __init__(self, nr_floats, device):
+        self.buf = torch.empty((max(int(nr_floats), 4),), dtype=torch.float32, device=device) if device is not None else None
+        self.off = 0
+        self.requested = 0          # floats asked for since the last reset (also counted when the arena is a dry run)
+
+    def reset(self):
+        if self.buf is not None:
+            self.buf.zero_()
+        self.off = self.requested = 0
+
+    def take(self, rows, cols, device):
+        n = rows * cols
+        n_al = (n + 3) // 4 * 4      # 16-byte aligned rows for the vector reductions
+        self.requested += n_al
+        if self.buf is None or self.buf.device != device or self.off + n_al > self.buf.numel():
+            return torch.zeros((rows, cols), dtype=torch.float32, device=device)
+        out = self.buf[self.off:self.off + n].view(rows, cols)
+        self.off += n_al
+        return out
+
+
+_ARENA = None
+
+
+def set_zero_arena(arena):
+    """Install (or with None remove) the arena `_zeroed` draws from; returns the previous one."""
+    global _ARENA
+    prev, _ARENA = _ARENA, arena
+    return prev
+
+
+def _zeroed(rows, cols, device):
+    if _ARENA is not None:
+        return _ARENA.take(rows, cols, device)
+    return torch.zeros((rows, cols), dtype=torch.float32, device=device)
+
+
+# ---- gradient targets --------------------------------------------------------------------------------------------
+# parallel.GradBucket registers, per parameter, the slice of its flat gradient buffer; the backward passes of the lattice
+# operators then write the weight gradients straight into those slices (cleared once per step by one memset) and hand
+# autograd a fresh view of the slice, which it adopts as `.grad` without a copy.
+_GRAD_TARGETS = {}      # data_ptr of the parameter -> (flat buffer, offset, shape)
+_GRAD_TARGETS_ACTIVE = False
+
+
+def register_grad_targets(targets):
+    _GRAD_TARGETS.clear()
+    _GRAD_TARGETS.update(targets)
+
+
+def set_grad_targets_active(flag):
+    global _GRAD_TARGETS_ACTIVE
+    _GRAD_TARGETS_ACTIVE = bool(flag)
+
+
+def grad_target(param):
+    """A fresh view of the gradient-bucket slice of `param` (None when no zeroed bucket is active this step)."""
+    if not _GRAD_TARGETS_ACTIVE:
+        return None
+    hit = _GRAD_TARGETS.get(param.data_ptr())
+    if hit is None or tuple(hit[2]) != tuple(param.shape):
+        return None
+    flat, off, shape = hit
+    return flat[off:off + param.numel()].view(shape)
+
+
+def _conv_needs_zero(nv, F, c_in, c_out):
+    return bool(_cabi.load().ln_conv_needs_zero(int(nv), int(F), int(c_in), int(c_out), int(CONV_PRECISION)))
 
 
 def _check(cond, msg):
@@ -59,10 +219,93 @@ def _check(cond, msg):
         raise RuntimeError(msg)
 
 
+def _check_dev_tensor(t, dtype, device, what):
+    # the kernels reinterpret raw pointers: a wrong dtype / device must fail here, as data_ptr<int>() / data_ptr<float>()
+    # do in the reference (Lattice.cu:751-787)
+    if t.dtype != dtype:
+        raise RuntimeError(f"{what} should be of type {dtype}, got {t.dtype}")
+    if not t.is_cuda or (device is not None and t.device != device):
+        raise RuntimeError(f"{what} should live on {device}, got {t.device}")
+
+
 def _as_cuda_f32(t, device):
     if t.dtype != torch.float32:
         raise RuntimeError(f"expected a float32 tensor, got {t.dtype}")
     return t.to(device).contiguous()
+
+
+def _conv_call(vals, table, fb, bias, residual, nv, F, c_in, c_out, flip, transposed):
+    """One ln_conv_fwd call: picks up the prepared slabs of `fb` when there are any, a zeroed output where the kernel
+    accumulates, and returns out [nv x c_out]."""
+    dev = vals.device
+    slabs, prepared = _slabs_for(fb, F, c_in, c_out, transposed)
+    needs_zero = slabs is not None and _conv_needs_zero(nv, F, c_in, c_out)
+    out = _zeroed(nv, c_out, dev) if needs_zero else torch.empty((nv, c_out), dtype=torch.float32, device=dev)
+    if residual is not None:
+        _check(tuple(residual.shape) == (nv, c_out) and residual.is_contiguous(), "residual should be a contiguous [nv x nr_filters] tensor")
+        _check_dev_tensor(residual, torch.float32, dev, "residual")
+    if bias is not None:
+        _check_dev_tensor(bias, torch.float32, dev, "bias")
+    call("ln_conv_fwd", ptr(vals), ptr(table), ptr(fb), ptr(bias), ptr(residual), nv, F, c_in, c_out, 1 if flip else 0,
+         1 if transposed else 0, CONV_PRECISION, ptr(slabs), prepared, 1 if needs_zero else 0, ptr(out), stream_ptr(dev))
+    return out
+
+
+def _conv_bwd_call(nbr_vals, table_fwd, g, table_bwd, fb, nv_q, nv_n, F, c_in, c_out, fb_is_linear_weight, grad_param=None):
+    """One ln_conv_bwd call -> (grad of the neighbour values or None, grad of the bank).  fb_is_linear_weight: `fb` is a
+    torch.nn.Linear weight [c_out x c_in] (F = 1), i.e. the bank stored transposed.  grad_param: the parameter whose gradient
+    the bank gradient IS (same layout); its gradient-bucket slice is written directly when one is active."""
+    dev = g.device
+    grad_in = None
+    slabs, prepared, in_zero = None, 0, 0
+    if table_bwd is not None:
+        # the data gradient reads the bank transposed; for a Linear weight (stored transposed) that is the plain reading
+        slabs, prepared = _slabs_for(fb, F, c_out, c_in, not fb_is_linear_weight)
+        in_zero = 1 if (slabs is not None and _conv_needs_zero(nv_n, F, c_out, c_in)) else 0
+        grad_in = _zeroed(nv_n, c_in, dev) if in_zero else torch.empty((nv_n, c_in), dtype=torch.float32, device=dev)
+    target = grad_target(grad_param) if grad_param is not None else None
+    if fb_is_linear_weight:
+        # dW [c_out x c_in] = G^T X is the weight gradient of the transposed problem: swap the roles of X and G
+        _check(F == 1, "a Linear weight is a filter bank of extent 1")
+        grad_filter = target if target is not None else torch.empty((c_out, c_in), dtype=torch.float32, device=dev)
+        if grad_in is not None:
+            call("ln_conv_fwd", ptr(g), ptr(table_bwd), ptr(fb), None, None, nv_n, 1, c_out, c_in, 0, 0, CONV_PRECISION, ptr(slabs), prepared,
+                 in_zero, ptr(grad_in), stream_ptr(dev))
+        call("ln_conv_wgrad", ptr(g), ptr(table_fwd), ptr(nbr_vals), nv_q, 1, c_out, c_in, CONV_PRECISION, 1 if target is not None else 0,
+             ptr(grad_filter), stream_ptr(dev))
+        return grad_in, grad_filter
+    grad_filter = target if target is not None else torch.empty((F * c_in, c_out), dtype=torch.float32, device=dev)
+    call("ln_conv_bwd", ptr(nbr_vals), ptr(table_fwd), ptr(g), ptr(table_bwd), ptr(fb), nv_q, nv_n, F, c_in, c_out, CONV_PRECISION,
+         ptr(slabs), prepared, ptr(grad_in), in_zero, ptr(grad_filter), 1 if target is not None else 0, stream_ptr(dev))
+    return grad_in, grad_filter
+
+
+def identity_table(nv, device):
+    """[nv x 1] int32 table q -> q: with it the convolution kernels are a plain row-major GEMM (filter extent 1)."""
+    key = (str(device), int(nv))
+    t = _IDENTITY_TABLES.get(key)
+    if t is None:
+        if len(_IDENTITY_TABLES) > 256:
+            _IDENTITY_TABLES.clear()
+        t = _IDENTITY_TABLES[key] = torch.arange(nv, dtype=torch.int32, device=device).view(nv, 1)
+    return t
+
+
+def linear_forward(x, weight, bias=None, residual=None):
+    """y = x W^T (+ bias) (+ residual) through the lattice-convolution kernels with filter extent 1 (tcgen05 when
+    in_features % 32 == 0).  weight: torch.nn.Linear layout [out_features x in_features]."""
+    m, k = x.shape
+    n = int(weight.shape[0])
+    return _conv_call(x.contiguous(), identity_table(m, x.device), weight, bias, residual, m, 1, k, n, False, True)
+
+
+def linear_backward(x, weight, grad_out, need_input_grad=True, grad_param=None):
+    """-> (dx = dy W or None, dW = dy^T x) with the data-gradient and weight-gradient kernels of the convolution."""
+    m, k = x.shape
+    n = int(weight.shape[0])
+    table = identity_table(m, x.device)
+    return _conv_bwd_call(x.contiguous(), table, grad_out.contiguous(), table if need_input_grad else None, weight, m, m, 1, k, n, True,
+                          grad_param)
 
 
 class _Structure:
@@ -85,6 +328,7 @@ class _Structure:
         self.nv = None            # host copy of nr_filled, None = dirty
         self.max_probe = 0
         self.neighbour_cache = {}
+        self.version = 0          # bumped whenever the key set may have changed; neighbour tables INTO this structure record it
         self.clear()
 
     def clear(self):
@@ -94,6 +338,7 @@ class _Structure:
     def mark_dirty(self):
         self.nv = self.bound          # None = unknown until read back; a bound is known without asking the device
         self.neighbour_cache.clear()
+        self.version += 1             # invalidates the tables OTHER structures hold into this one (checked on lookup)
 
     def nr_vertices_actual(self):
         """Blocking read of the device-side vertex count (raises on table overflow / exceeded bound)."""
@@ -119,7 +364,7 @@ class _Structure:
         other.entries = self.entries.clone()
         other.nr_filled = self.nr_filled.clone()
         other.status = self.status.clone()
-        other.nv, other.max_probe, other.neighbour_cache = self.nv, self.max_probe, {}
+        other.nv, other.max_probe, other.neighbour_cache, other.version = self.nv, self.max_probe, {}, 0
         return other
 
 
@@ -352,7 +597,9 @@ class Lattice:
                f"query lvl {self.m_lvl} and neighbour lvl {lattice_neighbours.m_lvl} may differ by one at most")   # Lattice.cu:442
         key = (id(n), int(dilation), self.m_lvl - lattice_neighbours.m_lvl)
         hit = q.neighbour_cache.get(key)
-        if hit is not None and hit[0]() is n:   # weak reference: no cycles between lattice levels
+        # weak reference: no cycles between lattice levels; the neighbour's version: it may have been cleared,
+        # re-splatted or grown in place since the table was built (the reference re-walks the hash table every call)
+        if hit is not None and hit[0]() is n and hit[2] == n.version:
             return hit[1]
         nv = q.nr_vertices()
         _check(nv != 0, "why does this lattice have zero vertices?")   # Lattice.cu:443
@@ -362,7 +609,7 @@ class Lattice:
         call("ln_neighbour_table", ptr(q.keys), nv, ptr(q.nr_filled) if q.bound is not None else None, q.pos_dim,
              ptr(n.keys), ptr(n.entries), n.capacity, n.bound or 0,
              self.m_lvl - lattice_neighbours.m_lvl, int(dilation), ptr(table), stream_ptr(q.device))
-        q.neighbour_cache[key] = (weakref.ref(n), table)
+        q.neighbour_cache[key] = (weakref.ref(n), table, n.version)
         return table
 
     # ---- splat / distribute -----------------------------------------------------------------------
@@ -529,11 +776,12 @@ class Lattice:
 
     # ---- convolution -----------------------------------------------------------------------------
     def convolve_im2row_standalone(self, filter_bank, dilation, lattice_neighbours=None, flip_neighbours=False, bias=None,
-                                   transposed_filter=False):
+                                   transposed_filter=False, residual=None):
         """values_new[nv_self x nr_filters] = im2row(lattice_neighbours) . filter_bank, as one implicit-GEMM
         kernel (Lattice.cu:424-474).  Returns a new handle sharing this lattice's structure.
         transposed_filter (extension): filter_bank is the forward bank [F*nr_filters x val_dim] of the convolution
-        whose data gradient this call computes; it is read transposed in place (lattice_funcs.py:304-311)."""
+        whose data gradient this call computes; it is read transposed in place (lattice_funcs.py:304-311).
+        bias / residual (extensions): added in the kernel's epilogue."""
         nbrs = self if lattice_neighbours is None else lattice_neighbours
         _check(filter_bank is not None and filter_bank.dim() == 2, "filter bank should be 2-D: (filter_extent*val_dim) x nr_filters")
         st = self._structure()
@@ -553,23 +801,13 @@ class Lattice:
         vals = nbrs.values()
         _check(vals.shape[0] >= nbrs.nr_lattice_vertices(), "neighbour lattice values have fewer rows than vertices")
         fb = _as_cuda_f32(filter_bank, st.device)
-        out = torch.empty((nv, nr_filters), dtype=torch.float32, device=st.device)
-        workspace = _workspace(self._conv_ws_bytes(F, vn, nr_filters), st.device)
-        call("ln_conv_fwd", ptr(vals.contiguous()), ptr(table), ptr(fb), ptr(bias), nv, F, vn, nr_filters,
-             1 if flip_neighbours else 0, 1 if transposed_filter else 0, CONV_PRECISION, ptr(workspace), ptr(out),
-             stream_ptr(st.device))
+        out = _conv_call(vals.contiguous(), table, fb, bias, residual, nv, F, vn, nr_filters, flip_neighbours, transposed_filter)
         new = self.clone_lattice()
         new.m_name = "convolved_lattice"
         new.m_hash_table.set_values(out)
         return new
 
-    @staticmethod
-    def _conv_ws_bytes(F, c_in, c_out):
-        if CONV_PRECISION == 0 or c_in % 32 != 0 or c_out > 1024:     # conv_tc_supported(), ln_conv_tc.cu
-            return 0
-        return 2 * F * c_in * ((c_out + 15) // 16 * 16) * 4      # == ln_conv_workspace_bytes()
-
-    def conv_backward(self, lattice_neighbours, grad_values, filter_bank, dilation, need_input_grad=True):
+    def conv_backward(self, lattice_neighbours, grad_values, filter_bank, dilation, need_input_grad=True, grad_param=None):
         """Backward of `out = self.convolve_im2row_standalone(filter_bank, dilation, lattice_neighbours)`:
         returns (grad w.r.t. lattice_neighbours.values(), grad w.r.t. filter_bank) from one C call
         (lattice_funcs.py:294-313 / 373-388 / 438-454 do it with two im2row buffers and three GEMMs)."""
@@ -580,19 +818,11 @@ class Lattice:
         vn = nbrs.val_dim()
         g = _as_cuda_f32(grad_values, st.device)
         _check(g.shape[0] == nv_q, "grad_values rows must match the query lattice")
-        c_out = int(g.shape[1])
         F = self.get_filter_extent(1)
         fb = _as_cuda_f32(filter_bank, st.device)
-        _check(tuple(fb.shape) == (F * vn, c_out), f"filter bank should be [{F * vn} x {c_out}], got {tuple(fb.shape)}")
-        grad_filter = torch.empty((F * vn, c_out), dtype=torch.float32, device=st.device)
-        grad_in = table_bwd = None
-        if need_input_grad:
-            table_bwd = nbrs._neighbour_table(self, dilation)
-            grad_in = torch.empty((nv_n, vn), dtype=torch.float32, device=st.device)
-        workspace = _workspace(self._conv_ws_bytes(F, c_out, vn), st.device)
-        call("ln_conv_bwd", ptr(nbrs.values().contiguous()), ptr(table_fwd), ptr(g), ptr(table_bwd), ptr(fb), nv_q, nv_n, F, vn,
-             c_out, CONV_PRECISION, ptr(workspace), ptr(grad_in), ptr(grad_filter), stream_ptr(st.device))
-        return grad_in, grad_filter
+        _check(tuple(fb.shape) == (F * vn, int(g.shape[1])), f"filter bank should be [{F * vn} x {int(g.shape[1])}], got {tuple(fb.shape)}")
+        table_bwd = nbrs._neighbour_table(self, dilation) if need_input_grad else None
+        return _conv_bwd_call(nbrs.values().contiguous(), table_fwd, g, table_bwd, fb, nv_q, nv_n, F, vn, int(g.shape[1]), False, grad_param)
 
     def conv_weight_grad(self, lattice_neighbours, grad_values, filter_extent, dilation):
         """grad_filter = im2row(lattice_neighbours)^T . grad_values without the rowified buffer
@@ -606,7 +836,7 @@ class Lattice:
         _check(g.shape[0] == nv, "grad_values rows must match the query lattice")
         grad_filter = torch.empty((filter_extent * vn, g.shape[1]), dtype=torch.float32, device=st.device)
         call("ln_conv_wgrad", ptr(nbrs.values().contiguous()), ptr(table), ptr(g), nv, filter_extent, vn,
-             int(g.shape[1]), CONV_PRECISION, ptr(grad_filter), stream_ptr(st.device))
+             int(g.shape[1]), CONV_PRECISION, 0, ptr(grad_filter), stream_ptr(st.device))
         return grad_filter
 
     @staticmethod
@@ -661,6 +891,9 @@ class Lattice:
         if idx is not None:
             _check(idx.numel() == n * (d + 1) and w.numel() == n * (d + 1),
                    f"indices / weights should have {n * (d + 1)} elements, got {tuple(idx.shape)} and {tuple(w.shape)}")   # Lattice.cu:771-773
+            dev = self._structure().device
+            _check_dev_tensor(idx, torch.int32, dev, "splatting_indices")
+            _check_dev_tensor(w, torch.float32, dev, "splatting_weights")
             idx, w = idx.contiguous(), w.contiguous()
         return n, d, idx, w
 
@@ -678,7 +911,7 @@ class Lattice:
         idx = torch.empty((n * (d + 1),), dtype=torch.int32, device=st.device)
         w = torch.empty((n * (d + 1),), dtype=torch.float32, device=st.device)
         call("ln_lookup_simplex", ptr(pos), ptr(self._sigmas_on(st.device)), n, d, ptr(st.keys), ptr(st.entries),
-             st.capacity, ptr(idx), ptr(w), stream_ptr(st.device))
+             st.capacity, st.bound or 0, ptr(idx), ptr(w), stream_ptr(st.device))
         return self.slice_standalone_with_precomputation(positions_raw, idx, w), idx, w
 
     def gather_standalone_with_precomputation(self, positions_raw, splatting_indices, splatting_weights):
@@ -698,7 +931,7 @@ class Lattice:
         idx = torch.empty((n * (d + 1),), dtype=torch.int32, device=st.device)
         w = torch.empty((n * (d + 1),), dtype=torch.float32, device=st.device)
         call("ln_lookup_simplex", ptr(pos), ptr(self._sigmas_on(st.device)), n, d, ptr(st.keys), ptr(st.entries),
-             st.capacity, ptr(idx), ptr(w), stream_ptr(st.device))
+             st.capacity, st.bound or 0, ptr(idx), ptr(w), stream_ptr(st.device))
         return self.gather_standalone_with_precomputation(positions_raw, idx, w), idx, w
 
     def slice_classify_with_precomputation(self, positions_raw, delta_weights, linear_clasify_weight, linear_clasify_bias,
@@ -722,7 +955,7 @@ class Lattice:
         idx = torch.empty((n * (d + 1),), dtype=torch.int32, device=st.device)
         w = torch.empty((n * (d + 1),), dtype=torch.float32, device=st.device)
         call("ln_lookup_simplex", ptr(pos), ptr(self._sigmas_on(st.device)), n, d, ptr(st.keys), ptr(st.entries),
-             st.capacity, ptr(idx), ptr(w), stream_ptr(st.device))
+             st.capacity, st.bound or 0, ptr(idx), ptr(w), stream_ptr(st.device))
         logits = self.slice_classify_with_precomputation(positions_raw, delta_weights, linear_clasify_weight,
                                                          linear_clasify_bias, nr_classes, idx, w)
         return logits, idx, w
@@ -738,6 +971,7 @@ class Lattice:
         n, d, idx, w = self._slice_prep(positions_raw, splatting_indices, splatting_weights)
         _check(grad_sliced_values.dim() == 2 and grad_sliced_values.is_contiguous(), "grad_sliced_values must be 2-D and contiguous")
         st = self._structure()
+        _check_dev_tensor(grad_sliced_values, torch.float32, st.device, "grad_sliced_values")
         v = int(grad_sliced_values.shape[1])
         grad = torch.zeros((st.nr_vertices(), v), dtype=torch.float32, device=st.device)
         call("ln_slice_bwd", ptr(grad_sliced_values), ptr(idx), ptr(w), n, d, v, int(grad.shape[0]), ptr(grad), stream_ptr(st.device))
@@ -748,6 +982,7 @@ class Lattice:
         n, d, idx, w = self._slice_prep(positions_raw, splatting_indices, splatting_weights)
         _check(grad_sliced_values.dim() == 2 and grad_sliced_values.is_contiguous(), "grad_sliced_values must be 2-D and contiguous")
         st = self._structure()
+        _check_dev_tensor(grad_sliced_values, torch.float32, st.device, "grad_sliced_values")
         v = int(grad_sliced_values.shape[1]) // (d + 1) - 1
         grad = torch.zeros((st.nr_vertices(), v), dtype=torch.float32, device=st.device)
         call("ln_gather_bwd", ptr(grad_sliced_values), ptr(idx), ptr(w), n, d, v, ptr(grad), stream_ptr(st.device))
@@ -762,8 +997,12 @@ class Lattice:
         _check(grad_class_logits.dim() == 2 and grad_class_logits.is_contiguous(), "grad_class_logits must be 2-D and contiguous")
         vals = initial_values.contiguous()
         dev = vals.device
+        for t, what in ((grad_class_logits, "grad_class_logits"), (vals, "initial_values"), (delta_weights, "delta_weights"),
+                        (linear_clasify_weight, "linear_clasify_weight")):
+            _check_dev_tensor(t, torch.float32, dev, what)
         for t in (grad_lattice_values, grad_delta_weights, grad_linear_clasify_weight, grad_linear_clasify_bias):
-            _check(t.is_contiguous() and t.is_cuda, "gradient buffers must be contiguous CUDA tensors")
+            _check(t.is_contiguous(), "gradient buffers must be contiguous CUDA tensors")
+            _check_dev_tensor(t, torch.float32, dev, "gradient buffers")
         call("ln_slice_classify_bwd", ptr(grad_class_logits), ptr(vals), ptr(idx), ptr(w), ptr(delta_weights.contiguous()),
              ptr(linear_clasify_weight.contiguous()), n, d, int(vals.shape[1]), int(nr_classes), ptr(grad_lattice_values),
              ptr(grad_delta_weights), ptr(grad_linear_clasify_weight), ptr(grad_linear_clasify_bias), stream_ptr(dev))

@@ -15,7 +15,7 @@ from torch.autograd import Function
 from .lattice_wrapper import LatticeWrapper
 
 
-def _conv_backward(query, neighbours, neighbour_values, filter_bank, grad_out, dilation, val_dim):
+def _conv_backward(query, neighbours, neighbour_values, filter_bank, grad_out, dilation, val_dim, need_input_grad=True):
     """Shared backward of out = conv(query <- neighbours):
     grad_filter = im2row(neighbours)^T . grad_out;  grad_neighbour_values = flipped conv of grad_out
     evaluated at the neighbour lattice's vertices with the re-laid-out filter (lattice_funcs.py:298-313)."""
@@ -23,7 +23,9 @@ def _conv_backward(query, neighbours, neighbour_values, filter_bank, grad_out, d
     grad_out = grad_out.contiguous()
     neighbours.set_values(neighbour_values)
     if hasattr(query, "conv_backward"):     # both gradients from one call into the CUDA library
-        grad_values, grad_filter = query.conv_backward(neighbours, grad_out, filter_bank, dilation)
+        # a bank that is a leaf parameter gets its gradient written straight into its gradient-bucket slice (when one is active)
+        grad_param = filter_bank if (filter_bank.is_leaf and filter_bank.requires_grad) else None
+        grad_values, grad_filter = query.conv_backward(neighbours, grad_out, filter_bank, dilation, need_input_grad, grad_param)
         query.set_values(grad_out)          # the reference leaves the query handle holding the incoming gradient
         return grad_values, grad_filter
     grad_filter = query.conv_weight_grad(neighbours, grad_out, filter_extent, dilation)
@@ -116,12 +118,20 @@ class Im2RowLattice(Function):
 
 
 class ConvIm2RowLattice(Function):
+    """forward(lattice_values, lattice, filter_bank, dilation) as in the reference (lattice_funcs.py:250-320); the two
+    optional trailing inputs are extensions: `bias` [nr_filters] and `residual` [nv x nr_filters] are added in the
+    convolution kernel's epilogue (the reference adds them with separate torch ops, lattice_modules.py:244-246, 1290)."""
+
     @staticmethod
-    def forward(ctx, lattice_values, lattice, filter_bank, dilation):
+    def forward(ctx, lattice_values, lattice, filter_bank, dilation, bias=None, residual=None):
         lattice.set_values(lattice_values)
-        convolved = lattice.convolve_im2row_standalone(filter_bank, dilation, lattice, False)
+        if bias is None and residual is None:
+            convolved = lattice.convolve_im2row_standalone(filter_bank, dilation, lattice, False)
+        else:
+            convolved = lattice.convolve_im2row_standalone(filter_bank, dilation, lattice, False, bias=bias, residual=residual)
         ctx.save_for_backward(filter_bank, lattice_values)
         ctx.lattice, ctx.dilation, ctx.val_dim = lattice, dilation, lattice.val_dim()
+        ctx.has_bias, ctx.has_residual = bias is not None, residual is not None
         return convolved.values(), LatticeWrapper.wrap(convolved)
 
     @staticmethod
@@ -130,9 +140,12 @@ class ConvIm2RowLattice(Function):
         lattice = ctx.lattice
         # same lattice on both sides: query a private alias so set_values on one role does not clobber the other
         query = lattice.clone_lattice()
-        grad_values, grad_filter = _conv_backward(query, lattice, lattice_values, filter_bank, grad_lattice_values, ctx.dilation, ctx.val_dim)
+        grad_values, grad_filter = _conv_backward(query, lattice, lattice_values, filter_bank, grad_lattice_values, ctx.dilation, ctx.val_dim,
+                                                  ctx.needs_input_grad[0])
         ctx.lattice = None
-        return grad_values, None, grad_filter, None
+        grad_bias = grad_lattice_values.sum(0) if (ctx.has_bias and ctx.needs_input_grad[4]) else None
+        grad_residual = grad_lattice_values if (ctx.has_residual and ctx.needs_input_grad[5]) else None
+        return grad_values, None, grad_filter, None, grad_bias, grad_residual
 
 
 class CoarsenLattice(Function):

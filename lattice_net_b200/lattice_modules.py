@@ -17,6 +17,7 @@ import numpy as np
 import torch
 from torch.nn import functional as F
 
+from . import lattice as _lattice
 from ._cabi import call, ptr, stream_ptr
 from .lattice import Lattice
 from .lattice_funcs import (CoarsenLattice, ConvIm2RowLattice, DistributeLattice, ExpandLattice, FinefyLattice,
@@ -81,33 +82,99 @@ def _gn_workspace(nv, c, groups, device):
     return torch.empty((nbytes // 4,), dtype=torch.float32, device=device) if nbytes > 0 else None
 
 
+def _gn_forward(x, gamma, beta, groups, eps, relu, nv_dev):
+    x = x.contiguous()
+    nv, c = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty((groups, 2), dtype=torch.float32, device=x.device)
+    call("ln_group_norm_fwd", ptr(x), ptr(gamma.contiguous()), ptr(beta.contiguous()), nv, ptr(nv_dev), c, groups, float(eps),
+         1 if relu else 0, ptr(y), ptr(stats), ptr(_gn_workspace(nv, c, groups, x.device)), stream_ptr(x.device))
+    return x, y, stats
+
+
+def _gn_backward(dy, x, y, gamma, beta, stats, groups, relu, nv_dev, dx_add):
+    """-> (dx [+ dx_add], dgamma, dbeta); the affine gradients land in their gradient-bucket slices when a bucket is active."""
+    nv, c = x.shape
+    dx = torch.empty_like(x)
+    dgamma = _lattice.grad_target(gamma)
+    dbeta = _lattice.grad_target(beta)
+    if dgamma is None or dbeta is None:
+        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
+    if dx_add is not None:
+        dx_add = dx_add.contiguous()
+    call("ln_group_norm_bwd", ptr(dy.contiguous()), ptr(x), ptr(y), ptr(gamma.contiguous()), ptr(stats), ptr(dx_add), nv, ptr(nv_dev), c,
+         groups, 1 if relu else 0, ptr(dx), ptr(dgamma), ptr(dbeta), ptr(_gn_workspace(nv, c, groups, x.device)), stream_ptr(x.device))
+    return dx, dgamma, dbeta
+
+
 class _GroupNormReLU(torch.autograd.Function):
     """GroupNorm (+ReLU) on vertex-major values [nv x C] in one kernel each way (ln_group_norm_fwd/bwd)."""
 
     @staticmethod
     def forward(ctx, x, gamma, beta, groups, eps, relu, nv_dev=None):
         # nv_dev: device int32[1] with the actual vertex count when x is padded to a row bound (static-shape mode)
-        x = x.contiguous()
-        nv, c = x.shape
-        y = torch.empty_like(x)
-        stats = torch.empty((groups, 2), dtype=torch.float32, device=x.device)
-        call("ln_group_norm_fwd", ptr(x), ptr(gamma.contiguous()), ptr(beta.contiguous()), nv, ptr(nv_dev), c, groups, float(eps),
-             1 if relu else 0, ptr(y), ptr(stats), ptr(_gn_workspace(nv, c, groups, x.device)), stream_ptr(x.device))
-        ctx.save_for_backward(x, y, gamma, stats)
+        x, y, stats = _gn_forward(x, gamma, beta, groups, eps, relu, nv_dev)
+        ctx.save_for_backward(x, y, gamma, beta, stats)
         ctx.groups, ctx.relu, ctx.nv_dev = groups, relu, nv_dev
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, gamma, stats = ctx.saved_tensors
-        nv, c = x.shape
-        dx = torch.empty_like(x)
-        dgamma = torch.empty_like(gamma)
-        dbeta = torch.empty_like(gamma)
-        call("ln_group_norm_bwd", ptr(dy.contiguous()), ptr(x), ptr(y), ptr(gamma.contiguous()), ptr(stats), nv, ptr(ctx.nv_dev), c,
-             ctx.groups, 1 if ctx.relu else 0, ptr(dx), ptr(dgamma), ptr(dbeta), ptr(_gn_workspace(nv, c, ctx.groups, x.device)),
-             stream_ptr(x.device))
+        x, y, gamma, beta, stats = ctx.saved_tensors
+        dx, dgamma, dbeta = _gn_backward(dy, x, y, gamma, beta, stats, ctx.groups, ctx.relu, ctx.nv_dev, None)
         return dx, dgamma, dbeta, None, None, None, None
+
+
+class _GroupNormReLUSplit(torch.autograd.Function):
+    """The head of a residual block: returns (GroupNorm(+ReLU)(x), x).  Both users of x -- the normalised branch and
+    the skip connection -- hang off this one node, so the two gradients meet INSIDE the backward kernel
+    (dx = gn_backward(dy) + d_skip, ln_group_norm_bwd's dx_add) instead of in an add kernel launched by autograd
+    (lattice_modules.py:1255-1290 / 1322-1358: `identity = lv ... lv = lv + identity`)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, relu, nv_dev=None):
+        xc, y, stats = _gn_forward(x, gamma, beta, groups, eps, relu, nv_dev)
+        ctx.save_for_backward(xc, y, gamma, beta, stats)
+        ctx.groups, ctx.relu, ctx.nv_dev = groups, relu, nv_dev
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, d_skip):
+        x, y, gamma, beta, stats = ctx.saved_tensors
+        if dy is None:
+            dy = torch.zeros_like(x)
+        dx, dgamma, dbeta = _gn_backward(dy, x, y, gamma, beta, stats, ctx.groups, ctx.relu, ctx.nv_dev, d_skip)
+        return dx, dgamma, dbeta, None, None, None, None
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T (+ bias) (+ residual) for the 1x1 layers (lattice_modules.py:806-832 uses torch.nn.Linear): forward, data
+    gradient and weight gradient run through the lattice-convolution kernels with filter extent 1 -- tcgen05 3xTF32 when
+    in_features % 32 == 0 -- with the bias / skip connection folded into the epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias=None, residual=None):
+        x = x.contiguous()
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias, ctx.has_residual = bias is not None, residual is not None
+        return _lattice.linear_forward(x, weight, bias, residual)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        grad_param = weight if (weight.is_leaf and weight.requires_grad) else None
+        dx, dw = _lattice.linear_backward(x, weight, dy, ctx.needs_input_grad[0], grad_param)
+        db = dy.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db, (dy if (ctx.has_residual and ctx.needs_input_grad[3]) else None)
+
+
+def linear(x, weight, bias=None, residual=None):
+    """F.linear(x, weight, bias) (+ residual) on the lattice kernels (CUDA fp32 2-D inputs), torch elsewhere."""
+    if x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and weight.dtype == torch.float32:
+        return _LinearFn.apply(x, weight, bias, residual)
+    y = F.linear(x, weight, bias)
+    return y if residual is None else y + residual
 
 
 # None: GroupNorm(+ReLU) always runs the kernels of ln_norm.cu (one CTA per group for ShapeNet-sized lattices, row-tiled
@@ -285,13 +352,22 @@ class ConvLatticeIm2RowModule(_LatticeFilterModule):
         super().__init__(in_channels, out_channels, bias, device)
         self.neighbourhood_size, self.dilation = neighbourhood_size, dilation
 
-    def forward(self, lattice_values, lattice_structure):
+    def forward(self, lattice_values, lattice_structure, residual=None):
+        """residual (extension): [nv x out_channels] added to the result inside the convolution kernel."""
         lattice_structure.set_values(lattice_values)
         self._check_in(lattice_structure)
-        lv, ls_wrap = ConvIm2RowLattice.apply(lattice_values, lattice_structure, self._filter(), self.dilation)
-        ls = ls_wrap.lattice   # a new handle: the value width may have changed
-        if self.use_bias:
-            lv = lv + self.bias
+        if lattice_values.is_cuda and hasattr(lattice_structure, "conv_backward"):
+            # bias and skip connection ride in the kernel's epilogue
+            lv, ls_wrap = ConvIm2RowLattice.apply(lattice_values, lattice_structure, self._filter(), self.dilation,
+                                                  self.bias if self.use_bias else None, residual)
+            ls = ls_wrap.lattice   # a new handle: the value width may have changed
+        else:
+            lv, ls_wrap = ConvIm2RowLattice.apply(lattice_values, lattice_structure, self._filter(), self.dilation)
+            ls = ls_wrap.lattice
+            if self.use_bias:
+                lv = lv + self.bias
+            if residual is not None:
+                lv = lv + residual
         ls.set_values(lv)
         return lv, ls
 
@@ -366,6 +442,25 @@ class GatherLatticeModule(torch.nn.Module):
         return GatherLattice.apply(lattice_values, lattice_structure, positions, splatting_indices, splatting_weights)
 
 
+def filter_readings(model, with_backward=True):
+    """Every (tensor, filter_extent, c_in, c_out, transposed) reading of the filter banks / 1x1 weights of `model` that a
+    forward (and backward) pass will ask the tensor-core convolution for -- the input of lattice.prepare_filters()."""
+    readings = []
+    for m in model.modules():
+        if isinstance(m, _LatticeFilterModule) and "weight" in m._parameters and m.weight is not None:
+            w, fe, ci, co = m.weight, m.filter_extent, m.in_channels, m.out_channels
+            readings.append((w, fe, ci, co, False))
+            if with_backward:
+                readings.append((w, fe, co, ci, True))
+        elif isinstance(m, GnRelu1x1):
+            w = m.linear.weight                       # [out x in]: the bank stored transposed
+            co, ci = w.shape
+            readings.append((w, 1, int(ci), int(co), True))
+            if with_backward:
+                readings.append((w, 1, int(co), int(ci), False))
+    return readings
+
+
 # --------------------------------------------------------------------------------------------------
 class BatchNormLatticeModule(torch.nn.Module):
     def __init__(self, nr_params, affine=True, device=None):
@@ -386,7 +481,9 @@ class GroupNormLatticeModule(torch.nn.Module):
         nr_groups = 32 if nr_params % 32 == 0 else int(nr_params / 2)   # lattice_modules.py:587-590
         self.gn = torch.nn.GroupNorm(nr_groups, nr_params).to(device or _default_device())
 
-    def forward(self, lattice_values, lattice_py, do_set_values=True, relu=False):
+    def forward(self, lattice_values, lattice_py, do_set_values=True, relu=False, split=False):
+        """split (extension): also return the input as the skip connection of a residual block -> (lv, skip, lattice);
+        the two gradients are then summed inside the GroupNorm backward kernel."""
         if lattice_values.dim() != 2:
             sys.exit("lattice should be 2 dimensional, nr_vertices x val_dim")
         # statistics run over (channels of a group) x (all vertices): vertices are the "length" axis
@@ -395,20 +492,26 @@ class GroupNormLatticeModule(torch.nn.Module):
         ht = getattr(lattice_py, "m_hash_table", None)      # (bench.py's reference arm passes its own handle type)
         st = ht.structure if ht is not None else None
         nv_dev = st.nr_filled if (st is not None and st.bound is not None) else None
+        skip = lattice_values
         if lattice_values.is_cuda and (nv_dev is not None or FUSED_NORM_MAX_ELEMS_PER_GROUP is None
                                        or nv * (c // gn.num_groups) <= FUSED_NORM_MAX_ELEMS_PER_GROUP):
-            lv = _GroupNormReLU.apply(lattice_values, gn.weight, gn.bias, gn.num_groups, gn.eps, relu, nv_dev)
+            if split:
+                lv, skip = _GroupNormReLUSplit.apply(lattice_values, gn.weight, gn.bias, gn.num_groups, gn.eps, relu, nv_dev)
+            else:
+                lv = _GroupNormReLU.apply(lattice_values, gn.weight, gn.bias, gn.num_groups, gn.eps, relu, nv_dev)
         else:
             lv = gn(lattice_values.t().unsqueeze(0)).squeeze(0).t()
             if relu:
                 lv = torch.relu(lv)
         if do_set_values:
             lattice_py.set_values(lv)
+        if split:
+            return lv, skip, lattice_py
         return lv, lattice_py
 
-    def forward_relu(self, lattice_values, lattice_py):
+    def forward_relu(self, lattice_values, lattice_py, split=False):
         """GroupNorm followed by ReLU as one fused op (the GN -> ReLU -> conv pattern of every block)."""
-        return self.forward(lattice_values, lattice_py, True, relu=True)
+        return self.forward(lattice_values, lattice_py, True, relu=True, split=split)
 
 
 class PointNetModule(torch.nn.Module):
@@ -517,12 +620,18 @@ class GnRelu1x1(torch.nn.Module):
         self.linear = torch.nn.Linear(in_channels, out_channels, bias=bias).to(dev)
         torch.nn.init.kaiming_normal_(self.linear.weight, mode="fan_in", nonlinearity="relu")
 
-    def forward(self, lv, ls):
+    def forward(self, lv, ls, residual=None, split=False):
+        """residual / split (extensions): the skip connection of a bottleneck block enters / leaves here, see
+        ConvLatticeIm2RowModule.forward and GroupNormLatticeModule.forward."""
         ls.set_values(lv)
-        lv, ls = self.norm.forward_relu(lv, ls)
-        lv = self.linear(lv)
+        skip = None
+        if split:
+            lv, skip, ls = self.norm.forward_relu(lv, ls, split=True)
+        else:
+            lv, ls = self.norm.forward_relu(lv, ls)
+        lv = linear(lv, self.linear.weight, self.linear.bias, residual)
         ls.set_values(lv)
-        return lv, ls
+        return (lv, skip, ls) if split else (lv, ls)
 
 
 class Gn(torch.nn.Module):
@@ -566,15 +675,19 @@ class GnReluConv(torch.nn.Module):
         self.relu = torch.nn.ReLU(inplace=False)
         self.drop = DropoutLattice(0.2) if with_dropout else None
 
-    def forward(self, lv, ls):
+    def forward(self, lv, ls, residual=None, split=False):
         ls.set_values(lv)
-        lv, ls = self.norm.forward_relu(lv, ls)
+        skip = None
+        if split:
+            lv, skip, ls = self.norm.forward_relu(lv, ls, split=True)
+        else:
+            lv, ls = self.norm.forward_relu(lv, ls)
         if self.drop is not None:
             lv = self.drop(lv)
             ls.set_values(lv)
-        lv_1, ls_1 = self.conv(lv, ls)
+        lv_1, ls_1 = self.conv(lv, ls, residual) if residual is not None else self.conv(lv, ls)
         ls_1.set_values(lv_1)
-        return lv_1, ls_1
+        return (lv_1, skip, ls_1) if split else (lv_1, ls_1)
 
 
 class BnReluConv(torch.nn.Module):
@@ -671,11 +784,11 @@ class ResnetBlock(torch.nn.Module):
         self.conv2 = GnReluConv(in_channels, out_channels, dilations[1], biases[1], with_dropout=with_dropout, device=device)
 
     def forward(self, lv, ls):
-        identity = lv
+        # lattice_modules.py:1255-1290: identity = lv; conv1; conv2; lv += identity.  The skip connection leaves through
+        # the first GroupNorm node and re-enters in the epilogue of the second convolution: no add kernels either way.
         ls.set_values(lv)
-        lv, ls = self.conv1(lv, ls)
-        lv, ls = self.conv2(lv, ls)
-        lv = lv + identity
+        lv, identity, ls = self.conv1(lv, ls, split=True)
+        lv, ls = self.conv2(lv, ls, residual=identity)
         ls.set_values(lv)
         return lv, ls
 
@@ -693,11 +806,9 @@ class BottleneckBlock(torch.nn.Module):
 
     def forward(self, lv, ls):
         ls.set_values(lv)
-        identity = lv
-        lv, ls = self.contract(lv, ls)
+        lv, identity, ls = self.contract(lv, ls, split=True)
         lv, ls = self.conv(lv, ls)
-        lv, ls = self.expand(lv, ls)
-        lv = lv + identity
+        lv, ls = self.expand(lv, ls, residual=identity)
         ls.set_values(lv)
         return lv, ls
 

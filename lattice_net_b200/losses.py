@@ -18,16 +18,22 @@ def lovasz_grad(gt_sorted):
 
 def lovasz_softmax(probas, labels, ignore_index=None):
     """probas [P, C] (class probabilities), labels [P] (int64).  Mean over the classes present.
-    All classes are handled by one batched sort / cumsum (the textbook version loops over classes)."""
-    if ignore_index is not None:
-        keep = labels != ignore_index
-        probas, labels = probas[keep], labels[keep]
+    All classes are handled by one batched sort / cumsum (the textbook version loops over classes).
+    ignore_index: that CLASS is left out of the mean; its points stay in every other class's sorted error vector as
+    negatives, exactly as in the reference (lovasz_loss.py:41-58 skips `c == ignore_index` in the class loop and never
+    drops a point).  No boolean-mask indexing: static shapes, so this runs inside a CUDA-graph capture."""
     if probas.numel() == 0:
         return probas.sum() * 0.0
     nr_classes = probas.shape[1]
-    # class-major [C, P] so that the sort and the scans run along the contiguous dimension
-    fg = torch.nn.functional.one_hot(labels, nr_classes).to(probas.dtype).t().contiguous()
+    # class-major [C, P] so that the sort and the scans run along the contiguous dimension; labels outside [0, C)
+    # (e.g. a negative "unlabelled" marker) are foreground of no class
+    in_range = (labels >= 0) & (labels < nr_classes)
+    fg = torch.nn.functional.one_hot(labels.clamp(0, nr_classes - 1), nr_classes).to(probas.dtype) * in_range.unsqueeze(1).to(probas.dtype)
+    fg = fg.t().contiguous()
     present = (fg.sum(1) > 0).to(probas.dtype)
+    if ignore_index is not None and 0 <= ignore_index < nr_classes:
+        present = present.clone()
+        present[ignore_index] = 0.0
     errors_sorted, perm = torch.sort((fg - probas.t()).abs(), dim=1, descending=True)
     fg_sorted = fg.gather(1, perm)
     gts = fg_sorted.sum(1, keepdim=True)
@@ -39,10 +45,12 @@ def lovasz_softmax(probas, labels, ignore_index=None):
     return (per_class * present).sum() / present.sum().clamp(min=1.0)
 
 
-def lovasz_softmax_loop(probas, labels):
+def lovasz_softmax_loop(probas, labels, ignore_index=None):
     """Per-class loop formulation (reference: latticenet_py/lattice/lovasz_loss.py:41-72), kept for tests."""
     losses = []
     for c in range(probas.shape[1]):
+        if c == ignore_index:
+            continue
         fg = (labels == c).float()
         if fg.sum() == 0:
             continue

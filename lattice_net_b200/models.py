@@ -6,8 +6,9 @@ reference `state_dict` maps one to one.
 """
 import torch
 
+from . import lattice as _lattice
 from .lattice_modules import (BottleneckBlock, CoarsenAct, DistributeLatticeModule, GnReluFinefy, PointNetModule,
-                              ResnetBlock, SliceFastCUDALatticeModule)
+                              ResnetBlock, SliceFastCUDALatticeModule, filter_readings)
 
 
 class LNN(torch.nn.Module):
@@ -82,6 +83,10 @@ class LNN(torch.nn.Module):
         self.logsoftmax = torch.nn.LogSoftmax(dim=1)
 
     def forward(self, ls, positions, values):
+        if positions.is_cuda:
+            # tensor-core slabs of every filter bank / 1x1 weight, forward and transposed readings, in one launch
+            # (nothing is launched while the weights have not changed since the last call)
+            _lattice.prepare_filters(filter_readings(self, torch.is_grad_enabled()))
         with torch.no_grad():
             ls, distributed, indices, weights = self.distribute(ls, positions, values)
         self.last_level1_lattice = ls          # kept for inspection / tests (vertex numbering of this pass)

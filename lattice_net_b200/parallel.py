@@ -63,16 +63,49 @@ class GradBucket:
             self.views.append(self.flat[off:off + n].view_as(p))
             off += n
         self.nbytes = total * 4
+        self._registered = False
+        self._direct = False
 
     def zero(self):
         """Call before backward."""
         for p in self.params:
             p.grad = None
 
+    def begin_direct_step(self):
+        """Call before forward: clears the flat buffer with ONE memset and lets the backward passes of the lattice
+        operators write weight gradients straight into their slices (lattice.grad_target); autograd then adopts those
+        slices as `.grad` without a copy.  Pair with end_direct_step() after backward."""
+        from . import lattice as _lattice
+        if not self._registered:
+            off, targets = 0, {}
+            for p in self.params:
+                targets[p.data_ptr()] = (self.flat, off, tuple(p.shape))
+                off += p.numel()
+            _lattice.register_grad_targets(targets)
+            self._registered = True
+        self.flat_with_extra.zero_()
+        for p in self.params:
+            p.grad = None
+        _lattice.set_grad_targets_active(True)
+        self._direct = True
+
+    def end_direct_step(self):
+        from . import lattice as _lattice
+        _lattice.set_grad_targets_active(False)
+
     def pack(self, extra=None):
-        """Call after backward: flat <- all grads (one fused copy), .grad <- views of flat."""
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-        torch._foreach_copy_(self.views, grads)
+        """Call after backward: flat <- the grads that are not already there (one fused copy), .grad <- views of flat."""
+        dst, src = [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                if not self._direct:
+                    v.zero_()                  # no memset cleared the buffer this step: drop the previous step's values
+                continue
+            if p.grad.data_ptr() != v.data_ptr():
+                dst.append(v)
+                src.append(p.grad)
+        if dst:
+            torch._foreach_copy_(dst, src)
         for p, v in zip(self.params, self.views):
             p.grad = v
         if extra is not None:

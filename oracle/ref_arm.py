@@ -235,7 +235,7 @@ class _RefIm2RowFn(torch.autograd.Function):
         return g, None, None, None
 
 
-def _ref_conv_module_forward(self, lattice_values, lattice_structure):
+def _ref_conv_module_forward(self, lattice_values, lattice_structure, residual=None):
     """ConvLatticeIm2RowModule.forward of the reference (lattice_modules.py:231-250): im2row, mm, clone."""
     lattice_structure.set_values(lattice_values)
     fe = lattice_structure.get_filter_extent(self.neighbourhood_size)
@@ -244,8 +244,15 @@ def _ref_conv_module_forward(self, lattice_values, lattice_structure):
     new = lattice_structure.clone_lattice()
     if self.use_bias:
         lv = lv + self.bias
+    if residual is not None:
+        lv = lv + residual
     new.set_values(lv)
     return lv, new
+
+
+def _torch_linear(x, weight, bias=None, residual=None):
+    y = torch.nn.functional.linear(x, weight, bias)
+    return y if residual is None else y + residual
 
 
 def patch_modules():
@@ -257,6 +264,7 @@ def patch_modules():
     lm.scatter_max = lambda src, index, nv: _torch_scatter_max(src, index, nv)
     lm.scatter_sum_count = _torch_scatter_sum_count
     lm.ConvLatticeIm2RowModule.forward = _ref_conv_module_forward
+    lm.linear = _torch_linear                  # torch.nn.Linear (cuBLAS), as in the reference's 1x1 layers
     lm.FUSED_NORM_MAX_ELEMS_PER_GROUP = 0      # torch GroupNorm + ReLU, as in the reference
     _L.m_expected_position_dimensions = 3            # static pos-dim the module constructors read
 

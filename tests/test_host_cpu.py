@@ -101,9 +101,9 @@ def test_c_abi_library_exports_every_declared_symbol():
 
 def test_workspace_size_queries_are_host_only_and_consistent():
     """ln_conv_workspace_bytes / ln_group_norm_workspace_bytes are pure host functions (callable without a GPU); the
-    Python-side copies of their rules (lattice.py:_conv_ws_bytes, lattice_modules.py:_gn_workspace) must agree."""
+    Python-side copies of their rules (lattice.py:_slab_floats / tensor_core_reading_ok, lattice_modules.py:_gn_workspace)
+    must agree."""
     from lattice_net_b200 import _cabi, lattice as lattice_mod
-    from lattice_net_b200.lattice import Lattice
     lib = _cabi.load()
     F = 9
     saved = lattice_mod.CONV_PRECISION
@@ -111,7 +111,9 @@ def test_workspace_size_queries_are_host_only_and_consistent():
         lattice_mod.CONV_PRECISION = 1
         for c_in, c_out in [(32, 32), (64, 128), (128, 96), (256, 256), (64, 512), (512, 384), (96, 7), (3, 32), (32, 2048)]:
             want = int(lib.ln_conv_workspace_bytes(F, c_in, c_out, 1))
-            assert Lattice._conv_ws_bytes(F, c_in, c_out) == want, (c_in, c_out)
+            mine = 4 * lattice_mod._slab_floats(F, c_in, c_out) if lattice_mod.tensor_core_reading_ok(F, c_in, c_out) else 0
+            assert mine == want, (c_in, c_out)
+        assert int(lib.ln_conv_workspace_bytes(1, 128, 64, 1)) == 2 * 128 * 64 * 4     # filter extent 1: the 1x1 layers
         # layers wider than one 256-column tile are chunked, not sent to the fp32 kernel
         assert int(lib.ln_conv_workspace_bytes(F, 64, 512, 1)) == 2 * F * 64 * 512 * 4
         assert int(lib.ln_conv_workspace_bytes(F, 3, 32, 1)) == 0          # c_in % 32 != 0: fp32 kernel, no workspace
@@ -158,6 +160,14 @@ def test_batched_lovasz_equals_per_class_loop():
     gb, = torch.autograd.grad(b, logits)
     assert torch.allclose(ga, gb, atol=1e-6)
     assert torch.isfinite(segmentation_loss(torch.log_softmax(logits, 1), labels))
+    # ignore_index leaves that CLASS out of the mean but keeps its points as negatives of the other classes
+    # (the reference's class loop, lovasz_loss.py:44-45), value and gradient
+    p = torch.softmax(logits, 1)
+    a, b = lovasz_softmax(p, labels, ignore_index=2), lovasz_softmax_loop(p, labels, ignore_index=2)
+    assert torch.allclose(a, b, atol=1e-6)
+    ga, = torch.autograd.grad(a, logits, retain_graph=True)
+    gb, = torch.autograd.grad(b, logits)
+    assert torch.allclose(ga, gb, atol=1e-6)
 
 
 # Names the reference binds to Python (live `.def` / `.def_static` / `.def_readonly` lines of
