@@ -228,8 +228,12 @@ def run_ours(args):
         model(lattice, *dev_clouds[0][:2])
     broadcast_parameters(model, 0)
     graphed = args.mode == "graph"
-    optimizer = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=3e-4, amsgrad=True, fused=True, capturable=graphed)
     bucket = GradBucket(model.parameters())
+    if graphed and not args.torch_optimizer:
+        from lattice_net_b200.optim import FlatAdamW          # AdamW-amsgrad as one kernel over the flat parameter / gradient buffers
+        optimizer = FlatAdamW(bucket, lr=1e-3, weight_decay=3e-4)
+    else:
+        optimizer = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=3e-4, amsgrad=True, fused=True, capturable=graphed)
     flush_buf = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=device)
 
     bounds = None
@@ -350,6 +354,7 @@ def main():
                     help="N>1: two graphs per step with an eager NCCL all-reduce between them")
     ap.add_argument("--conv-precision", type=int, default=1, choices=[0, 1, 2],
                     help="0 fp32 CUDA cores, 1 tcgen05 3xTF32 (fp32-equivalent, default), 2 tcgen05 TF32")
+    ap.add_argument("--torch-optimizer", action="store_true", help="torch.optim.AdamW(fused) instead of the one-kernel flat AdamW")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s CPU leg (profiler passes only; never for a reported line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -264,6 +264,29 @@ int ln_group_norm_bwd(const float* dy, const float* x, const float* y, const flo
                       const float* dx_add, int nv, const int* nv_dev, int c, int groups, int relu, float* dx, float* dgamma,
                       float* dbeta, float* workspace, void* stream);
 
+/* ---- loss and optimizer of the training step -------------------------------------
+ * 0.5 * Lovasz-softmax + 0.5 * NLL on log-probabilities (/root/reference/latticenet_py/ln_train.py:156-158,
+ * lattice/lovasz_loss.py:41-72), value and d/d logp in one launch: one CTA per class sorts the errors |fg - p| in shared
+ * memory.  n <= ln_seg_loss_max_points() (the ShapeNet-sized clouds this matters for; larger scans use the host-side
+ * batched formulation).  logp [n x nr_classes], labels int64 [n]; ignore_index: that class is left out of both terms
+ * (its points stay in the other classes' error vectors, as in the reference's class loop).
+ * grad_lov [n x nr_classes] (out): unnormalised Lovasz gradient; acc_zeroed: 8 floats of zeroed scratch;
+ * result (out, 4 floats): [0] loss, [1] classes present, [2] valid points. */
+int ln_seg_loss_max_points(void);
+int ln_seg_loss_fwd(const float* logp, const long long* labels, int n, int nr_classes, int ignore_index, float* grad_lov,
+                    float* acc_zeroed, float* result, void* stream);
+/* grad_logp = grad_loss[0] * d loss / d logp from the quantities ln_seg_loss_fwd left behind. */
+int ln_seg_loss_bwd(const float* grad_lov, const long long* labels, const float* result, const float* grad_loss, int n,
+                    int nr_classes, int ignore_index, float* grad_logp, void* stream);
+
+/* AdamW with amsgrad (ln_train.py:163-165) as ONE kernel over flat fp32 buffers of n elements (16-byte aligned),
+ * torch.optim.AdamW's update order.  state: 2 floats, [0] step count (advanced here), [1] scratch (zero).
+ * skip (may be NULL): device float, non-zero = leave parameters, moments and step count untouched.
+ * grad_scale is multiplied into the gradients first (1 / world_size after a sum all-reduce). */
+int ln_adamw_amsgrad(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, long long n,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, float* state,
+                     const float* skip, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

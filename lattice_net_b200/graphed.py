@@ -66,7 +66,8 @@ class GraphedTrainStep:
             self.pos.copy_(example[0])
             self.vals.copy_(example[1])
             self.labels.copy_(example[2])
-        optimizer.found_inf = self.found_inf
+        optimizer.found_inf = self.found_inf      # torch fused AdamW (capturable) and optim.FlatAdamW both honour it on the device
+        self.flat_optimizer = hasattr(optimizer, "flat_params")
         self.capture_collective = capture_collective and world > 1
         self.graphs = []
         self.launches_per_step = 0
@@ -91,7 +92,8 @@ class GraphedTrainStep:
         flags = torch.stack([l.m_hash_table.structure.status[0] for l in levels]).max()
         self.nv_actual.copy_(torch.cat([l.m_hash_table.structure.nr_filled for l in levels]))
         self.found_inf.copy_((flags > 0).to(torch.float32))
-        if self.world > 1:
+        if self.world > 1 or self.flat_optimizer:
+            # gradients that did not land in the bucket by themselves (a handful: weight-norm, slice-head scalars) are copied in
             self.bucket.pack(extra=self.found_inf)
 
     def _allreduce(self):
@@ -100,10 +102,14 @@ class GraphedTrainStep:
 
     def _update(self):
         if self.world > 1:
-            self.bucket.flat.mul_(1.0 / self.world)
             self.found_inf.copy_((self.bucket.extra > 0).to(torch.float32).reshape(()))   # any rank overflowed -> all skip
         self.overflow_steps.add_(self.found_inf)
-        self.optimizer.step()
+        if self.flat_optimizer:
+            self.optimizer.step(grad_scale=1.0 / self.world)         # the 1/W of the sum all-reduce rides in the update kernel
+        else:
+            if self.world > 1:
+                self.bucket.flat.mul_(1.0 / self.world)
+            self.optimizer.step()
 
     def _eager_step(self):
         self._forward_backward()
@@ -111,6 +117,9 @@ class GraphedTrainStep:
         self._update()
 
     def _snapshot(self):
+        if self.flat_optimizer:
+            o = self.optimizer
+            return [t.clone() for t in (o.flat_params, o.exp_avg, o.exp_avg_sq, o.max_exp_avg_sq, o.state)]
         params = [p for g in self.optimizer.param_groups for p in g["params"]]
         saved = []
         for p in params:
@@ -120,6 +129,12 @@ class GraphedTrainStep:
 
     def _restore(self, saved):
         # in place: the graph has captured the addresses of the parameters and of the optimizer state
+        if self.flat_optimizer:
+            o = self.optimizer
+            with torch.no_grad():
+                for dst, src in zip((o.flat_params, o.exp_avg, o.exp_avg_sq, o.max_exp_avg_sq, o.state), saved):
+                    dst.copy_(src)
+            return
         with torch.no_grad():
             for p, value, st in saved:
                 p.copy_(value)

@@ -1,7 +1,7 @@
 """Losses of the reference's training step: NLL on the log-softmax plus
 the Lovasz-softmax surrogate of the mean IoU (Berman et al. 2018), which
-/root/reference/latticenet_py/ln_train.py:156-158 combines 50/50.  Plain PyTorch: not part of the
-lattice hot path, present so the benchmark times the same step the reference runs."""
+/root/reference/latticenet_py/ln_train.py:156-158 combines 50/50.  ShapeNet-sized clouds
+run it as one kernel (csrc/ln_train.cu); the batched torch formulation serves larger scans and CPU tensors."""
 import torch
 
 
@@ -69,8 +69,51 @@ class LovaszSoftmax(torch.nn.Module):
         return lovasz_softmax(logsoftmax.exp(), labels, self.ignore_index)
 
 
+class _SegLossFn(torch.autograd.Function):
+    """0.5 * Lovasz-softmax + 0.5 * NLL and its gradient w.r.t. the log-probabilities from ONE kernel (ln_seg_loss_fwd:
+    one CTA per class sorts the errors in shared memory); the backward pass is a single scaling kernel."""
+
+    @staticmethod
+    def forward(ctx, logsoftmax, labels, ignore_index):
+        from ._cabi import call, ptr, stream_ptr
+        lp = logsoftmax.contiguous()
+        n, c = lp.shape
+        dev = lp.device
+        grad_lov = torch.empty((n, c), dtype=torch.float32, device=dev)
+        scratch = torch.zeros((12,), dtype=torch.float32, device=dev)        # [0:8) accumulators (zeroed), [8:12) result
+        call("ln_seg_loss_fwd", ptr(lp), ptr(labels), n, c, int(ignore_index), ptr(grad_lov), ptr(scratch[:8]), ptr(scratch[8:]), stream_ptr(dev))
+        ctx.save_for_backward(grad_lov, labels, scratch)
+        ctx.ignore_index = int(ignore_index)
+        return scratch[8]
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        from ._cabi import call, ptr, stream_ptr
+        grad_lov, labels, scratch = ctx.saved_tensors
+        n, c = grad_lov.shape
+        out = torch.empty_like(grad_lov)
+        call("ln_seg_loss_bwd", ptr(grad_lov), ptr(labels), ptr(scratch[8:]), ptr(grad_loss.contiguous()), n, c, ctx.ignore_index, ptr(out),
+             stream_ptr(out.device))
+        return out, None, None
+
+
 def segmentation_loss(logsoftmax, labels, ignore_index=-100):
-    """0.5 * Lovasz-softmax + 0.5 * NLL, as in ln_train.py:156-158."""
+    """0.5 * Lovasz-softmax + 0.5 * NLL, as in ln_train.py:156-158.  ShapeNet-sized clouds on the GPU run the fused
+    kernel; larger scans (and CPU tensors) the batched torch formulation above."""
+    if (logsoftmax.is_cuda and logsoftmax.dim() == 2 and logsoftmax.dtype == torch.float32 and labels.dtype == torch.int64
+            and labels.is_cuda and labels.is_contiguous() and 1 <= logsoftmax.shape[0] <= _fused_loss_max_points()):
+        return _SegLossFn.apply(logsoftmax, labels, ignore_index)
     nll = torch.nn.functional.nll_loss(logsoftmax, labels, ignore_index=ignore_index)
     lov = lovasz_softmax(logsoftmax.exp(), labels, ignore_index if ignore_index >= 0 else None)
     return 0.5 * lov + 0.5 * nll
+
+
+_MAX_POINTS = None
+
+
+def _fused_loss_max_points():
+    global _MAX_POINTS
+    if _MAX_POINTS is None:
+        from ._cabi import load
+        _MAX_POINTS = int(load().ln_seg_loss_max_points())
+    return _MAX_POINTS

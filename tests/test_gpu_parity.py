@@ -1249,3 +1249,76 @@ def test_scene_architecture_matches_cpu_port(name):
         if best_l2 <= TOL_GRADS:
             break
     assert best_l2 <= TOL_GRADS, f"{name} architecture: relative L2 error over all gradients, best of 4: {best_l2:.3e}"
+
+
+# ---- loss and optimizer kernels ------------------------------------------------------------------
+@pytest.mark.parametrize("n,nc,ignore", [(2048, 7, -100), (2000, 7, 2), (8192, 20, 0), (1, 3, -100), (1500, 50, -100)])
+def test_fused_segmentation_loss_vs_reference_formulation(n, nc, ignore):
+    """ln_seg_loss_fwd / _bwd against the per-class loop of the reference's LovaszSoftmax (lovasz_loss.py:41-72) plus
+    torch NLL, value (1e-5) and gradient w.r.t. the logits (1e-4 of the gradient scale; ties in the sort are broken
+    differently but errors of random logits do not tie)."""
+    from lattice_net_b200.losses import _SegLossFn, lovasz_softmax_loop, segmentation_loss
+    torch.manual_seed(n + nc)
+    logits = (torch.randn(n, nc, device="cuda") * 2.0).requires_grad_(True)
+    labels = torch.randint(0, max(nc - 2, 1), (n,), device="cuda")            # the last classes are absent
+    lsm = torch.log_softmax(logits, 1)
+    loss = segmentation_loss(lsm, labels, ignore)
+    assert isinstance(loss.grad_fn, _SegLossFn._backward_cls) or n > 8192
+    g, = torch.autograd.grad(loss * 3.0, logits)                               # upstream gradient != 1
+    logits64 = logits.detach().double().cpu().requires_grad_(True)
+    lsm64 = torch.log_softmax(logits64, 1)
+    lab = labels.cpu()
+    nll = torch.nn.functional.nll_loss(lsm64, lab, ignore_index=ignore)
+    lov = lovasz_softmax_loop(lsm64.exp(), lab, ignore if ignore >= 0 else None) if n > 1 or True else 0.0
+    ref = 0.5 * lov + 0.5 * nll
+    gr, = torch.autograd.grad(ref * 3.0, logits64)
+    assert abs(loss.item() - ref.item()) <= 1e-5 * max(abs(ref.item()), 1e-3), (loss.item(), ref.item())
+    assert_close(g.cpu().numpy(), gr.numpy(), 1e-4, "fused loss gradient")
+
+
+def test_flat_adamw_matches_torch_adamw_amsgrad():
+    """optim.FlatAdamW == torch.optim.AdamW(amsgrad=True) (ln_train.py:163-165) over several steps, including a skipped one."""
+    from lattice_net_b200.optim import FlatAdamW
+    from lattice_net_b200.parallel import GradBucket
+    torch.manual_seed(0)
+    shapes = [(288, 32), (32,), (7, 128), (1,), (1152, 128), (5, 3, 2)]
+    pa = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    ref = torch.optim.AdamW(pa, lr=1e-3, weight_decay=3e-4, amsgrad=True)
+    bucket = GradBucket(pb)
+    opt = FlatAdamW(bucket, lr=1e-3, weight_decay=3e-4)
+    skip = torch.zeros((), device="cuda")
+    opt.found_inf = skip
+    for it in range(6):
+        grads = [torch.randn(*s, device="cuda") * (0.1 + it) for s in shapes]
+        for p, q, g in zip(pa, pb, grads):
+            p.grad = g.clone()
+            q.grad = g.clone()
+        bucket.pack()
+        if it == 3:
+            skip.fill_(1.0)
+            before = [q.detach().clone() for q in pb]
+            opt.step()
+            skip.zero_()
+            assert all(torch.equal(a, q.detach()) for a, q in zip(before, pb)) and opt.steps_taken() == 3
+            continue
+        ref.step()
+        opt.step()
+        for p, q in zip(pa, pb):
+            assert_close(q.detach().cpu().numpy(), p.detach().cpu().numpy(), 2e-6, f"parameters after step {it}")
+    assert opt.steps_taken() == 5
+    # 1/world_size folded into the update
+    pc = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    pd = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    r2 = torch.optim.AdamW(pc, lr=1e-3, weight_decay=3e-4, amsgrad=True)
+    b2 = GradBucket(pd)
+    o2 = FlatAdamW(b2, lr=1e-3, weight_decay=3e-4)
+    for p, q, s in zip(pc, pd, shapes):
+        g = torch.randn(*s, device="cuda")
+        p.grad = g * 0.25
+        q.grad = g.clone()
+    b2.pack()
+    r2.step()
+    o2.step(grad_scale=0.25)
+    for p, q in zip(pc, pd):
+        assert_close(q.detach().cpu().numpy(), p.detach().cpu().numpy(), 2e-6, "grad_scale")
