@@ -24,17 +24,14 @@ class FlatAdamW:
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
         params = bucket.params
         dev = params[0].device
-        n = sum(p.numel() for p in params)
+        n = bucket.flat.numel()             # the bucket's layout (slices padded to 128-byte boundaries) is the layout of everything here
         self.n = n
-        self.flat_params = torch.empty((n,), dtype=torch.float32, device=dev)
-        off = 0
+        self.flat_params = torch.zeros((n,), dtype=torch.float32, device=dev)
         with torch.no_grad():
-            for p in params:
-                k = p.numel()
-                view = self.flat_params[off:off + k].view_as(p)
+            for p, off in zip(params, bucket.offsets):
+                view = self.flat_params[off:off + p.numel()].view_as(p)
                 view.copy_(p)
                 p.data = view               # the parameter now lives inside the flat buffer
-                off += k
         _lattice.invalidate_prepared_filters()      # prepared slabs and gradient targets are keyed by the old addresses
         bucket._registered = False
         self.exp_avg = torch.zeros_like(self.flat_params)

@@ -50,18 +50,18 @@ class GradBucket:
         self.params = [p for p in params if p.requires_grad]
         assert self.params, "no trainable parameters (run a warm-up forward first: they are created lazily)"
         dev = self.params[0].device
-        total = sum(p.numel() for p in self.params)
+        # every slice starts on a 128-byte boundary: the lattice kernels write weight gradients into the slices with
+        # 16-byte vector stores / reductions
+        self.offsets, total = [], 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += (p.numel() + 31) // 32 * 32
         # one extra trailing element rides along with the gradients in the same collective (a per-step flag,
         # e.g. "this rank's cloud exceeded its vertex bound", graphed.py)
         self.flat_with_extra = torch.zeros(total + 1, dtype=torch.float32, device=dev)
         self.flat = self.flat_with_extra[:total]
         self.extra = self.flat_with_extra[total:]
-        self.views = []
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            self.views.append(self.flat[off:off + n].view_as(p))
-            off += n
+        self.views = [self.flat[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
         self.nbytes = total * 4
         self._registered = False
         self._direct = False
@@ -77,11 +77,7 @@ class GradBucket:
         slices as `.grad` without a copy.  Pair with end_direct_step() after backward."""
         from . import lattice as _lattice
         if not self._registered:
-            off, targets = 0, {}
-            for p in self.params:
-                targets[p.data_ptr()] = (self.flat, off, tuple(p.shape))
-                off += p.numel()
-            _lattice.register_grad_targets(targets)
+            _lattice.register_grad_targets({p.data_ptr(): (self.flat, off, tuple(p.shape)) for p, off in zip(self.params, self.offsets)})
             self._registered = True
         self.flat_with_extra.zero_()
         for p in self.params:
