@@ -243,6 +243,25 @@ int ln_scatter_max(const float* src, const int* index, int m, int c, int nv,
 int ln_scatter_sum_count(const float* src, const int* index, int m, int c, int nv,
                          float* out_sum, float* out_count, void* stream);
 
+/* Fused distribute + PointNet front end (lattice_modules.py:52-96 + 620-733) without any per-row tensor: per-vertex mean
+ * position, centring, three weight-normalised Linear + LeakyReLU(0.2) layers evaluated per (point, simplex vertex) in
+ * registers, per-vertex max pooling, barycentric weight of each winning row, "< min_points" and vertex-0 masks.
+ *   out [nv_rows x 2*h3] = [ max | barycentric of the argmax row ],  arg [nv_rows x h3] = winning row (n*(pos_dim+1) = none)
+ * layer_ptrs: HOST array of 9 device pointers (weight_v [out x in], weight_g [out], bias [out]) x 3 layers.
+ * scratch_zeroed: ln_pointnet_scratch_floats() zeroed floats (kept for the backward: its head holds the per-vertex sums).
+ * Built for pos_dim 3 (4..8 input features) and 5 (6..9), widths 16/32/64 (every reference config); query with
+ * ln_pointnet_supported().  Backward: grad_ptrs = HOST array of the 9 gradient destinations (overwritten);
+ * grad_scratch_zeroed: ln_pointnet_grad_scratch_floats() zeroed floats. */
+int ln_pointnet_supported(int pos_dim, int val_dim, int h1, int h2, int h3);
+long long ln_pointnet_scratch_floats(int pos_dim, int nv_rows, int h3);
+long long ln_pointnet_grad_scratch_floats(int pos_dim, int val_dim, int h1, int h2, int h3);
+int ln_pointnet_fwd(const float* positions_raw, const float* sigmas, const float* values, const int* indices, const float* weights,
+                    int n, int pos_dim, int val_dim, const float* const* layer_ptrs, int h1, int h2, int h3, int nv_rows,
+                    int vertex0_quirk, int min_points, float* scratch_zeroed, float* out, int* arg, void* stream);
+int ln_pointnet_bwd(const float* positions_raw, const float* sigmas, const float* values, const int* indices, int n, int pos_dim,
+                    int val_dim, const float* const* layer_ptrs, float* const* grad_ptrs, int h1, int h2, int h3, int vertex0_quirk,
+                    const float* fwd_scratch, const float* grad_reduced, const int* arg, float* grad_scratch_zeroed, void* stream);
+
 /* ---- normalisation between lattice convolutions -----------------------
  * GroupNorm (+ optional fused ReLU) on vertex-major lattice values x [nv x c]: statistics per group over
  * (c/groups channels) x (all nv vertices), biased variance -- torch.nn.GroupNorm(groups, c) applied to the

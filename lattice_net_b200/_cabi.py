@@ -49,10 +49,15 @@ _F = ctypes.c_float
 _SIGNATURES.update({
     "ln_seg_loss_fwd": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "ln_seg_loss_bwd": [_P, _P, _P, _P, _I, _I, _I, _P, _P],
+    "ln_pointnet_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "ln_pointnet_bwd": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "ln_adamw_amsgrad": [_P, _P, _P, _P, _P, ctypes.c_longlong, _F, _F, _F, _F, _F, _F, _P, _P, _P],
 })
 _SPECIAL = {
     "ln_seg_loss_max_points": (ctypes.c_int, []),
+    "ln_pointnet_supported": (ctypes.c_int, [_I, _I, _I, _I, _I]),
+    "ln_pointnet_scratch_floats": (ctypes.c_longlong, [_I, _I, _I]),
+    "ln_pointnet_grad_scratch_floats": (ctypes.c_longlong, [_I, _I, _I, _I, _I]),
     "ln_version": (ctypes.c_char_p, []),
     "ln_last_error": (ctypes.c_char_p, []),
     "ln_launch_count": (ctypes.c_longlong, []),

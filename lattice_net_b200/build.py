@@ -10,7 +10,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "liblattice_b200.so")
-SOURCES = ["ln_api.cu", "ln_hash_splat.cu", "ln_neighbours.cu", "ln_slice.cu", "ln_conv.cu", "ln_conv_tc.cu", "ln_norm.cu", "ln_train.cu"]
+SOURCES = ["ln_api.cu", "ln_hash_splat.cu", "ln_neighbours.cu", "ln_slice.cu", "ln_conv.cu", "ln_conv_tc.cu", "ln_norm.cu", "ln_train.cu", "ln_pointnet.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

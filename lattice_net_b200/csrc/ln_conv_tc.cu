@@ -567,8 +567,14 @@ cudaError_t allow_max_smem(const void* kernel) {
     if (err != cudaSuccess) return err;
     std::lock_guard<std::mutex> lock(mu);
     if (done.count({dev, kernel})) return cudaSuccess;
-    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (err == cudaSuccess) done.insert({dev, kernel});
+    cudaFuncAttributes attr;
+    err = cudaFuncGetAttributes(&attr, kernel);          // static shared memory counts against the same 227 KB
+    if (err == cudaSuccess)
+        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)attr.sharedSizeBytes);
+    if (err == cudaSuccess)
+        done.insert({dev, kernel});
+    else
+        cudaGetLastError();                               // do not leave a sticky error behind for the next runtime call
     return err;
 }
 static int sm_count() {

@@ -716,6 +716,40 @@ class Lattice:
         st.mark_dirty()
         return new, distributed, idx, w
 
+    def distribute_structure(self, positions_raw, values, reset_hashmap=True):
+        """`distribute` without its [N(d+1) x (d+V+1)] rows (extension): -> (distributed_lattice, indices, weights).  The
+        fused PointNet front end (lattice_modules.PointNetModule.forward_fused) evaluates the rows on the fly instead."""
+        _check(positions_raw.shape[0] == values.shape[0], "positions and values need the same number of rows")
+        self._check_positions(positions_raw)
+        self._check_values(values)
+        device = self._device_of(positions_raw)
+        n, d = positions_raw.shape
+        v = values.shape[1]
+        self.m_positions = positions_raw
+        ht = self.m_hash_table
+        if not ht.is_initialized():
+            ht.init(d, v, device)
+        parent = ht.structure
+        dev = parent.device
+        pos = _as_cuda_f32(positions_raw, dev)
+        new = self.clone_lattice()
+        new.m_name = "distributed_lattice"
+        bound = self._bound_for(self.m_lvl)
+        if reset_hashmap:
+            new.m_hash_table.structure = _Structure(parent.capacity, d, dev, zero_keys=bound is None, bound=bound)
+        else:
+            new.m_hash_table.structure = parent.copy()
+            new.m_hash_table.structure.bound = bound
+        new.m_hash_table.m_values_tensor = torch.zeros((1, v), dtype=torch.float32, device=dev)      # replaced by the PointNet output
+        st = new.m_hash_table.structure
+        idx = torch.empty((n * (d + 1),), dtype=torch.int32, device=dev)
+        w = torch.empty((n * (d + 1),), dtype=torch.float32, device=dev)
+        if n > 0:
+            call("ln_splat_build", ptr(pos), ptr(self._sigmas_on(dev)), n, d, ptr(st.keys), ptr(st.entries),
+                 ptr(st.nr_filled), ptr(st.status), st.capacity, st.bound or 0, ptr(idx), ptr(w), stream_ptr(dev))
+        st.mark_dirty()
+        return new, idx, w
+
     def expand(self, positions_raw, point_multiplier, noise_stddev, expand_values):
         # Lattice::expand, Lattice.cu:292-348
         self._check_positions(positions_raw)

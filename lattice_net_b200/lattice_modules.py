@@ -169,6 +169,52 @@ class _LinearFn(torch.autograd.Function):
         return dx, dw, db, (dy if (ctx.has_residual and ctx.needs_input_grad[3]) else None)
 
 
+class _PointNetFusedFn(torch.autograd.Function):
+    """(positions, values, indices, weights, sigmas, nv_rows, quirk, v0, g0, b0, v1, g1, b1, v2, g2, b2) -> [nv_rows x 2*64]"""
+
+    @staticmethod
+    def forward(ctx, positions, values, indices, weights, sigmas, nv_rows, quirk, *params):
+        import ctypes
+        from ._cabi import load
+        lib = load()
+        n, d = positions.shape
+        v = values.shape[1]
+        dev = positions.device
+        widths = [int(params[3 * l].shape[0]) for l in range(3)]
+        scratch = torch.zeros((int(lib.ln_pointnet_scratch_floats(d, int(nv_rows), widths[2])),), dtype=torch.float32, device=dev)
+        out = torch.empty((nv_rows, 2 * widths[2]), dtype=torch.float32, device=dev)
+        arg = torch.empty((nv_rows, widths[2]), dtype=torch.int32, device=dev)
+        ps = [p.contiguous() for p in params]
+        ptrs = (ctypes.c_void_p * 9)(*[p.data_ptr() for p in ps])
+        call("ln_pointnet_fwd", ptr(positions), ptr(sigmas), ptr(values), ptr(indices), ptr(weights), n, d, v, ptrs, widths[0], widths[1],
+             widths[2], int(nv_rows), 1 if quirk else 0, 4, ptr(scratch), ptr(out), ptr(arg), stream_ptr(dev))
+        ctx.save_for_backward(positions, values, indices, sigmas, scratch, arg, *ps)
+        ctx.quirk, ctx.widths = bool(quirk), widths
+        ctx.mark_non_differentiable(arg)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        import ctypes
+        from ._cabi import load
+        positions, values, indices, sigmas, scratch, arg = ctx.saved_tensors[:6]
+        ps = ctx.saved_tensors[6:]
+        n, d = positions.shape
+        v = values.shape[1]
+        dev = positions.device
+        w = ctx.widths
+        gscratch = torch.zeros((int(load().ln_pointnet_grad_scratch_floats(d, v, w[0], w[1], w[2])),), dtype=torch.float32, device=dev)
+        grads = []
+        for p in ps:
+            t = _lattice.grad_target(p)
+            grads.append(t if t is not None else torch.empty_like(p))
+        ptrs = (ctypes.c_void_p * 9)(*[p.data_ptr() for p in ps])
+        gptrs = (ctypes.c_void_p * 9)(*[g.data_ptr() for g in grads])
+        call("ln_pointnet_bwd", ptr(positions), ptr(sigmas), ptr(values), ptr(indices), n, d, v, ptrs, gptrs, w[0], w[1], w[2],
+             1 if ctx.quirk else 0, ptr(scratch), ptr(grad_out.contiguous()), ptr(arg), ptr(gscratch), stream_ptr(dev))
+        return (None,) * 7 + tuple(grads)
+
+
 def linear(x, weight, bias=None, residual=None):
     """F.linear(x, weight, bias) (+ residual) on the lattice kernels (CUDA fp32 2-D inputs), torch elsewhere."""
     if x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and weight.dtype == torch.float32:
@@ -545,6 +591,40 @@ class PointNetModule(torch.nn.Module):
                     lin.bias.zero_()
                 self.layers.append(lin)
                 nr_in = nr_out
+
+    def _init_layers(self, nr_in, device):
+        if self.first_time:
+            self.first_time = False
+            for nr_out in self.nr_output_channels_per_layer:
+                lin = LinearWN(nr_in, nr_out, bias=True).to(device)
+                leaky_relu_init_(lin.weight_v, nr_in + nr_out)
+                with torch.no_grad():
+                    lin.weight_g.fill_(float(lin.weight_v.norm()))
+                    lin.bias.zero_()
+                self.layers.append(lin)
+                nr_in = nr_out
+
+    def fused_supported(self, pos_dim, val_dim):
+        from ._cabi import load
+        w = self.nr_output_channels_per_layer
+        return len(w) == 3 and bool(load().ln_pointnet_supported(int(pos_dim), int(val_dim), int(w[0]), int(w[1]), int(w[2])))
+
+    def forward_fused(self, lattice_py, positions, values, indices, weights):
+        """distribute rows + mean subtraction + MLP + per-vertex max pooling + masks in three kernels, without the
+        [N(d+1) x ...] tensors (csrc/ln_pointnet.cu); then the lattice convolution and activation as in forward()."""
+        self._init_layers(positions.shape[1] + values.shape[1], positions.device)
+        st = lattice_py.m_hash_table.structure
+        nv_rows = lattice_py.nr_lattice_vertices()
+        params = []
+        for layer in self.layers:
+            params += [layer.weight_v, layer.weight_g, layer.bias]
+        reduced = _PointNetFusedFn.apply(positions.contiguous(), values.contiguous(), indices, weights, lattice_py._sigmas_on(st.device),
+                                         nv_rows, REFERENCE_VERTEX0_QUIRK, *params)
+        lattice_py.set_values(reduced)
+        lv, ls = self.last_conv(reduced, lattice_py)
+        lv = self.act(lv)
+        ls.set_values(lv)
+        return lv, ls
 
     def forward(self, lattice_py, distributed, indices):
         if self.first_time:

@@ -51,7 +51,7 @@ def lovasz_softmax_loop(probas, labels, ignore_index=None):
     for c in range(probas.shape[1]):
         if c == ignore_index:
             continue
-        fg = (labels == c).float()
+        fg = (labels == c).to(probas.dtype)
         if fg.sum() == 0:
             continue
         errors = (fg - probas[:, c]).abs()

@@ -26,6 +26,7 @@ class LNN(torch.nn.Module):
         compression = mp.compression_factor()
         log = print if verbose else (lambda *a, **k: None)
 
+        self.fused_point_net = True      # False: the module-by-module path of the reference (distribute rows, torch MLP, scatter ops)
         self.distribute = DistributeLatticeModule()
         self.pointnet_channels_per_layer = list(mp.pointnet_channels_per_layer())
         self.start_nr_filters = mp.pointnet_start_nr_channels()
@@ -87,11 +88,20 @@ class LNN(torch.nn.Module):
             # tensor-core slabs of every filter bank / 1x1 weight, forward and transposed readings, in one launch
             # (nothing is launched while the weights have not changed since the last call)
             _lattice.prepare_filters(filter_readings(self, torch.is_grad_enabled()))
-        with torch.no_grad():
-            ls, distributed, indices, weights = self.distribute(ls, positions, values)
-        self.last_level1_lattice = ls          # kept for inspection / tests (vertex numbering of this pass)
-        self.last_level_lattices = [ls]        # one handle per lattice level of this pass (level 1 first)
-        lv, ls = self.point_net(ls, distributed, indices)
+        if positions.is_cuda and self.fused_point_net and self.point_net.fused_supported(positions.shape[1], values.shape[1]):
+            # distribute + PointNet without the [N(d+1) x ...] row tensors (csrc/ln_pointnet.cu)
+            with torch.no_grad():
+                ls.begin_splat(True)
+                ls, indices, weights = ls.distribute_structure(positions, values, True)
+            self.last_level1_lattice = ls
+            self.last_level_lattices = [ls]
+            lv, ls = self.point_net.forward_fused(ls, positions, values, indices, weights)
+        else:
+            with torch.no_grad():
+                ls, distributed, indices, weights = self.distribute(ls, positions, values)
+            self.last_level1_lattice = ls          # kept for inspection / tests (vertex numbering of this pass)
+            self.last_level_lattices = [ls]        # one handle per lattice level of this pass (level 1 first)
+            lv, ls = self.point_net(ls, distributed, indices)
 
         fine_structures, fine_values = [], []
         for lvl in range(self.nr_downsamples):

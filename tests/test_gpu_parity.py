@@ -1232,7 +1232,7 @@ def test_scene_architecture_matches_cpu_port(name):
         l1 = model.last_level1_lattice
         keys = l1.hash_table().m_keys_tensor[:l1.nr_lattice_vertices()].cpu().numpy()
         if cpu is None:
-            cpu = cpu_port.CpuLNN(spec["nr_classes"], mp)
+            cpu = cpu_port.CpuLNN(spec["nr_classes"], mp, val_dim=spec["val_dim"])
             cpu.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()}, strict=True)
         for p in cpu.parameters():
             p.grad = None
@@ -1322,3 +1322,47 @@ def test_flat_adamw_matches_torch_adamw_amsgrad():
     o2.step(grad_scale=0.25)
     for p, q in zip(pc, pd):
         assert_close(q.detach().cpu().numpy(), p.detach().cpu().numpy(), 2e-6, "grad_scale")
+
+
+@pytest.mark.parametrize("quirk", [True, False])
+@pytest.mark.parametrize("val_dim", [1, 4])
+def test_fused_pointnet_matches_the_module_by_module_path(built, val_dim, quirk):
+    """csrc/ln_pointnet.cu (no per-row tensors) against the reference-shaped path of this repo -- distribute rows, scatter
+    mean, torch MLP with weight norm, scatter max, index_select, masks (lattice_modules.py:52-96, 620-733) -- on the SAME
+    lattice structure: pooled features + the convolution after them to 1e-5, every parameter gradient to 1e-4."""
+    from lattice_net_b200 import lattice_modules as lm
+    b = built
+    if b["name"] == "boundary":
+        pytest.skip("two clouds cover it")
+    d = b["d"]
+    torch.manual_seed(11)
+    vals = cuda(cases.randn((b["n"], val_dim), 700 + val_dim))
+    saved = lm.REFERENCE_VERTEX0_QUIRK
+    lm.REFERENCE_VERTEX0_QUIRK = quirk
+    try:
+        lat = _lattice(b["spec"])
+        with torch.no_grad():
+            dl, distributed, idx, w = lm.DistributeLatticeModule()(lat, b["pos"], vals)
+        pn = lm.PointNetModule([16, 32, 64], 32, device=torch.device("cuda", 0))
+        assert pn.fused_supported(d, val_dim)
+        with torch.no_grad():
+            pn._init_layers(d + val_dim, b["pos"].device)
+            for layer in pn.layers:                      # non-trivial gains / biases
+                layer.weight_g.mul_(torch.rand_like(layer.weight_g) + 0.5)
+                layer.bias.uniform_(-0.2, 0.2)
+        nv = dl.nr_lattice_vertices()
+        g = torch.randn((nv, 32), device="cuda")
+        results = []
+        for fused in (False, True):
+            for p in pn.parameters():
+                p.grad = None
+            handle = dl.clone_lattice()
+            lv, _ = pn.forward_fused(handle, b["pos"], vals, idx, w) if fused else pn(handle, distributed.clone(), idx)
+            pooled = handle.values() if not fused else None
+            (lv * g).sum().backward()
+            results.append((lv.detach().cpu().numpy(), {n_: p.grad.detach().cpu().numpy().copy() for n_, p in pn.named_parameters()}))
+        assert_close(results[1][0], results[0][0], 1e-5, "PointNet + first convolution output")
+        for name, ga in results[0][1].items():
+            assert_close(results[1][1][name], ga, 1e-4, f"fused PointNet gradient of {name}")
+    finally:
+        lm.REFERENCE_VERTEX0_QUIRK = saved

@@ -30,7 +30,8 @@ def _worker(rank, world, port, out):
     gathered = [torch.zeros_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
     expected = sum(gathered) / world
-    ok = torch.allclose(bucket.flat, expected) and all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in model.parameters())
+    reduced = torch.cat([v.reshape(-1) for v in bucket.views])      # the flat buffer pads every slice to a 128-byte boundary
+    ok = torch.allclose(reduced, expected) and all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in model.parameters())
     w0 = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
     ws = [torch.zeros_like(w0) for _ in range(world)]
     dist.all_gather(ws, w0)
@@ -62,6 +63,7 @@ def test_bucket_pack_aliases_grads():
     model(torch.ones(1, 3)).sum().backward()
     expect = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
     bucket.pack()
-    assert torch.equal(bucket.flat, expect)
+    assert torch.equal(torch.cat([v.reshape(-1) for v in bucket.views]), expect)
+    assert all(off % 32 == 0 for off in bucket.offsets) and float(bucket.flat.sum()) == float(expect.sum())     # padding stays zero
     lo, hi = bucket.flat.data_ptr(), bucket.flat.data_ptr() + bucket.nbytes
     assert all(lo <= p.grad.data_ptr() < hi for p in model.parameters())
