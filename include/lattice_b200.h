@@ -48,6 +48,9 @@ const char* ln_last_error(void);
  * (bench.py reports it as `gpu_launches`). */
 long long ln_launch_count(void);
 void ln_reset_launch_count(void);
+/* Programmatic dependent launch of this library's kernels (on by default; see ln_common.cuh): 0 launches them with plain
+ * stream ordering.  Returns the previous setting.  Results are identical either way. */
+int ln_set_programmatic_launch(int enabled);
 
 /* ---- hash table ---------------------------------------------------------------------------
  * Replaces HashTable::clear() (/root/reference/src/HashTable.cu:49-57) for the structural

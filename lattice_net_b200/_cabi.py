@@ -65,6 +65,7 @@ _SPECIAL = {
     "ln_conv_needs_zero": (ctypes.c_int, [_I, _I, _I, _I, _I]),
     "ln_group_norm_workspace_bytes": (ctypes.c_longlong, [_I, _I, _I]),
     "ln_reset_launch_count": (None, []),
+    "ln_set_programmatic_launch": (ctypes.c_int, [_I]),
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + list(_SPECIAL))
 

@@ -27,6 +27,9 @@ int check_launch(const char* what) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+static std::atomic<int> g_pdl{1};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+
 }  // namespace ln
 
 extern "C" {
@@ -35,6 +38,10 @@ const char* ln_version(void) { return "lattice_b200 0.1 sm_100a"; }
 const char* ln_last_error(void) { return ln::g_error; }
 long long ln_launch_count(void) { return ln::g_launches.load(std::memory_order_relaxed); }
 void ln_reset_launch_count(void) { ln::g_launches.store(0, std::memory_order_relaxed); }
+int ln_set_programmatic_launch(int enabled) {
+    const int prev = ln::g_pdl.exchange(enabled ? 1 : 0, std::memory_order_relaxed);
+    return prev;
+}
 
 int ln_table_status(const int* nr_filled, const int* status, int* nr_filled_host, int* max_probe_host, void* stream) {
     LN_REQUIRE(nr_filled && nr_filled_host, "ln_table_status: null pointer");

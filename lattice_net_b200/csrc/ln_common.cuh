@@ -30,6 +30,41 @@ int launch_scatter_rows(const float* src, const int* indices, const float* weigh
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A ShapeNet-sized training step is a chain of ~450 kernels of a few microseconds each,
+// so the launch latency between two dependent kernels is a first-order cost.  Every kernel of this library signals
+// `launch_dependents` as its first instruction and waits for its predecessors (`griddepcontrol.wait`: all prerequisite
+// grids complete, their memory visible) before its first global-memory access; launched through launch_k() with the
+// programmatic-stream-serialization attribute, the NEXT kernel's launch, CTA scheduling and on-chip prologue (barrier
+// initialisation, TMEM allocation, weight staging in shared memory that does not depend on earlier kernels) overlap the
+// tail of the current one.  Inside a stream capture the attribute becomes a programmatic graph edge.
+// Rules kept by every kernel: (1) no global read or write before pdl_wait(); (2) every thread reaches pdl_wait() (no
+// early return before it), so a grid can never complete before its predecessor has.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#define LN_PDL_ENTRY()       \
+    do {                     \
+        ::ln::pdl_trigger(); \
+        ::ln::pdl_wait();    \
+    } while (0)
+
+bool pdl_enabled();   // ln_api.cu; ln_set_programmatic_launch()
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 constexpr int kEmpty = -1;   // entries[] states, HashTableGPU.cuh:24-26
 constexpr int kLocked = -2;
 

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(kThreads)
 conv_fwd_simt_kernel(const float* __restrict__ values, const int* __restrict__ neighbours,
                      const float* __restrict__ filter, const float* __restrict__ bias, const float* __restrict__ residual,
                      int nv_query, int F, int c_in, int c_out, int flip, int transposed, float* __restrict__ out) {
+    LN_PDL_ENTRY();
     __shared__ float a_sh[BK][BM + 4];
     __shared__ float b_sh[BK][BN + 4];
     __shared__ int nbr_sh[BM];
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(kThreads)
 conv_wgrad_simt_kernel(const float* __restrict__ values, const int* __restrict__ neighbours,
                        const float* __restrict__ grad_out, int nv_query, int F, int c_in, int c_out, int q_chunk,
                        int co_tiles, float* __restrict__ grad_filter) {
+    LN_PDL_ENTRY();
     __shared__ float a_sh[BK][BM + 4];   // [q][ci]
     __shared__ float g_sh[BK][BN + 4];   // [q][co]
     const int slot = blockIdx.z;
@@ -235,7 +237,7 @@ int conv_wgrad_launch(const float* nbr_values, const int* neighbours, const floa
     int q_chunk = cdiv(cdiv(nv_query, chunks), BK) * BK;
     chunks = cdiv(nv_query, q_chunk);
     dim3 grid(chunks, ci_tiles * co_tiles, filter_extent);
-    conv_wgrad_simt_kernel<<<grid, kThreads, 0, s>>>(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, q_chunk, co_tiles, grad_filter);
+    launch_k(conv_wgrad_simt_kernel, dim3(grid), dim3(kThreads), 0, s, nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, q_chunk, co_tiles, grad_filter);
     count_launch();
     return check_launch("conv_wgrad_simt");
 }
@@ -259,7 +261,7 @@ int conv_launch(const float* nbr_values, const int* neighbours, const float* fil
         return conv_fwd_tc(nbr_values, neighbours, slabs, bias, residual, nv_query, filter_extent, c_in, c_out, flip, precision, out, s);
     }
     dim3 grid(cdiv(nv_query, BM), cdiv(c_out, BN));
-    conv_fwd_simt_kernel<<<grid, kThreads, 0, s>>>(nbr_values, neighbours, filter, bias, residual, nv_query, filter_extent, c_in, c_out, flip,
+    launch_k(conv_fwd_simt_kernel, dim3(grid), dim3(kThreads), 0, s, nbr_values, neighbours, filter, bias, residual, nv_query, filter_extent, c_in, c_out, flip,
                                                    transposed_filter, out);
     count_launch();
     return check_launch(what);

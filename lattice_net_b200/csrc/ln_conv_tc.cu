@@ -218,12 +218,14 @@ __device__ __forceinline__ void filter_prep_element(const FilterPrepJob& j, long
 }
 
 __global__ void __launch_bounds__(256) filter_prep_kernel(FilterPrepJob job) {
+    LN_PDL_ENTRY();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < (long long)job.k_total * prep_n_pad_sum(job.c_out)) filter_prep_element(job, t);
 }
 
 // all banks of a model in ONE launch: jobs[] lives in device memory, sorted by first_thread
 __global__ void __launch_bounds__(256) filter_prep_batch_kernel(const FilterPrepJob* __restrict__ jobs, int n_jobs, long long total) {
+    LN_PDL_ENTRY();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     int lo = 0, hi = n_jobs - 1;              // last job whose first_thread <= t
@@ -259,6 +261,7 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
                 const float* __restrict__ b_hi, const float* __restrict__ b_lo, const float* __restrict__ bias,
                 const float* __restrict__ residual, int nv_query, int F, int c_in, int c_out, int ld_out, int n_pad, int flip,
                 int stages, int lookahead, int m_tiles, int n_items, int kb_per_split, float* __restrict__ out) {
+    pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t b_tile_bytes = (uint32_t)n_pad * kRowBytes;
     const uint32_t stage_bytes = (kSplit ? 2 : 1) * (kATileBytes + b_tile_bytes);
@@ -299,6 +302,7 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();          // everything above ran while the previous kernel was still finishing; global memory from here on
 
     const int cpb = c_in / kBlockK;          // K blocks per slot
     const int total_kb = F * cpb;
@@ -590,14 +594,14 @@ static int sm_count() {
 int filter_prepare(const float* filter, int F, int c_in, int c_out, int transposed, int precision, float* slabs, cudaStream_t s) {
     FilterPrepJob job{filter, slabs, F * c_in, c_in, c_out, transposed, precision == 1 ? 1 : 0, 0, 0};
     const long long total = (long long)job.k_total * prep_n_pad_sum(c_out);
-    filter_prep_kernel<<<cdiv(total, 256), 256, 0, s>>>(job);
+    launch_k(filter_prep_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, job);
     count_launch();
     return check_launch("filter_prep");
 }
 
 int filter_prepare_batch(const void* jobs_device, int n_jobs, long long total_threads, cudaStream_t s) {
     if (n_jobs <= 0 || total_threads <= 0) return LN_OK;
-    filter_prep_batch_kernel<<<cdiv(total_threads, 256), 256, 0, s>>>((const FilterPrepJob*)jobs_device, n_jobs, total_threads);
+    launch_k(filter_prep_batch_kernel, dim3(cdiv(total_threads, 256)), dim3(256), 0, s, (const FilterPrepJob*)jobs_device, n_jobs, total_threads);
     count_launch();
     return check_launch("filter_prep_batch");
 }
@@ -637,6 +641,7 @@ conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ n
                      const float* __restrict__ grad_out, int nv_query, int F, int c_in, int c_out, int ld_g, int n_pad,
                      int ci_tiles, int q_splits, int chunks_per_split, int stages, int lookahead,
                      float* __restrict__ grad_filter) {
+    pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int n_groups = (n_pad + 31) / 32;
     const uint32_t a_bytes = 4u * kWgGroupBytes;                       // 128 channels x 32 vertices = 16 KB
@@ -683,6 +688,7 @@ conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ n
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp < 8) {
         // ================= producers: one vertex row per thread-octet =================
@@ -882,12 +888,12 @@ static int conv_wgrad_tc_chunk(const float* nbr_values, const int* neighbours, c
     if (split) {
         err = allow_max_smem((const void*)conv_wgrad_tc_kernel<1>);
         if (err == cudaSuccess)
-            conv_wgrad_tc_kernel<1><<<grid, kWgThreads, smem, s>>>(nbr_values, neighbours, grad_out, nv_query, F, c_in, c_out, ld_g, n_pad, ci_tiles,
+            launch_k(conv_wgrad_tc_kernel<1>, dim3(grid), dim3(kWgThreads), smem, s, nbr_values, neighbours, grad_out, nv_query, F, c_in, c_out, ld_g, n_pad, ci_tiles,
                                                                     q_splits, chunks_per_split, stages, lookahead, grad_filter);
     } else {
         err = allow_max_smem((const void*)conv_wgrad_tc_kernel<0>);
         if (err == cudaSuccess)
-            conv_wgrad_tc_kernel<0><<<grid, kWgThreads, smem, s>>>(nbr_values, neighbours, grad_out, nv_query, F, c_in, c_out, ld_g, n_pad, ci_tiles,
+            launch_k(conv_wgrad_tc_kernel<0>, dim3(grid), dim3(kWgThreads), smem, s, nbr_values, neighbours, grad_out, nv_query, F, c_in, c_out, ld_g, n_pad, ci_tiles,
                                                                     q_splits, chunks_per_split, stages, lookahead, grad_filter);
     }
     if (err != cudaSuccess) {
@@ -956,12 +962,12 @@ static int conv_fwd_tc_chunk(const float* nbr_values, const int* neighbours, con
     if (split) {
         err = allow_max_smem((const void*)conv_tc2_kernel<1>);
         if (err == cudaSuccess)
-            conv_tc2_kernel<1><<<grid, kTc2Threads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias_chunk, res_chunk, nv_query, F, c_in, c_out, ld_n,
+            launch_k(conv_tc2_kernel<1>, dim3(grid), dim3(kTc2Threads), smem, s, nbr_values, neighbours, b_hi, b_lo, bias_chunk, res_chunk, nv_query, F, c_in, c_out, ld_n,
                                                                 n_pad, flip, stages, lookahead, m_tiles, n_items, kb_per_split, out_chunk);
     } else {
         err = allow_max_smem((const void*)conv_tc2_kernel<0>);
         if (err == cudaSuccess)
-            conv_tc2_kernel<0><<<grid, kTc2Threads, smem, s>>>(nbr_values, neighbours, b_hi, b_lo, bias_chunk, res_chunk, nv_query, F, c_in, c_out, ld_n,
+            launch_k(conv_tc2_kernel<0>, dim3(grid), dim3(kTc2Threads), smem, s, nbr_values, neighbours, b_hi, b_lo, bias_chunk, res_chunk, nv_query, F, c_in, c_out, ld_n,
                                                                 n_pad, flip, stages, lookahead, m_tiles, n_items, kb_per_split, out_chunk);
     }
     if (err != cudaSuccess) {

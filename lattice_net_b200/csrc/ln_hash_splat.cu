@@ -13,6 +13,7 @@ constexpr unsigned kFull = 0xffffffffu;
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) table_clear_kernel(int4* __restrict__ entries4, int* __restrict__ entries,
                                                              int* nr_filled, int* status, int capacity) {
+    LN_PDL_ENTRY();
     const int n4 = capacity >> 2;
     const int stride = gridDim.x * blockDim.x;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(kBlock)
 splat_build_kernel(const float* __restrict__ positions_raw, const float* __restrict__ sigmas,
                    const float* __restrict__ values, int n, int val_dim, TableView table,
                    int* __restrict__ indices, float* __restrict__ weights, float* __restrict__ distributed) {
+    LN_PDL_ENTRY();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool valid = idx < n;
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(kBlock)
 splat_accumulate_small_kernel(const float* __restrict__ values, const int* __restrict__ indices,
                               const float* __restrict__ weights, int n, int spv /* D+1 */,
                               float* __restrict__ lattice_values) {
+    LN_PDL_ENTRY();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)n * spv;
     const bool valid = t < total;
@@ -202,6 +205,7 @@ splat_accumulate_small_kernel(const float* __restrict__ values, const int* __res
 template <int D>
 __global__ void __launch_bounds__(kBlock)
 coarsen_kernel(ConstTableView fine, const int* __restrict__ fine_nr_filled, TableView coarse, int nv_upper) {
+    LN_PDL_ENTRY();
     constexpr int kTasks = 1 + 2 * (D + 1);
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int v = (int)(t / kTasks);
@@ -245,11 +249,11 @@ static int launch_splat_build(const float* positions_raw, const float* sigmas, c
     if (n == 0) return LN_OK;
     const int grid = cdiv(n, kBlock);
     if (distributed != nullptr)
-        splat_build_kernel<D, true, true><<<grid, kBlock, 0, s>>>(positions_raw, sigmas, values, n, val_dim, t, indices, weights, distributed);
+        launch_k((splat_build_kernel<D, true, true>), dim3(grid), dim3(kBlock), 0, s, positions_raw, sigmas, values, n, val_dim, t, indices, weights, distributed);
     else if (insert)
-        splat_build_kernel<D, false, true><<<grid, kBlock, 0, s>>>(positions_raw, sigmas, values, n, val_dim, t, indices, weights, nullptr);
+        launch_k((splat_build_kernel<D, false, true>), dim3(grid), dim3(kBlock), 0, s, positions_raw, sigmas, values, n, val_dim, t, indices, weights, nullptr);
     else
-        splat_build_kernel<D, false, false><<<grid, kBlock, 0, s>>>(positions_raw, sigmas, values, n, val_dim, t, indices, weights, nullptr);
+        launch_k((splat_build_kernel<D, false, false>), dim3(grid), dim3(kBlock), 0, s, positions_raw, sigmas, values, n, val_dim, t, indices, weights, nullptr);
     count_launch();
     return check_launch("splat_build");
 }
@@ -263,7 +267,7 @@ extern "C" {
 int ln_table_clear(int* entries, int* nr_filled, int* status, int capacity, void* stream) {
     LN_REQUIRE(entries && nr_filled && status && capacity > 0, "ln_table_clear: bad argument");
     const int grid = min(cdiv(max(capacity / 4, 1), kBlock), 148 * 8);
-    table_clear_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(reinterpret_cast<int4*>(entries), entries, nr_filled, status, capacity);
+    launch_k(table_clear_kernel, dim3(grid), dim3(kBlock), 0, (cudaStream_t)stream, reinterpret_cast<int4*>(entries), entries, nr_filled, status, capacity);
     count_launch();
     return check_launch("table_clear");
 }
@@ -325,9 +329,9 @@ int ln_splat_accumulate(const float* values, const int* indices, const float* we
     const long long rows = (long long)n * spv;
     if (val_dim <= 3) {
         const int grid = cdiv(rows, kBlock);
-        if (val_dim == 1) splat_accumulate_small_kernel<1><<<grid, kBlock, 0, s>>>(values, indices, weights, n, spv, lattice_values);
-        if (val_dim == 2) splat_accumulate_small_kernel<2><<<grid, kBlock, 0, s>>>(values, indices, weights, n, spv, lattice_values);
-        if (val_dim == 3) splat_accumulate_small_kernel<3><<<grid, kBlock, 0, s>>>(values, indices, weights, n, spv, lattice_values);
+        if (val_dim == 1) launch_k(splat_accumulate_small_kernel<1>, dim3(grid), dim3(kBlock), 0, s, values, indices, weights, n, spv, lattice_values);
+        if (val_dim == 2) launch_k(splat_accumulate_small_kernel<2>, dim3(grid), dim3(kBlock), 0, s, values, indices, weights, n, spv, lattice_values);
+        if (val_dim == 3) launch_k(splat_accumulate_small_kernel<3>, dim3(grid), dim3(kBlock), 0, s, values, indices, weights, n, spv, lattice_values);
     } else {
         // general V: the same scatter as the backward of slice (ln_slice.cu)
         return launch_scatter_rows(values, indices, weights, n, pos_dim, val_dim, nr_vertices, lattice_values, s, "splat_accumulate");
@@ -348,9 +352,9 @@ int ln_coarsen_keys(const int* fine_keys, const int* fine_entries, const int* fi
                      vertex_bound(coarse_max_vertices, coarse_capacity)};
     cudaStream_t s = (cudaStream_t)stream;
     if (pos_dim == 3)
-        coarsen_kernel<3><<<cdiv((long long)nv_fine_upper * 9, kBlock), kBlock, 0, s>>>(fine, fine_nr_filled, coarse, nv_fine_upper);
+        launch_k(coarsen_kernel<3>, dim3(cdiv((long long)nv_fine_upper * 9, kBlock)), dim3(kBlock), 0, s, fine, fine_nr_filled, coarse, nv_fine_upper);
     else if (pos_dim == 5)
-        coarsen_kernel<5><<<cdiv((long long)nv_fine_upper * 13, kBlock), kBlock, 0, s>>>(fine, fine_nr_filled, coarse, nv_fine_upper);
+        launch_k(coarsen_kernel<5>, dim3(cdiv((long long)nv_fine_upper * 13, kBlock)), dim3(kBlock), 0, s, fine, fine_nr_filled, coarse, nv_fine_upper);
     else {
         set_error("ln_coarsen_keys: unsupported pos_dim %d", pos_dim);
         return LN_ERR_UNSUPPORTED;

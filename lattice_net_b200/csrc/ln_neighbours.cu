@@ -17,6 +17,7 @@ template <int D>
 __global__ void __launch_bounds__(kBlock)
 neighbour_table_kernel(const int* __restrict__ query_keys, int nv_query, const int* __restrict__ nv_query_dev,
                        ConstTableView nbr, int nbr_max_vertices, int lvl_diff, int dilation, int* __restrict__ neighbours) {
+    LN_PDL_ENTRY();
     constexpr int F = 2 * (D + 1) + 1;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)nv_query * F) return;
@@ -165,9 +166,9 @@ int ln_neighbour_table(const int* query_keys, int nv_query, const int* nv_query_
     if (nbr_max_vertices <= 0 || nbr_max_vertices > nbr_capacity) nbr_max_vertices = nbr_capacity;
     cudaStream_t s = (cudaStream_t)stream;
     if (pos_dim == 3)
-        neighbour_table_kernel<3><<<cdiv((long long)nv_query * 9, kBlock), kBlock, 0, s>>>(query_keys, nv_query, nv_query_dev, nbr, nbr_max_vertices, lvl_diff, dilation, neighbours);
+        launch_k(neighbour_table_kernel<3>, dim3(cdiv((long long)nv_query * 9, kBlock)), dim3(kBlock), 0, s, query_keys, nv_query, nv_query_dev, nbr, nbr_max_vertices, lvl_diff, dilation, neighbours);
     else if (pos_dim == 5)
-        neighbour_table_kernel<5><<<cdiv((long long)nv_query * 13, kBlock), kBlock, 0, s>>>(query_keys, nv_query, nv_query_dev, nbr, nbr_max_vertices, lvl_diff, dilation, neighbours);
+        launch_k(neighbour_table_kernel<5>, dim3(cdiv((long long)nv_query * 13, kBlock)), dim3(kBlock), 0, s, query_keys, nv_query, nv_query_dev, nbr, nbr_max_vertices, lvl_diff, dilation, neighbours);
     else {
         set_error("ln_neighbour_table: unsupported pos_dim %d", pos_dim);
         return LN_ERR_UNSUPPORTED;

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kGnThreads)
 group_norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                       int nv_rows, const int* __restrict__ nv_dev, int c, int cpg, float eps, int relu,
                       float* __restrict__ y, float* __restrict__ stats) {
+    LN_PDL_ENTRY();
     __shared__ float red[32];
     const int g = blockIdx.x;
     const int c0 = g * cpg;
@@ -87,6 +88,7 @@ group_norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                       const float* __restrict__ gamma, const float* __restrict__ stats, const float* __restrict__ dx_add,
                       int nv_rows, const int* __restrict__ nv_dev, int c, int cpg, int relu, float* __restrict__ dx,
                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    LN_PDL_ENTRY();
     __shared__ float red[32];
     const int g = blockIdx.x;
     const int c0 = g * cpg;
@@ -197,6 +199,7 @@ __global__ void __launch_bounds__(kGnThreads)
 group_norm_fwd_small_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                             int nv_rows, const int* __restrict__ nv_dev, int c, float eps, int relu,
                             float* __restrict__ y, float* __restrict__ stats) {
+    LN_PDL_ENTRY();
     __shared__ float red[32 * 1];
     const int g = blockIdx.x;
     const int c0 = g * CPG;
@@ -263,6 +266,7 @@ group_norm_bwd_small_kernel(const float* __restrict__ dy, const float* __restric
                             const float* __restrict__ gamma, const float* __restrict__ stats, const float* __restrict__ dx_add,
                             int nv_rows, const int* __restrict__ nv_dev, int c, int relu, float* __restrict__ dx,
                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    LN_PDL_ENTRY();
     __shared__ float red[32 * 2 * CPG];
     const int g = blockIdx.x;
     const int c0 = g * CPG;
@@ -365,6 +369,7 @@ __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret
 __global__ void __launch_bounds__(kGtMaxThreads)
 gn_tiled_stats_kernel(const float* __restrict__ x, int nv_rows, const int* __restrict__ nv_dev, int c, int cpg, int tpr,
                       int rows_per_cta, float* __restrict__ partial) {
+    LN_PDL_ENTRY();
     extern __shared__ __align__(16) float sh[];   // [rpp][c] per-row-slot channel sums, [c] channel sums, [G] group means
     const int rpp = blockDim.x / tpr;
     float* part = sh;
@@ -433,6 +438,7 @@ gn_tiled_stats_kernel(const float* __restrict__ x, int nv_rows, const int* __res
 __global__ void __launch_bounds__(128)
 gn_tiled_finalize_kernel(const float* __restrict__ partial, int ctas, int G, int rows_per_cta, int nv_rows,
                          const int* __restrict__ nv_dev, int cpg, float eps, float* __restrict__ stats) {
+    LN_PDL_ENTRY();
     __shared__ float red[32];
     const int g = blockIdx.x;
     const int nv = nv_dev ? min(nv_rows, __ldg(nv_dev)) : nv_rows;
@@ -460,6 +466,7 @@ __global__ void __launch_bounds__(kGtMaxThreads)
 gn_tiled_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                       const float* __restrict__ stats, int nv_rows, const int* __restrict__ nv_dev, int c, int cpg, int tpr,
                       int rows_per_cta, int relu, float* __restrict__ y) {
+    LN_PDL_ENTRY();
     const int rpp = blockDim.x / tpr;
     const int nv = nv_dev ? min(nv_rows, __ldg(nv_dev)) : nv_rows;
     const int col = threadIdx.x % tpr, rsub = threadIdx.x / tpr;
@@ -495,6 +502,7 @@ __global__ void __launch_bounds__(kGtMaxThreads)
 gn_tiled_bwd_partial_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
                             const float* __restrict__ stats, int nv_rows, const int* __restrict__ nv_dev, int c, int cpg,
                             int tpr, int rows_per_cta, int relu, float* __restrict__ partial_ab) {
+    LN_PDL_ENTRY();
     extern __shared__ __align__(16) float sh[];   // [rpp][2c]
     const int rpp = blockDim.x / tpr;
     const int nv = nv_dev ? min(nv_rows, __ldg(nv_dev)) : nv_rows;
@@ -544,6 +552,7 @@ gn_tiled_bwd_partial_kernel(const float* __restrict__ dy, const float* __restric
 // finalize kernel then walks S rows instead of thousands with a single CTA per 128 channels.
 __global__ void __launch_bounds__(128)
 gn_tiled_reduce_rows_kernel(const float* __restrict__ in, int rows, int width, float* __restrict__ out) {
+    LN_PDL_ENTRY();
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= width) return;
     float acc = 0.0f;
@@ -559,6 +568,7 @@ constexpr int kGtFinSlices = 4;
 __global__ void __launch_bounds__(kGtFinLanes * kGtFinSlices)
 gn_tiled_bwd_finalize_kernel(const float* __restrict__ partial_ab, int ctas, int c, int cpg, int cpc, const float* __restrict__ gamma,
                              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ gstat) {
+    LN_PDL_ENTRY();
     __shared__ float red[kGtFinSlices][2][kGtFinLanes];
     __shared__ float ch_a[kGtFinLanes], ch_b[kGtFinLanes];
     const int lane = threadIdx.x % kGtFinLanes, slice = threadIdx.x / kGtFinLanes;
@@ -606,6 +616,7 @@ gn_tiled_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict_
                           const float* __restrict__ gamma, const float* __restrict__ stats, const float* __restrict__ gstat,
                           const float* __restrict__ dx_add, int nv_rows, const int* __restrict__ nv_dev, int c, int cpg, int tpr,
                           int rows_per_cta, int relu, float* __restrict__ dx) {
+    LN_PDL_ENTRY();
     const int rpp = blockDim.x / tpr;
     const int nv = nv_dev ? min(nv_rows, __ldg(nv_dev)) : nv_rows;
     const int col = threadIdx.x % tpr, rsub = threadIdx.x / tpr;
@@ -678,7 +689,7 @@ int ln_group_norm_fwd(const float* x, const float* gamma, const float* beta, int
     const int cpg = c / groups;
     cudaStream_t s = (cudaStream_t)stream;
     if (gn_small_ok(nv, cpg)) {
-#define LN_GN_FWD(CPG) group_norm_fwd_small_kernel<CPG><<<groups, kGnThreads, 0, s>>>(x, gamma, beta, nv, nv_dev, c, eps, relu, y, stats)
+#define LN_GN_FWD(CPG) launch_k(group_norm_fwd_small_kernel<CPG>, dim3(groups), dim3(kGnThreads), 0, s, x, gamma, beta, nv, nv_dev, c, eps, relu, y, stats)
         switch (cpg) {
             case 1: LN_GN_FWD(1); break;
             case 2: LN_GN_FWD(2); break;
@@ -690,13 +701,13 @@ int ln_group_norm_fwd(const float* x, const float* gamma, const float* beta, int
 #undef LN_GN_FWD
     } else if (GtPlan p; workspace != nullptr && gt_plan(nv, c, cpg, &p)) {
         const size_t smem = ((size_t)p.rpp * c + c + groups) * sizeof(float);
-        gn_tiled_stats_kernel<<<p.ctas, p.threads, smem, s>>>(x, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, workspace);
-        gn_tiled_finalize_kernel<<<groups, 128, 0, s>>>(workspace, p.ctas, groups, p.rows_per_cta, nv, nv_dev, cpg, eps, stats);
-        gn_tiled_apply_kernel<<<p.ctas, p.threads, 0, s>>>(x, gamma, beta, stats, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, relu, y);
+        launch_k(gn_tiled_stats_kernel, dim3(p.ctas), dim3(p.threads), smem, s, x, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, workspace);
+        launch_k(gn_tiled_finalize_kernel, dim3(groups), dim3(128), 0, s, workspace, p.ctas, groups, p.rows_per_cta, nv, nv_dev, cpg, eps, stats);
+        launch_k(gn_tiled_apply_kernel, dim3(p.ctas), dim3(p.threads), 0, s, x, gamma, beta, stats, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, relu, y);
         count_launch();
         count_launch();
     } else {
-        group_norm_fwd_kernel<<<groups, kGnThreads, 0, s>>>(x, gamma, beta, nv, nv_dev, c, cpg, eps, relu, y, stats);
+        launch_k(group_norm_fwd_kernel, dim3(groups), dim3(kGnThreads), 0, s, x, gamma, beta, nv, nv_dev, c, cpg, eps, relu, y, stats);
     }
     count_launch();
     return check_launch("group_norm_fwd");
@@ -711,7 +722,7 @@ int ln_group_norm_bwd(const float* dy, const float* x, const float* y, const flo
     const int cpg = c / groups;
     cudaStream_t s = (cudaStream_t)stream;
     if (gn_small_ok(nv, cpg)) {
-#define LN_GN_BWD(CPG) group_norm_bwd_small_kernel<CPG><<<groups, kGnThreads, 0, s>>>(dy, x, y, gamma, stats, dx_add, nv, nv_dev, c, relu, dx, dgamma, dbeta)
+#define LN_GN_BWD(CPG) launch_k(group_norm_bwd_small_kernel<CPG>, dim3(groups), dim3(kGnThreads), 0, s, dy, x, y, gamma, stats, dx_add, nv, nv_dev, c, relu, dx, dgamma, dbeta)
         switch (cpg) {
             case 1: LN_GN_BWD(1); break;
             case 2: LN_GN_BWD(2); break;
@@ -726,22 +737,22 @@ int ln_group_norm_bwd(const float* dy, const float* x, const float* y, const flo
         float* reduced_ab = workspace + (size_t)p.ctas * 2 * c;
         float* gstat = reduced_ab + (size_t)kGtRedRows * 2 * c;
         const size_t smem = (size_t)p.rpp * 2 * c * sizeof(float);
-        gn_tiled_bwd_partial_kernel<<<p.ctas, p.threads, smem, s>>>(dy, x, y, stats, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, relu, partial_ab);
+        launch_k(gn_tiled_bwd_partial_kernel, dim3(p.ctas), dim3(p.threads), smem, s, dy, x, y, stats, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, relu, partial_ab);
         const float* fin_in = partial_ab;
         int fin_rows = p.ctas;
         if (p.ctas > 4 * kGtRedRows) {
-            gn_tiled_reduce_rows_kernel<<<dim3((2 * c + 127) / 128, kGtRedRows), 128, 0, s>>>(partial_ab, p.ctas, 2 * c, reduced_ab);
+            launch_k(gn_tiled_reduce_rows_kernel, dim3(dim3((2 * c + 127) / 128, kGtRedRows)), dim3(128), 0, s, partial_ab, p.ctas, 2 * c, reduced_ab);
             count_launch();
             fin_in = reduced_ab;
             fin_rows = kGtRedRows;
         }
         const int cpc = cpg >= kGtFinLanes ? cpg : (kGtFinLanes / cpg) * cpg;       // whole groups per CTA
-        gn_tiled_bwd_finalize_kernel<<<(c + cpc - 1) / cpc, kGtFinLanes * kGtFinSlices, 0, s>>>(fin_in, fin_rows, c, cpg, cpc, gamma, dgamma, dbeta, gstat);
-        gn_tiled_bwd_apply_kernel<<<p.ctas, p.threads, 0, s>>>(dy, x, y, gamma, stats, gstat, dx_add, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, relu, dx);
+        launch_k(gn_tiled_bwd_finalize_kernel, dim3((c + cpc - 1) / cpc), dim3(kGtFinLanes * kGtFinSlices), 0, s, fin_in, fin_rows, c, cpg, cpc, gamma, dgamma, dbeta, gstat);
+        launch_k(gn_tiled_bwd_apply_kernel, dim3(p.ctas), dim3(p.threads), 0, s, dy, x, y, gamma, stats, gstat, dx_add, nv, nv_dev, c, cpg, p.tpr, p.rows_per_cta, relu, dx);
         count_launch();
         count_launch();
     } else {
-        group_norm_bwd_kernel<<<groups, kGnThreads, 0, s>>>(dy, x, y, gamma, stats, dx_add, nv, nv_dev, c, cpg, relu, dx, dgamma, dbeta);
+        launch_k(group_norm_bwd_kernel, dim3(groups), dim3(kGnThreads), 0, s, dy, x, y, gamma, stats, dx_add, nv, nv_dev, c, cpg, relu, dx, dgamma, dbeta);
     }
     count_launch();
     return check_launch("group_norm_bwd");

@@ -84,6 +84,7 @@ template <int D>
 __global__ void __launch_bounds__(256)
 pn_mean_kernel(const float* __restrict__ positions_raw, const float* __restrict__ sigmas, const int* __restrict__ indices, int n,
                float* __restrict__ acc) {
+    LN_PDL_ENTRY();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)n * (D + 1)) return;
     const int p = (int)(t / (D + 1));
@@ -118,6 +119,7 @@ pn_mlp_max_kernel(const float* __restrict__ positions_raw, const float* __restri
                   const int* __restrict__ indices, int n, PnLayers L, const float* __restrict__ acc, int vertex0_quirk,
                   unsigned long long* __restrict__ packed) {
     __shared__ __align__(16) float w1[H1 * IN], w2[H2 * H1], w3[H3 * H2], b1[H1], b2[H2], b3[H3], red[4];
+    LN_PDL_ENTRY();
     pn_load_weights<IN, H1, H2, H3>(L, w1, w2, w3, b1, b2, b3, red);
     const long long rows = (long long)n * (D + 1);
     for (long long row = (long long)blockIdx.x * kPnThreads + threadIdx.x; row < rows; row += (long long)gridDim.x * kPnThreads) {
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(256)
 pn_finish_kernel(const unsigned long long* __restrict__ packed, const float* __restrict__ weights, const float* __restrict__ acc,
                  int nv_rows, int h3, long long rows_total, int vertex0_quirk, int min_points, float* __restrict__ out,
                  int* __restrict__ arg) {
+    LN_PDL_ENTRY();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)nv_rows * h3) return;
     const int v = (int)(t / h3), c = (int)(t - (long long)v * h3);
@@ -189,6 +192,7 @@ pn_mlp_bwd_kernel(const float* __restrict__ positions_raw, const float* __restri
                   const int* __restrict__ indices, int n, PnLayers L, const float* __restrict__ acc, int vertex0_quirk,
                   const float* __restrict__ grad_reduced /* [nv x 2*H3] */, const int* __restrict__ arg, float* __restrict__ gacc) {
     using A = PnAccLayout<IN, H1, H2, H3>;
+    LN_PDL_ENTRY();
     constexpr int kStride = H3 + 2 * H2 + 2 * H1 + IN + 1;       // odd for the reference widths: conflict-free row-parallel stores
     extern __shared__ __align__(16) float pn_smem[];
     float* w1 = pn_smem;
@@ -351,6 +355,7 @@ pn_mlp_bwd_kernel(const float* __restrict__ positions_raw, const float* __restri
 //   dg[o] = sum_i dW[o,i] v[o,i] / n;   dv = dW * g[o] / n  -  v * (sum_{o,i} dW[o,i] v[o,i] g[o]) / n^3
 __global__ void __launch_bounds__(kPnThreads)
 pn_wn_bwd_kernel(PnLayers L, PnGrads G, const float* __restrict__ gacc, int in0, int h1, int h2, int h3) {
+    LN_PDL_ENTRY();
     __shared__ float red[4];
     const int l = blockIdx.x;
     const int outs[3] = {h1, h2, h3}, ins[3] = {in0, h1, h2};
@@ -384,10 +389,10 @@ static int pn_forward(const float* positions_raw, const float* sigmas, const flo
                       const PnLayers& L, int nv_rows, int vertex0_quirk, int min_points, float* acc, unsigned long long* packed, float* out,
                       int* arg, cudaStream_t s) {
     const long long rows = (long long)n * (D + 1);
-    pn_mean_kernel<D><<<cdiv(rows, 256), 256, 0, s>>>(positions_raw, sigmas, indices, n, acc);
+    launch_k(pn_mean_kernel<D>, dim3(cdiv(rows, 256)), dim3(256), 0, s, positions_raw, sigmas, indices, n, acc);
     const int grid = (int)min((long long)148 * 8, (rows + kPnThreads - 1) / kPnThreads);
-    pn_mlp_max_kernel<D, IN, 16, 32, 64><<<grid, kPnThreads, 0, s>>>(positions_raw, sigmas, values, indices, n, L, acc, vertex0_quirk, packed);
-    pn_finish_kernel<D><<<cdiv((long long)nv_rows * 64, 256), 256, 0, s>>>(packed, weights, acc, nv_rows, 64, rows, vertex0_quirk, min_points, out, arg);
+    launch_k((pn_mlp_max_kernel<D, IN, 16, 32, 64>), dim3(grid), dim3(kPnThreads), 0, s, positions_raw, sigmas, values, indices, n, L, acc, vertex0_quirk, packed);
+    launch_k(pn_finish_kernel<D>, dim3(cdiv((long long)nv_rows * 64, 256)), dim3(256), 0, s, packed, weights, acc, nv_rows, 64, rows, vertex0_quirk, min_points, out, arg);
     count_launch(3);
     return check_launch("pointnet_fwd");
 }
@@ -407,9 +412,9 @@ static int pn_backward(const float* positions_raw, const float* sigmas, const fl
     }
     const long long rows = (long long)n * (D + 1);
     const int grid = (int)min((long long)148 * 2, (rows + kPnThreads - 1) / kPnThreads);
-    pn_mlp_bwd_kernel<D, IN, H1, H2, H3><<<grid, kPnThreads, smem, s>>>(positions_raw, sigmas, values, indices, n, L, acc, vertex0_quirk,
+    launch_k((pn_mlp_bwd_kernel<D, IN, H1, H2, H3>), dim3(grid), dim3(kPnThreads), smem, s, positions_raw, sigmas, values, indices, n, L, acc, vertex0_quirk,
                                                                          grad_reduced, arg, gacc);
-    pn_wn_bwd_kernel<<<3, kPnThreads, 0, s>>>(L, G, gacc, IN, H1, H2, H3);
+    launch_k(pn_wn_bwd_kernel, dim3(3), dim3(kPnThreads), 0, s, L, G, gacc, IN, H1, H2, H3);
     count_launch(2);
     return check_launch("pointnet_bwd");
 }

@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kBlock)
 slice_fwd_kernel(const float* __restrict__ lattice_values, const int* __restrict__ indices,
                  const float* __restrict__ weights, int n, int val_dim, int slab_ch, int n_slabs, int lpp_log2,
                  float* __restrict__ out) {
+    LN_PDL_ENTRY();
     const int lpp = 1 << lpp_log2;
     const int g = threadIdx.x & (lpp - 1);
     const int pts_per_block = kBlock >> lpp_log2;
@@ -201,6 +202,7 @@ __global__ void __launch_bounds__(kBlock)
 scatter_rows_kernel(const float* __restrict__ src, const int* __restrict__ indices,
                     const float* __restrict__ weights, int n, int val_dim, int slab_ch, int n_slabs, int lpp_log2,
                     float* __restrict__ rows) {
+    LN_PDL_ENTRY();
     const int lpp = 1 << lpp_log2;
     const int g = threadIdx.x & (lpp - 1);
     const int pts_per_block = kBlock >> lpp_log2;
@@ -269,7 +271,7 @@ int launch_scatter_rows(const float* src, const int* indices, const float* weigh
     do {                                                                                                             \
         static const int resident = blocks_per_sm((const void*)scatter_rows_kernel<VEC, SPV>);                       \
         const SlabPlan pl = plan_slabs(n, nr_vertices, val_dim, VEC, resident);                                      \
-        scatter_rows_kernel<VEC, SPV><<<pl.grid, kBlock, 0, s>>>(src, indices, weights, n, val_dim, pl.slab_ch, pl.n_slabs, pl.lpp_log2, rows); \
+        launch_k((scatter_rows_kernel<VEC, SPV>), dim3(pl.grid), dim3(kBlock), 0, s, src, indices, weights, n, val_dim, pl.slab_ch, pl.n_slabs, pl.lpp_log2, rows); \
     } while (0)
     if (vec == 4) {
         if (spv == 4) LN_LAUNCH_SCATTER(4, 4); else LN_LAUNCH_SCATTER(4, 6);
@@ -286,6 +288,7 @@ int launch_scatter_rows(const float* src, const int* indices, const float* weigh
 __global__ void __launch_bounds__(kBlock)
 gather_fwd_kernel(const float* __restrict__ lattice_values, const int* __restrict__ indices,
                   const float* __restrict__ weights, int n, int spv, int val_dim, float* __restrict__ out) {
+    LN_PDL_ENTRY();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int chunk = val_dim + 1;
     if (t >= (long long)n * spv * chunk) return;
@@ -303,6 +306,7 @@ gather_fwd_kernel(const float* __restrict__ lattice_values, const int* __restric
 __global__ void __launch_bounds__(kBlock)
 gather_bwd_kernel(const float* __restrict__ grad_out, const int* __restrict__ indices,
                   const float* __restrict__ weights, int n, int spv, int val_dim, float* __restrict__ grad_values) {
+    LN_PDL_ENTRY();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)n * spv * val_dim) return;
     const int j = (int)(t % val_dim);
@@ -324,6 +328,7 @@ slice_classify_fwd_kernel(const float* __restrict__ lattice_values, const int* _
                           const float* __restrict__ weights, const float* __restrict__ delta_weights,
                           const float* __restrict__ cls_weight, const float* __restrict__ cls_bias, int n, int spv,
                           int val_dim, int nr_classes, float* __restrict__ logits) {
+    LN_PDL_ENTRY();
     extern __shared__ float smem[];
     float* w_sh = smem;   // [nr_classes][val_dim]
     for (int i = threadIdx.x; i < nr_classes * val_dim; i += blockDim.x) w_sh[i] = __ldg(cls_weight + i);
@@ -378,6 +383,7 @@ slice_classify_fwd_tiled_kernel(const float* __restrict__ lattice_values, const 
                                 const float* __restrict__ weights, const float* __restrict__ delta_weights,
                                 const float* __restrict__ cls_weight, const float* __restrict__ cls_bias, int n,
                                 int val_dim, int nr_classes, float* __restrict__ logits) {
+    LN_PDL_ENTRY();
     extern __shared__ __align__(16) float smem_t[];
     const int lds = val_dim + 4;
     float* w_sh = smem_t;                            // [nc][V]
@@ -461,6 +467,7 @@ slice_classify_bwd_kernel(const float* __restrict__ grad_logits, const float* __
                           int spv, int val_dim, int nr_classes, float* __restrict__ grad_lattice_values,
                           float* __restrict__ grad_delta_weights, float* __restrict__ grad_cls_weight,
                           float* __restrict__ grad_cls_bias) {
+    LN_PDL_ENTRY();
     extern __shared__ float smem[];
     float* w_sh = smem;                                 // [nc][V]
     float* s_sh = w_sh + nr_classes * val_dim;          // [kTile][V]
@@ -572,6 +579,7 @@ slice_classify_bwd_vec_kernel(const float* __restrict__ grad_logits, const float
                               int val_dim, int nr_classes, float* __restrict__ grad_lattice_values,
                               float* __restrict__ grad_delta_weights, float* __restrict__ grad_cls_weight,
                               float* __restrict__ grad_cls_bias) {
+    LN_PDL_ENTRY();
     extern __shared__ __align__(16) float smem_v[];
     float* w_sh = smem_v;                               // [nc][V]
     float* s_sh = w_sh + nr_classes * val_dim;          // [kTile][V]
@@ -715,6 +723,7 @@ __device__ __forceinline__ float ordered_to_float(unsigned int o) {
 __global__ void __launch_bounds__(kBlock)
 scatter_max_pack_kernel(const float* __restrict__ src, const int* __restrict__ index, int m, int c,
                         unsigned long long* __restrict__ packed) {
+    LN_PDL_ENTRY();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)m * c) return;
     const int row = (int)(t / c);
@@ -729,6 +738,7 @@ scatter_max_pack_kernel(const float* __restrict__ src, const int* __restrict__ i
 __global__ void __launch_bounds__(kBlock)
 scatter_max_unpack_kernel(const unsigned long long* __restrict__ packed, long long total, int m,
                           float* __restrict__ out_max, int* __restrict__ out_arg) {
+    LN_PDL_ENTRY();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     const unsigned long long key = packed[t];
@@ -744,6 +754,7 @@ scatter_max_unpack_kernel(const unsigned long long* __restrict__ packed, long lo
 __global__ void __launch_bounds__(kBlock)
 scatter_sum_count_kernel(const float* __restrict__ src, const int* __restrict__ index, int m, int c,
                          float* __restrict__ out_sum, float* __restrict__ out_count) {
+    LN_PDL_ENTRY();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)m * c) return;
     const int row = (int)(t / c);
@@ -773,7 +784,7 @@ int ln_slice_fwd(const float* lattice_values, const int* indices, const float* w
     do {                                                                                                             \
         static const int resident = blocks_per_sm((const void*)slice_fwd_kernel<VEC, SPV>);                          \
         const SlabPlan pl = plan_slabs(n, nr_vertices, val_dim, VEC, resident);                                      \
-        slice_fwd_kernel<VEC, SPV><<<pl.grid, kBlock, 0, s>>>(lattice_values, indices, weights, n, val_dim, pl.slab_ch, pl.n_slabs, pl.lpp_log2, out); \
+        launch_k((slice_fwd_kernel<VEC, SPV>), dim3(pl.grid), dim3(kBlock), 0, s, lattice_values, indices, weights, n, val_dim, pl.slab_ch, pl.n_slabs, pl.lpp_log2, out); \
     } while (0)
     const int spv = pos_dim + 1;
     if (spv != 4 && spv != 6) {
@@ -804,7 +815,7 @@ int ln_gather_fwd(const float* lattice_values, const int* indices, const float* 
     LN_SLICE_ARGS_OK("ln_gather_fwd");
     if (n == 0) return LN_OK;
     const long long total = (long long)n * (pos_dim + 1) * (val_dim + 1);
-    gather_fwd_kernel<<<cdiv(total, kBlock), kBlock, 0, (cudaStream_t)stream>>>(lattice_values, indices, weights, n, pos_dim + 1, val_dim, out);
+    launch_k(gather_fwd_kernel, dim3(cdiv(total, kBlock)), dim3(kBlock), 0, (cudaStream_t)stream, lattice_values, indices, weights, n, pos_dim + 1, val_dim, out);
     count_launch();
     return check_launch("gather_fwd");
 }
@@ -815,7 +826,7 @@ int ln_gather_bwd(const float* grad_out, const int* indices, const float* weight
     LN_SLICE_ARGS_OK("ln_gather_bwd");
     if (n == 0) return LN_OK;
     const long long total = (long long)n * (pos_dim + 1) * val_dim;
-    gather_bwd_kernel<<<cdiv(total, kBlock), kBlock, 0, (cudaStream_t)stream>>>(grad_out, indices, weights, n, pos_dim + 1, val_dim, grad_values);
+    launch_k(gather_bwd_kernel, dim3(cdiv(total, kBlock)), dim3(kBlock), 0, (cudaStream_t)stream, grad_out, indices, weights, n, pos_dim + 1, val_dim, grad_values);
     count_launch();
     return check_launch("gather_bwd");
 }
@@ -856,11 +867,11 @@ int ln_slice_classify_fwd(const float* lattice_values, const int* indices, const
             if (pos_dim == 3) {
                 if (smem_t > 48 * 1024) err = allow_max_smem((const void*)slice_classify_fwd_tiled_kernel<4>);
                 if (err == cudaSuccess)
-                    slice_classify_fwd_tiled_kernel<4><<<grid_t, kBlock, smem_t, s>>>(lattice_values, indices, weights, delta_weights, cls_weight, cls_bias, n, val_dim, nr_classes, logits);
+                    launch_k(slice_classify_fwd_tiled_kernel<4>, dim3(grid_t), dim3(kBlock), smem_t, s, lattice_values, indices, weights, delta_weights, cls_weight, cls_bias, n, val_dim, nr_classes, logits);
             } else {
                 if (smem_t > 48 * 1024) err = allow_max_smem((const void*)slice_classify_fwd_tiled_kernel<6>);
                 if (err == cudaSuccess)
-                    slice_classify_fwd_tiled_kernel<6><<<grid_t, kBlock, smem_t, s>>>(lattice_values, indices, weights, delta_weights, cls_weight, cls_bias, n, val_dim, nr_classes, logits);
+                    launch_k(slice_classify_fwd_tiled_kernel<6>, dim3(grid_t), dim3(kBlock), smem_t, s, lattice_values, indices, weights, delta_weights, cls_weight, cls_bias, n, val_dim, nr_classes, logits);
             }
             if (err != cudaSuccess) {
                 set_error("ln_slice_classify_fwd: %s", cudaGetErrorString(err));
@@ -876,7 +887,7 @@ int ln_slice_classify_fwd(const float* lattice_values, const int* indices, const
 #define LN_LAUNCH_SCF(KV)                                                                                          \
     do {                                                                                                           \
         if (smem > 48 * 1024) allow_max_smem((const void*)slice_classify_fwd_kernel<KV>); \
-        slice_classify_fwd_kernel<KV><<<grid, kBlock, smem, s>>>(lattice_values, indices, weights, delta_weights, cls_weight, cls_bias, n, pos_dim + 1, val_dim, nr_classes, logits); \
+        launch_k(slice_classify_fwd_kernel<KV>, dim3(grid), dim3(kBlock), smem, s, lattice_values, indices, weights, delta_weights, cls_weight, cls_bias, n, pos_dim + 1, val_dim, nr_classes, logits); \
     } while (0)
     if (kv <= 1) LN_LAUNCH_SCF(1);
     else if (kv <= 2) LN_LAUNCH_SCF(2);
@@ -912,7 +923,7 @@ int ln_slice_classify_bwd(const float* grad_logits, const float* lattice_values,
             set_error("ln_slice_classify_bwd: %s", cudaGetErrorString(err));                                       \
             return LN_ERR_CUDA;                                                                                    \
         }                                                                                                          \
-        slice_classify_bwd_vec_kernel<KV4, SPV><<<grid, kBlock, smem, s>>>(grad_logits, lattice_values, indices, weights, delta_weights, cls_weight, n, val_dim, nr_classes, grad_lattice_values, grad_delta_weights, grad_cls_weight, grad_cls_bias); \
+        launch_k((slice_classify_bwd_vec_kernel<KV4, SPV>), dim3(grid), dim3(kBlock), smem, s, grad_logits, lattice_values, indices, weights, delta_weights, cls_weight, n, val_dim, nr_classes, grad_lattice_values, grad_delta_weights, grad_cls_weight, grad_cls_bias); \
     } while (0)
         if (val_dim <= 128) {
             if (pos_dim == 3) LN_LAUNCH_SCBV(1, 4); else LN_LAUNCH_SCBV(1, 6);
@@ -927,7 +938,7 @@ int ln_slice_classify_bwd(const float* grad_logits, const float* lattice_values,
 #define LN_LAUNCH_SCB(KV)                                                                                          \
     do {                                                                                                           \
         if (smem > 48 * 1024) allow_max_smem((const void*)slice_classify_bwd_kernel<KV>); \
-        slice_classify_bwd_kernel<KV><<<grid, kBlock, smem, s>>>(grad_logits, lattice_values, indices, weights, delta_weights, cls_weight, n, pos_dim + 1, val_dim, nr_classes, grad_lattice_values, grad_delta_weights, grad_cls_weight, grad_cls_bias); \
+        launch_k(slice_classify_bwd_kernel<KV>, dim3(grid), dim3(kBlock), smem, s, grad_logits, lattice_values, indices, weights, delta_weights, cls_weight, n, pos_dim + 1, val_dim, nr_classes, grad_lattice_values, grad_delta_weights, grad_cls_weight, grad_cls_bias); \
     } while (0)
     if (kv <= 1) LN_LAUNCH_SCB(1);
     else if (kv <= 2) LN_LAUNCH_SCB(2);
@@ -947,10 +958,10 @@ int ln_scatter_max(const float* src, const int* index, int m, int c, int nv, flo
     const long long total = (long long)nv * c;
     if (cudaMemsetAsync(workspace, 0, total * sizeof(unsigned long long), s) != cudaSuccess) return check_launch("scatter_max memset");
     if (m > 0) {
-        scatter_max_pack_kernel<<<cdiv((long long)m * c, kBlock), kBlock, 0, s>>>(src, index, m, c, workspace);
+        launch_k(scatter_max_pack_kernel, dim3(cdiv((long long)m * c, kBlock)), dim3(kBlock), 0, s, src, index, m, c, workspace);
         count_launch();
     }
-    scatter_max_unpack_kernel<<<cdiv(total, kBlock), kBlock, 0, s>>>(workspace, total, m, out_max, out_arg);
+    launch_k(scatter_max_unpack_kernel, dim3(cdiv(total, kBlock)), dim3(kBlock), 0, s, workspace, total, m, out_max, out_arg);
     count_launch();
     return check_launch("scatter_max");
 }
@@ -964,7 +975,7 @@ int ln_scatter_sum_count(const float* src, const int* index, int m, int c, int n
     cudaMemsetAsync(out_sum, 0, (size_t)nv * c * sizeof(float), s);
     if (out_count) cudaMemsetAsync(out_count, 0, (size_t)nv * sizeof(float), s);
     if (m > 0) {
-        scatter_sum_count_kernel<<<cdiv((long long)m * c, kBlock), kBlock, 0, s>>>(src, index, m, c, out_sum, out_count);
+        launch_k(scatter_sum_count_kernel, dim3(cdiv((long long)m * c, kBlock)), dim3(kBlock), 0, s, src, index, m, c, out_sum, out_count);
         count_launch();
     }
     return check_launch("scatter_sum_count");

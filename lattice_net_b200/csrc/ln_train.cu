@@ -36,6 +36,7 @@ __device__ __forceinline__ float block_sum_1024(float v, float* red) {
 __global__ void __launch_bounds__(kLossThreads)
 seg_loss_kernel(const float* __restrict__ logp, const long long* __restrict__ labels, int n, int nr_classes, int n_pad,
                 int ignore_index, float* __restrict__ grad_lov, float* __restrict__ acc, float* __restrict__ result) {
+    LN_PDL_ENTRY();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);          // [n_pad]
     int* cum = reinterpret_cast<int*>(keys + n_pad);                                      // [n_pad] inclusive prefix of sorted fg
@@ -167,6 +168,7 @@ seg_loss_kernel(const float* __restrict__ logp, const long long* __restrict__ la
 __global__ void __launch_bounds__(256)
 seg_loss_bwd_kernel(const float* __restrict__ grad_lov, const long long* __restrict__ labels, const float* __restrict__ result,
                     const float* __restrict__ grad_loss, int n, int nr_classes, int ignore_index, float* __restrict__ grad_logp) {
+    LN_PDL_ENTRY();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)n * nr_classes) return;
     const int i = (int)(t / nr_classes), c = (int)(t - (long long)i * nr_classes);
@@ -187,6 +189,7 @@ __global__ void __launch_bounds__(256)
 adamw_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                      float* __restrict__ vmax, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
                      float grad_scale, float* __restrict__ state, const float* __restrict__ skip) {
+    LN_PDL_ENTRY();
     const bool skipped = skip != nullptr && *skip != 0.0f;
     const float step = state[0] + 1.0f;
     if (!skipped) {
@@ -260,7 +263,7 @@ int ln_seg_loss_fwd(const float* logp, const long long* labels, int n, int nr_cl
             return LN_ERR_CUDA;
         }
     }
-    seg_loss_kernel<<<nr_classes, kLossThreads, smem, (cudaStream_t)stream>>>(logp, labels, n, nr_classes, n_pad, ignore_index, grad_lov,
+    launch_k(seg_loss_kernel, dim3(nr_classes), dim3(kLossThreads), smem, (cudaStream_t)stream, logp, labels, n, nr_classes, n_pad, ignore_index, grad_lov,
                                                                             acc_zeroed, result);
     count_launch();
     return check_launch("seg_loss");
@@ -270,7 +273,7 @@ int ln_seg_loss_bwd(const float* grad_lov, const long long* labels, const float*
                     int nr_classes, int ignore_index, float* grad_logp, void* stream) {
     LN_REQUIRE(grad_lov && labels && result && grad_loss && grad_logp, "ln_seg_loss_bwd: null pointer");
     LN_REQUIRE(n >= 1 && nr_classes >= 1, "ln_seg_loss_bwd: bad size");
-    seg_loss_bwd_kernel<<<cdiv((long long)n * nr_classes, 256), 256, 0, (cudaStream_t)stream>>>(grad_lov, labels, result, grad_loss, n,
+    launch_k(seg_loss_bwd_kernel, dim3(cdiv((long long)n * nr_classes, 256)), dim3(256), 0, (cudaStream_t)stream, grad_lov, labels, result, grad_loss, n,
                                                                                                 nr_classes, ignore_index, grad_logp);
     count_launch();
     return check_launch("seg_loss_bwd");
@@ -285,7 +288,7 @@ int ln_adamw_amsgrad(float* params, const float* grads, float* exp_avg, float* e
                "ln_adamw_amsgrad: buffers must be 16-byte aligned");
     if (n == 0) return LN_OK;
     const int grid = (int)min((long long)148 * 8, (n / 4 + 255) / 256 + 1);
-    adamw_amsgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, max_exp_avg_sq, n, lr, beta1, beta2, eps,
+    launch_k(adamw_amsgrad_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, max_exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                   weight_decay, grad_scale, state, skip);
     count_launch();
     return check_launch("adamw_amsgrad");

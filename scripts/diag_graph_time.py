@@ -18,6 +18,10 @@ def main():
     from lattice_net_b200.parallel import GradBucket
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
+    if "--no-pdl" in sys.argv:
+        from lattice_net_b200 import _cabi
+        _cabi.load().ln_set_programmatic_launch(0)
+        print("programmatic dependent launch OFF")
     lattice, model = bench.build_training(dev)
     clouds = [bench.synthetic_cloud(i) for i in range(8)]
     dc = [(torch.from_numpy(p).to(dev), torch.zeros((bench.NR_POINTS, 1), device=dev), torch.from_numpy(l).to(dev)) for p, l in clouds]

@@ -1366,3 +1366,45 @@ def test_fused_pointnet_matches_the_module_by_module_path(built, val_dim, quirk)
             assert_close(results[1][1][name], ga, 1e-4, f"fused PointNet gradient of {name}")
     finally:
         lm.REFERENCE_VERTEX0_QUIRK = saved
+
+
+def test_programmatic_dependent_launch_does_not_change_results(built):
+    """ln_set_programmatic_launch(0 / 1): the same chain of dependent kernels (GroupNorm -> convolution -> GroupNorm ->
+    slice, forward and backward) with and without programmatic dependent launch; deterministic kernels bit-equal, the
+    reduction-based ones within their usual tolerance.  Guards the rule that no kernel touches global memory before its
+    griddepcontrol.wait."""
+    from lattice_net_b200 import _cabi
+    from lattice_net_b200.lattice_funcs import ConvIm2RowLattice, SliceLattice
+    from lattice_net_b200.lattice_modules import _GroupNormReLU
+    b = built
+    F = 2 * (b["d"] + 1) + 1
+    C = 64
+    torch.manual_seed(3)
+    x0 = torch.randn((b["nv"], C), device="cuda")
+    w0 = torch.randn((F * C, C), device="cuda") * 0.05
+    gam, bet = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda") * 0.1
+    gy = torch.randn((b["n"], C), device="cuda")
+    lib = _cabi.load()
+
+    def run():
+        x = x0.clone().requires_grad_(True)
+        w = w0.clone().requires_grad_(True)
+        g1, b1 = gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+        h = x
+        for _ in range(6):      # a dependent chain long enough for several kernels to be in flight
+            h = _GroupNormReLU.apply(h, g1, b1, 32, 1e-5, True, None)
+            h, _ = ConvIm2RowLattice.apply(h, b["ours"].clone_lattice(), w, 1)
+        s = SliceLattice.apply(h, b["ours"].clone_lattice(), b["pos"], b["idx"], b["w"])
+        (s * gy).sum().backward()
+        torch.cuda.synchronize()
+        return [t.detach().cpu().numpy() for t in (s, x.grad, w.grad, g1.grad, b1.grad)]
+
+    prev = lib.ln_set_programmatic_launch(1)
+    try:
+        on = run()
+        lib.ln_set_programmatic_launch(0)
+        off = run()
+    finally:
+        lib.ln_set_programmatic_launch(prev)
+    for a, c, what in zip(on, off, ("sliced", "dx", "dw", "dgamma", "dbeta")):
+        assert_close(a, c, 1e-4, f"programmatic launch on vs off: {what}")
