@@ -48,6 +48,11 @@ const char* ln_last_error(void);
  * (bench.py reports it as `gpu_launches`). */
 long long ln_launch_count(void);
 void ln_reset_launch_count(void);
+/* Bookkeeping of a static-shape lattice pyramid without a host round trip: nv_out[l] = vertex count of level l,
+ * overflow_out[0] = 1.0 if any level's table filled up or exceeded its row bound, else 0.0.  nr_filled_ptrs / status_ptrs:
+ * HOST arrays of n_levels (<= 8) device pointers (the nr_filled / status words of ln_splat_build). */
+int ln_levels_status(const int* const* nr_filled_ptrs, const int* const* status_ptrs, int n_levels, int* nv_out, float* overflow_out,
+                     void* stream);
 /* Programmatic dependent launch of this library's kernels (on by default; see ln_common.cuh): 0 launches them with plain
  * stream ordering.  Returns the previous setting.  Results are identical either way. */
 int ln_set_programmatic_launch(int enabled);
@@ -234,6 +239,16 @@ int ln_slice_classify_bwd(const float* grad_logits, const float* lattice_values,
                           float* grad_lattice_values, float* grad_delta_weights,
                           float* grad_cls_weight, float* grad_cls_bias, void* stream);
 
+/* Learned barycentric offsets of the DeformSlice head (lattice_modules.py:465-567: gather, max over the simplex, affine,
+ * Linear(9 -> 1)) in one kernel each way.  values [nv x 8] (the head's bottleneck features), gamma / beta / lin_w [9],
+ * lin_b [1]; delta_w [n x (pos_dim+1)].  Backward: grad_values_zeroed [nv x 8] and the four zeroed parameter gradients
+ * (lin_w [9], lin_b [1], gamma [9], beta [9]) are accumulated into. */
+int ln_deltaw_fwd(const float* values, const int* indices, const float* weights, const float* gamma, const float* beta,
+                  const float* lin_w, const float* lin_b, int n, int pos_dim, int val_dim, float* delta_w, void* stream);
+int ln_deltaw_bwd(const float* values, const int* indices, const float* weights, const float* gamma, const float* beta,
+                  const float* lin_w, const float* grad_delta_w, int n, int pos_dim, int val_dim, float* grad_values_zeroed,
+                  float* grad_lin_w_zeroed, float* grad_lin_b_zeroed, float* grad_gamma_zeroed, float* grad_beta_zeroed, void* stream);
+
 /* ---- PointNet glue on lattice vertices ---------------------------
  * Segmented reductions over the points that splat onto each vertex, replacing the torch_scatter
  * calls of /root/reference/latticenet_py/lattice/lattice_modules.py:78,688,692.
@@ -300,6 +315,13 @@ int ln_seg_loss_fwd(const float* logp, const long long* labels, int n, int nr_cl
 /* grad_logp = grad_loss[0] * d loss / d logp from the quantities ln_seg_loss_fwd left behind. */
 int ln_seg_loss_bwd(const float* grad_lov, const long long* labels, const float* result, const float* grad_loss, int n,
                     int nr_classes, int ignore_index, float* grad_logp, void* stream);
+
+/* Weight normalisation w = v * (g / ||v||_F) of a [rows x cols] tensor with one gain per column (gain_per_col != 0: the
+ * lattice filter banks, g_dim = 1) or per row (Linear, g_dim = 0) -- /root/reference/latticenet_py/utils/utils.py:72-158 --
+ * and its backward (dv, dg from dw), one launch each. */
+int ln_weight_norm_fwd(const float* v, const float* g, int rows, int cols, int gain_per_col, float* w, void* stream);
+int ln_weight_norm_bwd(const float* v, const float* g, const float* dw, int rows, int cols, int gain_per_col, float* dv, float* dg,
+                       void* stream);
 
 /* AdamW with amsgrad (ln_train.py:163-165) as ONE kernel over flat fp32 buffers of n elements (16-byte aligned),
  * torch.optim.AdamW's update order.  state: 2 floats, [0] step count (advanced here), [1] scratch (zero).

@@ -51,6 +51,11 @@ _SIGNATURES.update({
     "ln_seg_loss_bwd": [_P, _P, _P, _P, _I, _I, _I, _P, _P],
     "ln_pointnet_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "ln_pointnet_bwd": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "ln_deltaw_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P],
+    "ln_deltaw_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "ln_levels_status": [_P, _P, _I, _P, _P, _P],
+    "ln_weight_norm_fwd": [_P, _P, _I, _I, _I, _P, _P],
+    "ln_weight_norm_bwd": [_P, _P, _P, _I, _I, _I, _P, _P, _P],
     "ln_adamw_amsgrad": [_P, _P, _P, _P, _P, ctypes.c_longlong, _F, _F, _F, _F, _F, _F, _P, _P, _P],
 })
 _SPECIAL = {

@@ -30,9 +30,40 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static std::atomic<int> g_pdl{1};
 bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 
+struct LevelPtrs {
+    const int* nr_filled[8];
+    const int* status[8];
+};
+// per-step bookkeeping of a static-shape lattice pyramid in one launch: vertex count of every level, and 1.0 when any
+// level's table overflowed or exceeded its row bound (the "skip this update" flag of the graphed step)
+__global__ void levels_status_kernel(LevelPtrs p, int n_levels, int* __restrict__ nv_out, float* __restrict__ overflow_out) {
+    LN_PDL_ENTRY();
+    if (threadIdx.x == 0) {
+        int bad = 0;
+        for (int l = 0; l < n_levels; l++) {
+            nv_out[l] = *p.nr_filled[l];
+            bad |= p.status[l][0];
+        }
+        *overflow_out = bad != 0 ? 1.0f : 0.0f;
+    }
+}
+
 }  // namespace ln
 
 extern "C" {
+
+int ln_levels_status(const int* const* nr_filled_ptrs, const int* const* status_ptrs, int n_levels, int* nv_out, float* overflow_out,
+                     void* stream) {
+    LN_REQUIRE(nr_filled_ptrs && status_ptrs && nv_out && overflow_out && n_levels >= 1 && n_levels <= 8, "ln_levels_status: bad argument");
+    ln::LevelPtrs p;
+    for (int l = 0; l < 8; l++) {
+        p.nr_filled[l] = l < n_levels ? nr_filled_ptrs[l] : nullptr;
+        p.status[l] = l < n_levels ? status_ptrs[l] : nullptr;
+    }
+    ln::launch_k(ln::levels_status_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, p, n_levels, nv_out, overflow_out);
+    ln::count_launch();
+    return ln::check_launch("levels_status");
+}
 
 const char* ln_version(void) { return "lattice_b200 0.1 sm_100a"; }
 const char* ln_last_error(void) { return ln::g_error; }

@@ -764,6 +764,138 @@ scatter_sum_count_kernel(const float* __restrict__ src, const int* __restrict__ 
     if (col == 0 && out_count != nullptr) atomicAdd(out_count + v, 1.0f);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Learned barycentric offsets of the DeformSlice head (lattice_modules.py:465-567), one kernel each way instead of
+// gather -> view -> max -> affine -> subtract -> Linear(9 -> 1) -> reshape (and their ~20 autograd kernels):
+//   g[r] = [ w_r * values[idx_r, 0:8] | w_r ]   (zeros where idx_r < 0: gather_with_precomputation, LatticeGPU.cuh:2886-2929)
+//   m = max_r g[r];   t[r] = g[r] - (gamma * m + beta);   delta_w[p, r] = <W, t[r]> + bias
+constexpr int kDwC = 8;            // bottleneck width of the slice head
+constexpr int kDwF = kDwC + 1;     // features per simplex vertex
+
+template <int SPV>
+__device__ __forceinline__ void deltaw_features(const float* __restrict__ values, const int* __restrict__ indices,
+                                                const float* __restrict__ weights, long long p, int* id, float* w, float (*g)[kDwF]) {
+    load_simplex<SPV>(indices, weights, p, id, w);
+#pragma unroll
+    for (int r = 0; r < SPV; r++) {
+        if (id[r] >= 0) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(values + (size_t)id[r] * kDwC));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(values + (size_t)id[r] * kDwC) + 1);
+            g[r][0] = a.x * w[r]; g[r][1] = a.y * w[r]; g[r][2] = a.z * w[r]; g[r][3] = a.w * w[r];
+            g[r][4] = b.x * w[r]; g[r][5] = b.y * w[r]; g[r][6] = b.z * w[r]; g[r][7] = b.w * w[r];
+            g[r][8] = w[r];
+        } else {
+#pragma unroll
+            for (int j = 0; j < kDwF; j++) g[r][j] = 0.0f;
+        }
+    }
+}
+
+template <int SPV>
+__global__ void __launch_bounds__(kBlock)
+deltaw_fwd_kernel(const float* __restrict__ values, const int* __restrict__ indices, const float* __restrict__ weights,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ lin_w,
+                  const float* __restrict__ lin_b, int n, float* __restrict__ delta_w) {
+    LN_PDL_ENTRY();
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int id[SPV];
+    float w[SPV], g[SPV][kDwF];
+    deltaw_features<SPV>(values, indices, weights, p, id, w, g);
+    float out[SPV];
+    const float b0 = __ldg(lin_b);
+#pragma unroll
+    for (int r = 0; r < SPV; r++) out[r] = b0;
+#pragma unroll
+    for (int j = 0; j < kDwF; j++) {
+        float m = g[0][j];
+#pragma unroll
+        for (int r = 1; r < SPV; r++) m = fmaxf(m, g[r][j]);
+        const float shift = __ldg(gamma + j) * m + __ldg(beta + j);
+        const float wj = __ldg(lin_w + j);
+#pragma unroll
+        for (int r = 0; r < SPV; r++) out[r] = fmaf(wj, g[r][j] - shift, out[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < SPV; r++) delta_w[p * SPV + r] = out[r];
+}
+
+// the four small gradients (zeroed by the caller) are accumulated with one atomic per CTA and element
+template <int SPV>
+__global__ void __launch_bounds__(kBlock)
+deltaw_bwd_kernel(const float* __restrict__ values, const int* __restrict__ indices, const float* __restrict__ weights,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ lin_w,
+                  const float* __restrict__ grad_delta_w, int n, float* __restrict__ grad_values, float* __restrict__ g_lin_w,
+                  float* __restrict__ g_lin_b, float* __restrict__ g_gamma, float* __restrict__ g_beta) {
+    LN_PDL_ENTRY();
+    __shared__ float red[3 * kDwF + 1][kBlock / 32];
+    float acc[3 * kDwF + 1];
+#pragma unroll
+    for (int k = 0; k < 3 * kDwF + 1; k++) acc[k] = 0.0f;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        int id[SPV];
+        float w[SPV], g[SPV][kDwF], d[SPV];
+        deltaw_features<SPV>(values, indices, weights, p, id, w, g);
+        float dsum = 0.0f;
+#pragma unroll
+        for (int r = 0; r < SPV; r++) {
+            d[r] = __ldg(grad_delta_w + p * SPV + r);
+            dsum += d[r];
+        }
+        acc[kDwF] += dsum;                                   // d bias
+        float dv[SPV][kDwC];
+#pragma unroll
+        for (int j = 0; j < kDwF; j++) {
+            float m = g[0][j];
+            int arg = 0;
+#pragma unroll
+            for (int r = 1; r < SPV; r++)
+                if (g[r][j] > m) {                           // first maximum, as torch.max(dim) reports it
+                    m = g[r][j];
+                    arg = r;
+                }
+            const float gm = __ldg(gamma + j), wj = __ldg(lin_w + j);
+            const float shift = gm * m + __ldg(beta + j);
+            float dwj = 0.0f;
+#pragma unroll
+            for (int r = 0; r < SPV; r++) dwj = fmaf(d[r], g[r][j] - shift, dwj);
+            acc[j] += dwj;                                   // d lin_w[j]
+            const float dt_sum = wj * dsum;                  // sum_r d t[r][j]
+            acc[kDwF + 1 + j] -= m * dt_sum;                 // d gamma[j]
+            acc[2 * kDwF + 1 + j] -= dt_sum;                 // d beta[j]
+            if (j < kDwC) {
+#pragma unroll
+                for (int r = 0; r < SPV; r++) dv[r][j] = (d[r] * wj - (r == arg ? gm * dt_sum : 0.0f)) * w[r];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < SPV; r++) {
+            if (id[r] < 0) continue;
+            float* dst = grad_values + (size_t)id[r] * kDwC;
+            atomicAdd(reinterpret_cast<float4*>(dst), make_float4(dv[r][0], dv[r][1], dv[r][2], dv[r][3]));
+            atomicAdd(reinterpret_cast<float4*>(dst) + 1, make_float4(dv[r][4], dv[r][5], dv[r][6], dv[r][7]));
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 3 * kDwF + 1; k++) {
+        float v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[k][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * kDwF + 1) {
+        float t = 0.0f;
+#pragma unroll
+        for (int wv = 0; wv < kBlock / 32; wv++) t += red[threadIdx.x][wv];
+        const int k = threadIdx.x;       // acc layout: [0:9) d lin_w, [9] d lin_b, [10:19) d gamma, [19:28) d beta
+        float* dst = k < kDwF ? g_lin_w + k : k == kDwF ? g_lin_b : k < 2 * kDwF + 1 ? g_gamma + (k - kDwF - 1) : g_beta + (k - 2 * kDwF - 1);
+        atomicAdd(dst, t);
+    }
+}
+
 }  // namespace ln
 
 using namespace ln;
@@ -979,6 +1111,38 @@ int ln_scatter_sum_count(const float* src, const int* index, int m, int c, int n
         count_launch();
     }
     return check_launch("scatter_sum_count");
+}
+
+int ln_deltaw_fwd(const float* values, const int* indices, const float* weights, const float* gamma, const float* beta,
+                  const float* lin_w, const float* lin_b, int n, int pos_dim, int val_dim, float* delta_w, void* stream) {
+    LN_REQUIRE(values && indices && weights && gamma && beta && lin_w && lin_b && delta_w, "ln_deltaw_fwd: null pointer");
+    LN_REQUIRE(n >= 0 && val_dim == kDwC && (pos_dim == 3 || pos_dim == 5), "ln_deltaw_fwd: built for val_dim 8 and pos_dim 3 / 5 (got %d, %d)", val_dim, pos_dim);
+    if (n == 0) return LN_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (pos_dim == 3)
+        launch_k(deltaw_fwd_kernel<4>, dim3(cdiv(n, kBlock)), dim3(kBlock), 0, s, values, indices, weights, gamma, beta, lin_w, lin_b, n, delta_w);
+    else
+        launch_k(deltaw_fwd_kernel<6>, dim3(cdiv(n, kBlock)), dim3(kBlock), 0, s, values, indices, weights, gamma, beta, lin_w, lin_b, n, delta_w);
+    count_launch();
+    return check_launch("deltaw_fwd");
+}
+
+int ln_deltaw_bwd(const float* values, const int* indices, const float* weights, const float* gamma, const float* beta,
+                  const float* lin_w, const float* grad_delta_w, int n, int pos_dim, int val_dim, float* grad_values_zeroed,
+                  float* grad_lin_w_zeroed, float* grad_lin_b_zeroed, float* grad_gamma_zeroed, float* grad_beta_zeroed, void* stream) {
+    LN_REQUIRE(values && indices && weights && gamma && beta && lin_w && grad_delta_w && grad_values_zeroed && grad_lin_w_zeroed &&
+                   grad_lin_b_zeroed && grad_gamma_zeroed && grad_beta_zeroed,
+               "ln_deltaw_bwd: null pointer");
+    LN_REQUIRE(n >= 0 && val_dim == kDwC && (pos_dim == 3 || pos_dim == 5), "ln_deltaw_bwd: built for val_dim 8 and pos_dim 3 / 5");
+    if (n == 0) return LN_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = min(cdiv(n, kBlock), device_sms() * 4);
+    if (pos_dim == 3)
+        launch_k(deltaw_bwd_kernel<4>, dim3(grid), dim3(kBlock), 0, s, values, indices, weights, gamma, beta, lin_w, grad_delta_w, n, grad_values_zeroed, grad_lin_w_zeroed, grad_lin_b_zeroed, grad_gamma_zeroed, grad_beta_zeroed);
+    else
+        launch_k(deltaw_bwd_kernel<6>, dim3(grid), dim3(kBlock), 0, s, values, indices, weights, gamma, beta, lin_w, grad_delta_w, n, grad_values_zeroed, grad_lin_w_zeroed, grad_lin_b_zeroed, grad_gamma_zeroed, grad_beta_zeroed);
+    count_launch();
+    return check_launch("deltaw_bwd");
 }
 
 }  // extern "C"

@@ -240,6 +240,56 @@ adamw_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Weight normalisation of a filter bank, reference utils.weight_norm_wrapper(cls, g_dim, v_dim=None)
+// (/root/reference/latticenet_py/utils/utils.py:72-158): w = v * (g / ||v||_F), one gain per slice of dimension g_dim.
+// v is [rows x cols]; gain_per_col != 0: g has `cols` entries (g_dim = 1, the lattice filter banks), else `rows`
+// (g_dim = 0, Linear).  One CTA: the bank of the one weight-normalised convolution of LatticeNet is 37 k floats.
+__global__ void __launch_bounds__(kLossThreads)
+weight_norm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, int rows, int cols, int gain_per_col,
+                       float* __restrict__ w) {
+    LN_PDL_ENTRY();
+    __shared__ float red[33];
+    const int n = rows * cols;
+    float s = 0.0f;
+    for (int i = threadIdx.x; i < n; i += kLossThreads) {
+        const float x = __ldg(v + i);
+        s = fmaf(x, x, s);
+    }
+    const float norm = sqrtf(block_sum_1024(s, red));
+    for (int i = threadIdx.x; i < n; i += kLossThreads) w[i] = __ldg(v + i) * (__ldg(g + (gain_per_col ? i % cols : i / cols)) / norm);
+}
+
+//   dg[j] = sum_{i in slice j} dw_i v_i / n;   dv_i = dw_i g[j(i)] / n  -  v_i (sum_i dw_i v_i g[j(i)]) / n^3
+__global__ void __launch_bounds__(kLossThreads)
+weight_norm_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ dw, int rows, int cols,
+                       int gain_per_col, float* __restrict__ dv, float* __restrict__ dg) {
+    LN_PDL_ENTRY();
+    __shared__ float red[33];
+    const int n = rows * cols;
+    float s = 0.0f, dot = 0.0f;
+    for (int i = threadIdx.x; i < n; i += kLossThreads) {
+        const float x = __ldg(v + i);
+        s = fmaf(x, x, s);
+        dot = fmaf(__ldg(dw + i) * x, __ldg(g + (gain_per_col ? i % cols : i / cols)), dot);
+    }
+    const float n2 = block_sum_1024(s, red);
+    const float total = block_sum_1024(dot, red);
+    const float norm = sqrtf(n2);
+    for (int i = threadIdx.x; i < n; i += kLossThreads)
+        dv[i] = __ldg(dw + i) * (__ldg(g + (gain_per_col ? i % cols : i / cols)) / norm) - __ldg(v + i) * (total / (n2 * norm));
+    const int n_gain = gain_per_col ? cols : rows;
+    for (int j = threadIdx.x; j < n_gain; j += kLossThreads) {
+        float d = 0.0f;
+        if (gain_per_col)
+            for (int r = 0; r < rows; r++) d = fmaf(__ldg(dw + (size_t)r * cols + j), __ldg(v + (size_t)r * cols + j), d);
+        else
+            for (int c = 0; c < cols; c++) d = fmaf(__ldg(dw + (size_t)j * cols + c), __ldg(v + (size_t)j * cols + c), d);
+        dg[j] = d / norm;
+    }
+}
+
 }  // namespace ln
 
 using namespace ln;
@@ -292,6 +342,21 @@ int ln_adamw_amsgrad(float* params, const float* grads, float* exp_avg, float* e
                                                                   weight_decay, grad_scale, state, skip);
     count_launch();
     return check_launch("adamw_amsgrad");
+}
+
+int ln_weight_norm_fwd(const float* v, const float* g, int rows, int cols, int gain_per_col, float* w, void* stream) {
+    LN_REQUIRE(v && g && w && rows >= 1 && cols >= 1, "ln_weight_norm_fwd: bad argument");
+    launch_k(weight_norm_fwd_kernel, dim3(1), dim3(kLossThreads), 0, (cudaStream_t)stream, v, g, rows, cols, gain_per_col, w);
+    count_launch();
+    return check_launch("weight_norm_fwd");
+}
+
+int ln_weight_norm_bwd(const float* v, const float* g, const float* dw, int rows, int cols, int gain_per_col, float* dv, float* dg,
+                       void* stream) {
+    LN_REQUIRE(v && g && dw && dv && dg && rows >= 1 && cols >= 1, "ln_weight_norm_bwd: bad argument");
+    launch_k(weight_norm_bwd_kernel, dim3(1), dim3(kLossThreads), 0, (cudaStream_t)stream, v, g, dw, rows, cols, gain_per_col, dv, dg);
+    count_launch();
+    return check_launch("weight_norm_bwd");
 }
 
 }  // extern "C"

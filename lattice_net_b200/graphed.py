@@ -88,10 +88,12 @@ class GraphedTrainStep:
             _lattice.set_zero_arena(prev)
             self.bucket.end_direct_step()
         self.loss.copy_(loss.detach())
-        levels = self.model.last_level_lattices
-        flags = torch.stack([l.m_hash_table.structure.status[0] for l in levels]).max()
-        self.nv_actual.copy_(torch.cat([l.m_hash_table.structure.nr_filled for l in levels]))
-        self.found_inf.copy_((flags > 0).to(torch.float32))
+        import ctypes
+        from ._cabi import call, ptr, stream_ptr
+        sts = [l.m_hash_table.structure for l in self.model.last_level_lattices]
+        call("ln_levels_status", (ctypes.c_void_p * len(sts))(*[s.nr_filled.data_ptr() for s in sts]),
+             (ctypes.c_void_p * len(sts))(*[s.status.data_ptr() for s in sts]), len(sts), ptr(self.nv_actual), ptr(self.found_inf),
+             stream_ptr(self.device))
         if self.world > 1 or self.flat_optimizer:
             # gradients that did not land in the bucket by themselves (a handful: weight-norm, slice-head scalars) are copied in
             self.bucket.pack(extra=self.found_inf)

@@ -1007,7 +1007,7 @@ class Lattice:
         st = self._structure()
         _check_dev_tensor(grad_sliced_values, torch.float32, st.device, "grad_sliced_values")
         v = int(grad_sliced_values.shape[1])
-        grad = torch.zeros((st.nr_vertices(), v), dtype=torch.float32, device=st.device)
+        grad = _zeroed(st.nr_vertices(), v, st.device)
         call("ln_slice_bwd", ptr(grad_sliced_values), ptr(idx), ptr(w), n, d, v, int(grad.shape[0]), ptr(grad), stream_ptr(st.device))
         self.m_hash_table.m_values_tensor = grad
 
@@ -1018,7 +1018,7 @@ class Lattice:
         st = self._structure()
         _check_dev_tensor(grad_sliced_values, torch.float32, st.device, "grad_sliced_values")
         v = int(grad_sliced_values.shape[1]) // (d + 1) - 1
-        grad = torch.zeros((st.nr_vertices(), v), dtype=torch.float32, device=st.device)
+        grad = _zeroed(st.nr_vertices(), v, st.device)
         call("ln_gather_bwd", ptr(grad_sliced_values), ptr(idx), ptr(w), n, d, v, ptr(grad), stream_ptr(st.device))
         self.m_hash_table.m_values_tensor = grad
 

@@ -12,6 +12,7 @@ import sys
 import torch
 from torch.autograd import Function
 
+from . import lattice as _lattice_mod
 from .lattice_wrapper import LatticeWrapper
 
 
@@ -231,10 +232,21 @@ class SliceClassifyLattice(Function):
     def backward(ctx, grad_class_logits):
         positions, initial_values, delta_weights, cls_w, cls_b, splatting_indices, splatting_weights = ctx.saved_tensors
         lattice = ctx.lattice_structure
-        grad_lattice_values = torch.zeros_like(initial_values)
-        grad_delta_weights = torch.zeros_like(delta_weights)
-        grad_cls_w = torch.zeros_like(cls_w)
-        grad_cls_b = torch.zeros_like(cls_b)
+        zeroed = getattr(_lattice_mod, "_zeroed", None)
+        if initial_values.is_cuda and zeroed is not None:
+            # one memset per step clears the arena these come from (graphed step); the classifier gradients go straight
+            # into their gradient-bucket slices when a zeroed bucket is active
+            grad_lattice_values = zeroed(initial_values.shape[0], initial_values.shape[1], initial_values.device)
+            grad_delta_weights = zeroed(delta_weights.shape[0], delta_weights.shape[1], delta_weights.device)
+            grad_cls_w = _lattice_mod.grad_target(cls_w) if cls_w.is_leaf else None
+            grad_cls_b = _lattice_mod.grad_target(cls_b) if cls_b.is_leaf else None
+            if grad_cls_w is None or grad_cls_b is None:
+                grad_cls_w, grad_cls_b = torch.zeros_like(cls_w), torch.zeros_like(cls_b)
+        else:
+            grad_lattice_values = torch.zeros_like(initial_values)
+            grad_delta_weights = torch.zeros_like(delta_weights)
+            grad_cls_w = torch.zeros_like(cls_w)
+            grad_cls_b = torch.zeros_like(cls_b)
         lattice.slice_classify_backwards_with_precomputation(
             grad_class_logits.contiguous(), positions, initial_values, delta_weights, cls_w, cls_b, ctx.nr_classes,
             grad_lattice_values, grad_delta_weights, grad_cls_w, grad_cls_b, splatting_indices, splatting_weights)

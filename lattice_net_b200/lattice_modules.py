@@ -181,7 +181,7 @@ class _PointNetFusedFn(torch.autograd.Function):
         v = values.shape[1]
         dev = positions.device
         widths = [int(params[3 * l].shape[0]) for l in range(3)]
-        scratch = torch.zeros((int(lib.ln_pointnet_scratch_floats(d, int(nv_rows), widths[2])),), dtype=torch.float32, device=dev)
+        scratch = _lattice._zeroed(1, int(lib.ln_pointnet_scratch_floats(d, int(nv_rows), widths[2])), dev).view(-1)
         out = torch.empty((nv_rows, 2 * widths[2]), dtype=torch.float32, device=dev)
         arg = torch.empty((nv_rows, widths[2]), dtype=torch.int32, device=dev)
         ps = [p.contiguous() for p in params]
@@ -203,7 +203,7 @@ class _PointNetFusedFn(torch.autograd.Function):
         v = values.shape[1]
         dev = positions.device
         w = ctx.widths
-        gscratch = torch.zeros((int(load().ln_pointnet_grad_scratch_floats(d, v, w[0], w[1], w[2])),), dtype=torch.float32, device=dev)
+        gscratch = _lattice._zeroed(1, int(load().ln_pointnet_grad_scratch_floats(d, v, w[0], w[1], w[2])), dev).view(-1)
         grads = []
         for p in ps:
             t = _lattice.grad_target(p)
@@ -213,6 +213,40 @@ class _PointNetFusedFn(torch.autograd.Function):
         call("ln_pointnet_bwd", ptr(positions), ptr(sigmas), ptr(values), ptr(indices), n, d, v, ptrs, gptrs, w[0], w[1], w[2],
              1 if ctx.quirk else 0, ptr(scratch), ptr(grad_out.contiguous()), ptr(arg), ptr(gscratch), stream_ptr(dev))
         return (None,) * 7 + tuple(grads)
+
+
+class _DeltaWFn(torch.autograd.Function):
+    """Learned barycentric offsets of the DeformSlice head in one kernel each way (ln_deltaw_fwd / _bwd):
+    (bottleneck values [nv x 8], indices, weights, gamma [9], beta [9], lin_w [1 x 9], lin_b [1], pos_dim) -> [N x (d+1)]."""
+
+    @staticmethod
+    def forward(ctx, values, indices, weights, gamma, beta, lin_w, lin_b, pos_dim):
+        values = values.contiguous()
+        n = indices.numel() // (pos_dim + 1)
+        out = torch.empty((n, pos_dim + 1), dtype=torch.float32, device=values.device)
+        call("ln_deltaw_fwd", ptr(values), ptr(indices), ptr(weights), ptr(gamma.contiguous()), ptr(beta.contiguous()), ptr(lin_w.contiguous()),
+             ptr(lin_b.contiguous()), n, pos_dim, int(values.shape[1]), ptr(out), stream_ptr(values.device))
+        ctx.save_for_backward(values, indices, weights, gamma, beta, lin_w, lin_b)
+        ctx.pos_dim = pos_dim
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        values, indices, weights, gamma, beta, lin_w, lin_b = ctx.saved_tensors
+        n = indices.numel() // (ctx.pos_dim + 1)
+        dev = values.device
+        g_values = _lattice._zeroed(values.shape[0], values.shape[1], dev)
+        grads = []
+        for p in (lin_w, lin_b, gamma, beta):        # bucket slices when a zeroed gradient bucket is active, fresh zeros otherwise
+            t = _lattice.grad_target(p)
+            grads.append(t)
+        if any(t is None for t in grads):
+            small = torch.zeros((28,), dtype=torch.float32, device=dev)
+            grads = [small[0:9].view_as(lin_w), small[9:10].view_as(lin_b), small[10:19].view_as(gamma), small[19:28].view_as(beta)]
+        call("ln_deltaw_bwd", ptr(values), ptr(indices), ptr(weights), ptr(gamma.contiguous()), ptr(beta.contiguous()), ptr(lin_w.contiguous()),
+             ptr(grad_out.contiguous()), n, ctx.pos_dim, int(values.shape[1]), ptr(g_values), ptr(grads[0]), ptr(grads[1]), ptr(grads[2]),
+             ptr(grads[3]), stream_ptr(dev))
+        return g_values, None, None, grads[2], grads[3], grads[0], grads[1], None
 
 
 def linear(x, weight, bias=None, residual=None):
@@ -248,8 +282,35 @@ def _split_weight_norm(module, g_dim):
     module._wn_g_dim = g_dim
 
 
+class _WeightNormFn(torch.autograd.Function):
+    """w = v * (g / ||v||) in one kernel each way (ln_weight_norm_fwd / _bwd) for 2-D CUDA weights."""
+
+    @staticmethod
+    def forward(ctx, v, g, g_dim):
+        v, g = v.contiguous(), g.contiguous()
+        w = torch.empty_like(v)
+        call("ln_weight_norm_fwd", ptr(v), ptr(g), int(v.shape[0]), int(v.shape[1]), 1 if g_dim == 1 else 0, ptr(w), stream_ptr(v.device))
+        ctx.save_for_backward(v, g)
+        ctx.g_dim = g_dim
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        v, g = ctx.saved_tensors
+        dv = _lattice.grad_target(v)
+        dg = _lattice.grad_target(g)
+        if dv is None or dg is None:
+            dv, dg = torch.empty_like(v), torch.empty_like(g)
+        call("ln_weight_norm_bwd", ptr(v), ptr(g), ptr(dw.contiguous()), int(v.shape[0]), int(v.shape[1]), 1 if ctx.g_dim == 1 else 0, ptr(dv),
+             ptr(dg), stream_ptr(v.device))
+        return dv, dg, None
+
+
 def _normed_weight(module):
-    return module.weight_v * (module.weight_g / module.weight_v.norm())
+    v, g = module.weight_v, module.weight_g
+    if v.is_cuda and v.dim() == 2 and v.dtype == torch.float32 and v.numel() <= (1 << 22):
+        return _WeightNormFn.apply(v, g, module._wn_g_dim)
+    return v * (g / v.norm())
 
 
 class LinearWN(torch.nn.Linear):
@@ -908,6 +969,7 @@ class SliceFastCUDALatticeModule(torch.nn.Module):
         if dropout_prob > 0.0:
             self.dropout = DropoutLattice(dropout_prob)
         self.experiment = experiment
+        self.fused_delta_weights = True     # False: gather -> max -> affine -> Linear as separate torch ops (the reference's sequence)
         cur = in_channels
         for i in range(2):
             nr_out = int(in_channels / np.power(2, i))
@@ -927,9 +989,13 @@ class SliceFastCUDALatticeModule(torch.nn.Module):
         for layer in self.stepdown:
             lv_b, ls_b = layer(lv_b, ls_b)
         lv_b, ls_b = self.bottleneck(lv_b, ls_b)
-        gathered = GatherLattice.apply(lv_b, ls_b, positions, splatting_indices, splatting_weights)
         spv = ls.pos_dim() + 1
-        per_vertex = int(gathered.shape[1] / spv)
+        per_vertex = self.bottleneck_size + 1
+        fused = (self.fused_delta_weights and lv.is_cuda and self.bottleneck_size == 8 and spv in (4, 6) and self.experiment != "slice_no_deform"
+                 and splatting_indices is not None and hasattr(ls, "m_hash_table"))
+        if not fused:
+            gathered = GatherLattice.apply(lv_b, ls_b, positions, splatting_indices, splatting_weights)
+            per_vertex = int(gathered.shape[1] / spv)
         if self.linear_deltaW is None:
             self.linear_deltaW = torch.nn.Linear(per_vertex, 1, bias=True).to(lv.device)
             with torch.no_grad():
@@ -938,12 +1004,17 @@ class SliceFastCUDALatticeModule(torch.nn.Module):
                 torch.nn.init.zeros_(self.linear_deltaW.bias)
             self.gamma = torch.nn.Parameter(torch.ones(per_vertex, device=lv.device))
             self.beta = torch.nn.Parameter(torch.zeros(per_vertex, device=lv.device))
-        gathered = gathered.view(nr_positions, spv, per_vertex)
-        max_vals, _ = gathered.max(1)
-        gathered = gathered - (self.gamma * max_vals.unsqueeze(1) + self.beta)
-        delta_weights = self.linear_deltaW(gathered).reshape(nr_positions, spv)
-        if self.experiment == "slice_no_deform":
-            delta_weights = delta_weights * 0
+        if fused:
+            ls_b.set_values(lv_b)
+            delta_weights = _DeltaWFn.apply(lv_b, splatting_indices, splatting_weights, self.gamma, self.beta, self.linear_deltaW.weight,
+                                            self.linear_deltaW.bias, spv - 1)
+        else:
+            gathered = gathered.view(nr_positions, spv, per_vertex)
+            max_vals, _ = gathered.max(1)
+            gathered = gathered - (self.gamma * max_vals.unsqueeze(1) + self.beta)
+            delta_weights = self.linear_deltaW(gathered).reshape(nr_positions, spv)
+            if self.experiment == "slice_no_deform":
+                delta_weights = delta_weights * 0
         if self.linear_clasify is None:
             self.linear_clasify = torch.nn.Linear(val_dim, self.nr_classes, bias=True).to(lv.device)
             leaky_relu_init_(self.linear_clasify.weight, val_dim + self.nr_classes, alpha=1.0)

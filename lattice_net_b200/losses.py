@@ -80,7 +80,8 @@ class _SegLossFn(torch.autograd.Function):
         n, c = lp.shape
         dev = lp.device
         grad_lov = torch.empty((n, c), dtype=torch.float32, device=dev)
-        scratch = torch.zeros((12,), dtype=torch.float32, device=dev)        # [0:8) accumulators (zeroed), [8:12) result
+        from . import lattice as _lattice
+        scratch = _lattice._zeroed(1, 12, dev).view(-1)                        # [0:8) accumulators (zeroed), [8:12) result
         call("ln_seg_loss_fwd", ptr(lp), ptr(labels), n, c, int(ignore_index), ptr(grad_lov), ptr(scratch[:8]), ptr(scratch[8:]), stream_ptr(dev))
         ctx.save_for_backward(grad_lov, labels, scratch)
         ctx.ignore_index = int(ignore_index)

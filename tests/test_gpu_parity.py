@@ -1408,3 +1408,57 @@ def test_programmatic_dependent_launch_does_not_change_results(built):
         lib.ln_set_programmatic_launch(prev)
     for a, c, what in zip(on, off, ("sliced", "dx", "dw", "dgamma", "dbeta")):
         assert_close(a, c, 1e-4, f"programmatic launch on vs off: {what}")
+
+
+def test_fused_delta_weights_match_the_torch_sequence(built):
+    """ln_deltaw_fwd / _bwd against gather -> view -> max -> affine -> subtract -> Linear(9 -> 1)
+    (lattice_modules.py:465-567) through the slice head module with the fusion switched off: logits to 1e-5, every
+    gradient (head parameters and incoming lattice values) to 1e-4."""
+    from lattice_net_b200 import lattice_modules as lm
+    b = built
+    if b["name"] == "boundary":
+        pytest.skip("two clouds cover it")
+    torch.manual_seed(21)
+    dev = torch.device("cuda", 0)
+    C, nc = 64, 7
+    head = lm.SliceFastCUDALatticeModule(C, nc, 0.0, "none", device=dev)
+    lv0 = torch.randn((b["nv"], C), device=dev)
+    g = torch.randn((b["n"], nc), device=dev)
+    with torch.no_grad():
+        head(lv0, b["ours"].clone_lattice(), b["pos"], b["idx"], b["w"])         # lazy layers
+        head.linear_deltaW.weight.normal_(0.0, 0.5)
+        head.linear_deltaW.bias.fill_(0.1)
+        head.gamma.uniform_(0.5, 1.5)
+        head.beta.uniform_(-0.3, 0.3)
+    outs = []
+    for fused in (False, True):
+        head.fused_delta_weights = fused
+        for p in head.parameters():
+            p.grad = None
+        lv = lv0.clone().requires_grad_(True)
+        logits = head(lv, b["ours"].clone_lattice(), b["pos"], b["idx"], b["w"])
+        (logits * g).sum().backward()
+        outs.append((logits.detach().cpu().numpy(), lv.grad.cpu().numpy(), {n_: p.grad.cpu().numpy().copy() for n_, p in head.named_parameters()}))
+    assert_close(outs[1][0], outs[0][0], 1e-5, "logits with fused delta weights")
+    assert_close(outs[1][1], outs[0][1], 1e-4, "gradient of the lattice values")
+    for name, ga in outs[0][2].items():
+        assert_close(outs[1][2][name], ga, 1e-4, f"gradient of {name}")
+
+
+@pytest.mark.parametrize("rows,cols,g_dim", [(1152, 32, 1), (16, 4, 0), (64, 32, 0), (2304, 64, 1)])
+def test_weight_norm_kernels_vs_torch(rows, cols, g_dim):
+    from lattice_net_b200.lattice_modules import _WeightNormFn
+    torch.manual_seed(rows + cols)
+    v = torch.randn(rows, cols, device="cuda", requires_grad=True)
+    gshape = (1, cols) if g_dim == 1 else (rows, 1)
+    g = (torch.rand(*gshape, device="cuda") + 0.5).requires_grad_(True)
+    up = torch.randn(rows, cols, device="cuda")
+    w = _WeightNormFn.apply(v, g, g_dim)
+    w.backward(up)
+    got = (w.detach().clone(), v.grad.clone(), g.grad.clone())
+    v.grad = g.grad = None
+    wr = v * (g / v.norm())
+    wr.backward(up)
+    assert_close(got[0].cpu().numpy(), wr.detach().cpu().numpy(), 1e-6, "weight norm forward")
+    assert_close(got[1].cpu().numpy(), v.grad.cpu().numpy(), 1e-5, "weight norm dv")
+    assert_close(got[2].cpu().numpy(), g.grad.cpu().numpy(), 1e-5, "weight norm dg")
