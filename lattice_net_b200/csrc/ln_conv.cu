@@ -12,7 +12,7 @@ namespace ln {
 
 // ln_conv_tc.cu
 int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* slabs, const float* bias, const float* residual, int nv_query,
-                int F, int c_in, int c_out, int flip, int precision, float* out, cudaStream_t s);
+                int F, int c_in, int c_out, int flip, int precision, float* out, int cta_budget, cudaStream_t s);
 int filter_prepare(const float* filter, int F, int c_in, int c_out, int transposed, int precision, float* slabs, cudaStream_t s);
 int filter_prepare_batch(const void* jobs_device, int n_jobs, long long total_threads, cudaStream_t s);
 size_t conv_tc_workspace_bytes(int F, int c_in, int c_out);
@@ -21,7 +21,7 @@ bool conv_tc_needs_zero(int nv_query, int F, int c_in);
 bool conv_wgrad_tc_supported(int F, int c_in, int c_out);
 bool conv_wgrad_tc_needs_zero(int nv_query, int F, int c_in);
 int conv_wgrad_tc(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query, int F, int c_in,
-                  int c_out, int precision, float* grad_filter, cudaStream_t s);
+                  int c_out, int precision, float* grad_filter, int cta_budget, cudaStream_t s);
 
 constexpr int kThreads = 256;
 constexpr int BM = 64, BN = 64, BK = 16;
@@ -223,13 +223,13 @@ SideStream* side_stream() {
 
 int conv_wgrad_launch(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query,
                       int filter_extent, int c_in, int c_out, int precision, float* grad_filter, bool already_zero,
-                      cudaStream_t s) {
+                      int cta_budget, cudaStream_t s) {
     const size_t bytes = (size_t)filter_extent * c_in * c_out * sizeof(float);
     const bool tc = precision != 0 && conv_wgrad_tc_supported(filter_extent, c_in, c_out);
     const bool needs_zero = nv_query == 0 || !tc || conv_wgrad_tc_needs_zero(nv_query, filter_extent, c_in);
     if (needs_zero && !already_zero && cudaMemsetAsync(grad_filter, 0, bytes, s) != cudaSuccess) return check_launch("conv_wgrad memset");
     if (nv_query == 0) return LN_OK;
-    if (tc) return conv_wgrad_tc(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, precision, grad_filter, s);
+    if (tc) return conv_wgrad_tc(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, precision, grad_filter, cta_budget, s);
     const int ci_tiles = cdiv(c_in, BM), co_tiles = cdiv(c_out, BN);
     // enough q-chunks to fill the machine (~4 waves of 148 SMs), at least 256 rows each
     const int tiles = ci_tiles * co_tiles * filter_extent;
@@ -245,7 +245,7 @@ int conv_wgrad_launch(const float* nbr_values, const int* neighbours, const floa
 // out = conv(values through `neighbours`) [+ bias] [+ residual]; tensor cores when the shape allows and precision != 0
 int conv_launch(const float* nbr_values, const int* neighbours, const float* filter, const float* bias, const float* residual, int nv_query,
                 int filter_extent, int c_in, int c_out, int flip, int transposed_filter, int precision, float* slabs, int slabs_prepared,
-                int out_is_zero, float* out, cudaStream_t s, const char* what) {
+                int out_is_zero, float* out, int cta_budget, cudaStream_t s, const char* what) {
     if (precision != 0 && conv_tc_supported(filter_extent, c_in, c_out)) {
         if (slabs == nullptr) {
             set_error("%s: precision %d needs a slab buffer of ln_conv_workspace_bytes() bytes", what, precision);
@@ -258,7 +258,7 @@ int conv_launch(const float* nbr_values, const int* neighbours, const float* fil
         if (!out_is_zero && conv_tc_needs_zero(nv_query, filter_extent, c_in) &&
             cudaMemsetAsync(out, 0, (size_t)nv_query * c_out * sizeof(float), s) != cudaSuccess)
             return check_launch("conv memset");
-        return conv_fwd_tc(nbr_values, neighbours, slabs, bias, residual, nv_query, filter_extent, c_in, c_out, flip, precision, out, s);
+        return conv_fwd_tc(nbr_values, neighbours, slabs, bias, residual, nv_query, filter_extent, c_in, c_out, flip, precision, out, cta_budget, s);
     }
     dim3 grid(cdiv(nv_query, BM), cdiv(c_out, BN));
     launch_k(conv_fwd_simt_kernel, dim3(grid), dim3(kThreads), 0, s, nbr_values, neighbours, filter, bias, residual, nv_query, filter_extent, c_in, c_out, flip,
@@ -301,7 +301,7 @@ int ln_conv_fwd(const float* nbr_values, const int* neighbours, const float* fil
     LN_REQUIRE(precision >= 0 && precision <= 2, "ln_conv_fwd: precision must be 0 (fp32), 1 (3xTF32) or 2 (TF32)");
     if (nv_query == 0) return LN_OK;
     return conv_launch(nbr_values, neighbours, filter, bias, residual, nv_query, filter_extent, c_in, c_out, flip, transposed_filter, precision,
-                       slabs, slabs_prepared, out_is_zero, out, (cudaStream_t)stream, "conv_fwd_simt");
+                       slabs, slabs_prepared, out_is_zero, out, 0, (cudaStream_t)stream, "conv_fwd_simt");
 }
 
 int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query,
@@ -310,7 +310,7 @@ int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* g
     LN_REQUIRE(nv_query >= 0 && filter_extent >= 1 && c_in >= 1 && c_out >= 1, "ln_conv_wgrad: bad size");
     LN_REQUIRE(precision >= 0 && precision <= 2, "ln_conv_wgrad: precision must be 0 (fp32), 1 (3xTF32) or 2 (TF32)");
     return conv_wgrad_launch(nbr_values, neighbours, grad_out, nv_query, filter_extent, c_in, c_out, precision, grad_filter, grad_is_zero != 0,
-                             (cudaStream_t)stream);
+                             0, (cudaStream_t)stream);
 }
 
 int ln_conv_bwd(const float* nbr_values, const int* neighbours_fwd, const float* grad_out, const int* neighbours_bwd,
@@ -326,14 +326,22 @@ int ln_conv_bwd(const float* nbr_values, const int* neighbours_fwd, const float*
     SideStream* ss = (want_dgrad && grad_filter != nullptr && nv_query > 0) ? side_stream() : nullptr;
     if (ss != nullptr && (cudaEventRecord(ss->fork, s) != cudaSuccess || cudaStreamWaitEvent(ss->stream, ss->fork, 0) != cudaSuccess))
         return check_launch("conv_bwd fork");
+    // both kernels take an SM per CTA: when they run side by side each gets half the machine, so neither waits for the other's SMs
+    int half = 0;
+    if (ss != nullptr) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        // (only in the latency-bound regime of small lattices; scene-sized levels keep persistent full-machine grids)
+        if (cdiv(nv_nbr, 128) < sms && cdiv(nv_query, 128) < sms) half = sms / 2;
+    }
     int rw = LN_OK;
     if (grad_filter != nullptr)
         rw = conv_wgrad_launch(nbr_values, neighbours_fwd, grad_out, nv_query, filter_extent, c_in, c_out, precision, grad_filter,
-                               grad_filter_is_zero != 0, ss ? ss->stream : s);
+                               grad_filter_is_zero != 0, half, ss ? ss->stream : s);
     int rd = LN_OK;
     if (want_dgrad)   // flipped convolution of grad_out at the neighbour lattice's vertices, forward bank read transposed (c_in <-> c_out)
         rd = conv_launch(grad_out, neighbours_bwd, filter, nullptr, nullptr, nv_nbr, filter_extent, c_out, c_in, 1, 1, precision, slabs_bwd,
-                         slabs_prepared, grad_nbr_is_zero, grad_nbr_values, s, "conv_dgrad_simt");
+                         slabs_prepared, grad_nbr_is_zero, grad_nbr_values, half, s, "conv_dgrad_simt");
     if (ss != nullptr && (cudaEventRecord(ss->join, ss->stream) != cudaSuccess || cudaStreamWaitEvent(s, ss->join, 0) != cudaSuccess))
         return check_launch("conv_bwd join");
     return rw != LN_OK ? rw : rd;

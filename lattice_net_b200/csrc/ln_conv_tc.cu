@@ -849,14 +849,19 @@ bool conv_wgrad_tc_supported(int F, int c_in, int c_out) {
 
 // K blocks in flight per producer thread = half the ring: a stage published `stages - lookahead` iterations ago has had
 // that long for its MMAs to retire before the producer needs it back (lookahead = stages - 1 serialises the two).
-static inline int lookahead_for(int stages) { return max(1, min(stages - 1, stages / 2)); }
+// A CTA whose whole K range fits the ring (the split-K regime of small lattices) issues everything up front.
+static inline int lookahead_for(int stages, int blocks_per_cta) {
+    if (blocks_per_cta <= stages) return max(1, stages - 1);
+    return max(1, min(stages - 1, stages / 2));
+}
 
 // Vertex-range splits of the weight gradient: enough CTAs for the machine (two waves at most), at least 4 stages of
 // vertices per CTA.
-static int wgrad_q_splits(int nv_query, int F, int c_in) {
+static int wgrad_q_splits(int nv_query, int F, int c_in, int cta_budget = 0) {
     const int tiles = F * cdiv(c_in, 128);
     const int total_chunks = cdiv(nv_query, kWgRows);
-    int q_splits = max(1, min(cdiv(total_chunks, 4), (2 * sm_count()) / tiles));
+    const int ctas = cta_budget > 0 ? cta_budget : 2 * sm_count();
+    int q_splits = max(1, min(cdiv(total_chunks, 4), ctas / tiles));
     const int chunks_per_split = cdiv(total_chunks, q_splits);
     return cdiv(total_chunks, chunks_per_split);
 }
@@ -864,14 +869,14 @@ bool conv_wgrad_tc_needs_zero(int nv_query, int F, int c_in) { return wgrad_q_sp
 
 // grad_filter must be zero when conv_wgrad_tc_needs_zero() (partial sums of vertex ranges are combined with vector atomics).
 static int conv_wgrad_tc_chunk(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query, int F, int c_in,
-                               int c_out, int ld_g, int precision, float* grad_filter, cudaStream_t s) {
+                               int c_out, int ld_g, int precision, float* grad_filter, int cta_budget, cudaStream_t s) {
     const int split = precision == 1 ? 1 : 0;
     const int n_pad = (c_out + 15) / 16 * 16;
     const int n_groups = (n_pad + 31) / 32;
     const int ci_tiles = cdiv(c_in, 128);
     const int total_chunks = cdiv(nv_query, kWgRows);
     const int tiles = F * ci_tiles;
-    const int q_splits = wgrad_q_splits(nv_query, F, c_in);
+    const int q_splits = wgrad_q_splits(nv_query, F, c_in, cta_budget);
     const int chunks_per_split = cdiv(total_chunks, q_splits);
     const size_t stage_bytes = (size_t)(split ? 2 : 1) * (4 + n_groups) * kWgGroupBytes;
     const size_t fixed = (2 * kMaxStages + 1) * 8 + 16 + 1024;
@@ -880,7 +885,7 @@ static int conv_wgrad_tc_chunk(const float* nbr_values, const int* neighbours, c
         set_error("conv_wgrad_tc: tile does not fit shared memory (c_out=%d)", c_out);
         return LN_ERR_UNSUPPORTED;
     }
-    const int lookahead = lookahead_for(stages);
+    const int lookahead = lookahead_for(stages, chunks_per_split);
     // > half of the SM's shared memory: one CTA per SM (TMEM columns, see conv_tc2)
     const size_t smem = max((size_t)stages * stage_bytes + fixed, (size_t)120 * 1024);
     const int grid = tiles * q_splits;
@@ -904,23 +909,26 @@ static int conv_wgrad_tc_chunk(const float* nbr_values, const int* neighbours, c
     return check_launch("conv_wgrad_tc");
 }
 
+// cta_budget (0 = the whole machine): upper bound on the CTAs of one launch, so that a data-gradient convolution running on
+// another stream at the same time finds free SMs (every CTA of either kernel needs an SM to itself)
 int conv_wgrad_tc(const float* nbr_values, const int* neighbours, const float* grad_out, int nv_query, int F, int c_in,
-                  int c_out, int precision, float* grad_filter, cudaStream_t s) {
+                  int c_out, int precision, float* grad_filter, int cta_budget, cudaStream_t s) {
     // column chunks of grad_out / grad_filter (row stride c_out): each chunk is an independent GEMM over the same gathered A
     for (int n_off = 0; n_off < c_out; n_off += kMaxTileN) {
         const int rc = conv_wgrad_tc_chunk(nbr_values, neighbours, grad_out + n_off, nv_query, F, c_in, min(kMaxTileN, c_out - n_off),
-                                           c_out, precision, grad_filter + n_off, s);
+                                           c_out, precision, grad_filter + n_off, cta_budget, s);
         if (rc != LN_OK) return rc;
     }
     return LN_OK;
 }
 
 // K splits of the convolution: enough CTAs for the machine when there are few M tiles (148 SMs, one CTA each)
-static int conv_k_splits(int nv_query, int F, int c_in) {
+static int conv_k_splits(int nv_query, int F, int c_in, int cta_budget = 0) {
     const int num_kb = F * (c_in / kBlockK);
     const int m_tiles = cdiv(nv_query, kTileM);
+    const int ctas = cta_budget > 0 ? min(cta_budget, sm_count()) : sm_count();
     int splits = 1;
-    if (m_tiles < sm_count()) splits = max(1, min(num_kb, sm_count() / m_tiles));
+    if (m_tiles < ctas) splits = max(1, min(num_kb, ctas / m_tiles));
     const int kb_per_split = cdiv(num_kb, splits);
     return cdiv(num_kb, kb_per_split);
 }
@@ -931,7 +939,7 @@ bool conv_tc_needs_zero(int nv_query, int F, int c_in) { return conv_k_splits(nv
 // the layer's first channel; `slabs` at this chunk's prepared filter.
 static int conv_fwd_tc_chunk(const float* nbr_values, const int* neighbours, const float* slabs, const float* bias, const float* residual,
                              int nv_query, int F, int c_in, int c_out, int ld_n, int n_off, int flip, int precision, float* out,
-                             cudaStream_t s) {
+                             int cta_budget, cudaStream_t s) {
     const int n_pad = (c_out + 15) / 16 * 16;
     const int k_total = F * c_in;
     const int split = precision == 1 ? 1 : 0;
@@ -939,7 +947,7 @@ static int conv_fwd_tc_chunk(const float* nbr_values, const int* neighbours, con
     const float* b_lo = slabs + (size_t)k_total * n_pad;
     const int num_kb = F * (c_in / kBlockK);
     const int m_tiles = cdiv(nv_query, kTileM);
-    const int splits = conv_k_splits(nv_query, F, c_in);
+    const int splits = conv_k_splits(nv_query, F, c_in, cta_budget);
     const int kb_per_split = cdiv(num_kb, splits);
     const size_t b_tile = (size_t)n_pad * kRowBytes;
     const size_t stage_bytes = (split ? 2 : 1) * (kATileBytes + b_tile);
@@ -953,11 +961,11 @@ static int conv_fwd_tc_chunk(const float* nbr_values, const int* neighbours, con
         set_error("ln_conv_fwd: tensor-core tile does not fit shared memory (c_out=%d)", c_out);
         return LN_ERR_UNSUPPORTED;
     }
-    const int lookahead = lookahead_for(stages);
+    const int n_items = m_tiles * splits;
+    const int grid = min(n_items, cta_budget > 0 ? min(cta_budget, sm_count()) : sm_count());
+    const int lookahead = lookahead_for(stages, cdiv(n_items, grid) * kb_per_split);
     // > half of the SM's shared memory: exactly one CTA per SM, so the 2*n_pad TMEM columns are always available
     const size_t smem = max((size_t)stages * stage_bytes + fixed, (size_t)120 * 1024);
-    const int n_items = m_tiles * splits;
-    const int grid = min(n_items, sm_count());
     cudaError_t err;
     if (split) {
         err = allow_max_smem((const void*)conv_tc2_kernel<1>);
@@ -981,10 +989,10 @@ static int conv_fwd_tc_chunk(const float* nbr_values, const int* neighbours, con
 // slabs: prepared filter of this reading (filter_prepare / filter_prepare_batch).  `out` must be zero when
 // conv_tc_needs_zero() (the caller clears it or hands over a zeroed buffer).
 int conv_fwd_tc(const float* nbr_values, const int* neighbours, const float* slabs, const float* bias, const float* residual, int nv_query,
-                int F, int c_in, int c_out, int flip, int precision, float* out, cudaStream_t s) {
+                int F, int c_in, int c_out, int flip, int precision, float* out, int cta_budget, cudaStream_t s) {
     for (int n_off = 0; n_off < c_out; n_off += kMaxTileN) {
         const int rc = conv_fwd_tc_chunk(nbr_values, neighbours, slabs + (size_t)2 * F * c_in * n_off, bias, residual, nv_query, F, c_in,
-                                         min(kMaxTileN, c_out - n_off), c_out, n_off, flip, precision, out, s);
+                                         min(kMaxTileN, c_out - n_off), c_out, n_off, flip, precision, out, cta_budget, s);
         if (rc != LN_OK) return rc;
     }
     return LN_OK;
