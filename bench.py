@@ -145,7 +145,9 @@ def timed_region(fn, steps, world, device, flush_buf):
 
 def kernel_roofline(device):
     """Live CUDA-event timing of the dominant lattice kernel of this workload: the level-1 lattice
-    convolution (128 -> 128 channels, K = 9*128) of the decoder's ResnetBlocks."""
+    convolution (128 -> 128 channels, K = 9*128) of the decoder's ResnetBlocks -- the tcgen05 kernel ALONE, as it runs
+    inside the step: filter slabs prepared beforehand (once per optimizer step), output taken from the zeroed arena."""
+    import bench_ops
     from lattice_net_b200 import Lattice
     from lattice_net_b200 import lattice as lattice_mod
     pos = torch.from_numpy(synthetic_cloud(1234)[0]).to(device)
@@ -159,19 +161,30 @@ def kernel_roofline(device):
     fb = torch.randn((F * cin, cout), device=device) * 0.05
     l2 = lat.clone_lattice()
     l2.set_values(lv)
-    # device time only: the calls are captured into a CUDA graph (as in the benchmarked step) and the replay is timed
-    side = torch.cuda.Stream(device=device)
-    side.wait_stream(torch.cuda.current_stream(device))
-    with torch.cuda.stream(side):
-        for _ in range(3):
-            l2.convolve_im2row_standalone(fb, 1, l2, False)
-    torch.cuda.current_stream(device).wait_stream(side)
-    torch.cuda.synchronize(device)
-    per_graph = 20
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        for _ in range(per_graph):
-            l2.convolve_im2row_standalone(fb, 1, l2, False)
+    lattice_mod.prepare_filters([(fb, F, cin, cout, False)])
+    arena = lattice_mod.ZeroArena(nv * cout + 64, device)
+    prev_arena = lattice_mod.set_zero_arena(arena)
+
+    def one():
+        arena.off = 0          # the same (already accumulated-into) buffer again: timing only
+        l2.convolve_im2row_standalone(fb, 1, l2, False)
+
+    try:
+        # device time only: the calls are captured into a CUDA graph (as in the benchmarked step) and the replay is timed
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                one()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        per_graph = 20
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(per_graph):
+                one()
+    finally:
+        lattice_mod.set_zero_arena(prev_arena)
     graph.replay()
     torch.cuda.synchronize(device)
     replays = 10
@@ -190,20 +203,50 @@ def kernel_roofline(device):
     except Exception:
         pass
     peak = float(peaks.get("bf16_tflops", 1590.0))
+    tf32_peak = bench_ops.TF32 or bench_ops.measure_tf32_peak()
     achieved = flops / sec / 1e12
-    # DRAM bytes of the same call (filter prep + tcgen05 kernel) from one `ncu --set full` capture of exactly this
-    # configuration: scripts/ncu_bench_conv.py -> scripts/roofline_traffic.py -> profiles/roofline_traffic.json
+    # DRAM bytes of the same launch from one `ncu --set full` capture of exactly this configuration:
+    # scripts/ncu_bench_conv.py -> scripts/roofline_traffic.py -> profiles/roofline_traffic.json
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             traffic = float(json.load(f)["traffic_bytes_per_call"])
     except Exception:
         pass
-    return {"bound": "tensor", "kernel": "lattice conv fwd 128->128 (K=1152), nv=%d, precision mode %d; per ln_conv_fwd call = filter prep + tcgen05 kernel, "
-                                         "device time from a CUDA-graph replay of 20 back-to-back calls (working set stays in L2, as inside the step)" % (nv, lattice_mod.CONV_PRECISION),
+    return {"bound": "tensor", "kernel": "conv_tc2_kernel<1>: lattice conv fwd 128->128 (K=1152), nv=%d, precision mode %d (3xTF32: three tcgen05 kind::tf32 passes per "
+                                         "algorithmic flop); one launch = the tcgen05 kernel alone (filter slabs prepared once per step), device time from a CUDA-graph "
+                                         "replay of 20 back-to-back launches (working set stays in L2, as inside the step)" % (nv, lattice_mod.CONV_PRECISION),
             "achieved": achieved, "peak": peak, "peak_source": "measured bf16 burst (MEASURED_PEAKS.json)" if peaks else "fallback",
             "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "us_per_launch": sec * 1e6,
-            "algorithmic_bytes": 4.0 * (nv * cin + nv * F + F * cin * cout + nv * cout)}
+            "tf32_peak_measured_here": tf32_peak, "frac_of_tf32_peak": achieved / tf32_peak,
+            "algorithmic_flops": flops, "algorithmic_bytes": 4.0 * (nv * cin + nv * F + F * cin * cout + nv * cout)}
+
+
+def extra_measurements(args):
+    """BASELINE configs[2..4] next to the headline: SemanticKITTI- / ScanNet-sized scans (graph mode) and the operator
+    roofline points at 10^6 points.  Rank 0, N = 1 only; ~1 minute."""
+    import bench_ops
+    import bench_scenes
+    out = {}
+    try:
+        ops = bench_ops.headline_ops(1000000, (64, 128))
+        out["ops"] = {"n_points": 1000000, "hbm_peak_GBps": bench_ops.HBM, "bf16_peak_TFLOPs": bench_ops.TF, "tf32_peak_TFLOPs_measured_here": bench_ops.TF32,
+                      "entries": [{k: v for k, v in r.items() if k in ("op", "nv", "val_dim", "c_out", "us", "algo_GB", "GBps", "hbm_frac", "TFLOPs",
+                                                                          "tensor_frac", "tf32_frac", "points_per_s")} for r in ops]}
+    except Exception as exc:
+        out["ops"] = {"error": f"{type(exc).__name__}: {exc}"}
+    torch.cuda.empty_cache()
+    scenes = []
+    for name in ("kitti", "scannet"):
+        try:
+            r = bench_scenes.run_scene(name, "ours", 5, 2, args.conv_precision, "graph")
+            scenes.append({k: r[k] for k in ("scene", "n_points", "vertices_per_level", "fwd_bwd_ms", "scans_per_s", "points_per_s", "inference_ms",
+                                              "inference_points_per_s", "execution", "conv")})
+        except Exception as exc:
+            scenes.append({"scene": name, "error": f"{type(exc).__name__}: {exc}"})
+        torch.cuda.empty_cache()
+    out["scenes"] = scenes
+    return out
 
 
 def run_ours(args):
@@ -296,6 +339,7 @@ def run_ours(args):
         return
     roof = kernel_roofline(device)
     cpu = cpu_baseline(model) if (world == 1 and not args.no_cpu_baseline) else None     # reported at N=1 only
+    extras = extra_measurements(args) if (world == 1 and not args.no_extras) else {}
     scans = args.steps * world
     h2d = NR_POINTS * (3 * 4 + 1 * 4 + 8)
     line = {
@@ -317,6 +361,7 @@ def run_ours(args):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "final_loss": losses[-1] if losses else None,
     }
+    line.update(extras)
     print(json.dumps(line))
 
 
@@ -354,6 +399,7 @@ def main():
                     help="N>1: two graphs per step with an eager NCCL all-reduce between them")
     ap.add_argument("--conv-precision", type=int, default=1, choices=[0, 1, 2],
                     help="0 fp32 CUDA cores, 1 tcgen05 3xTF32 (fp32-equivalent, default), 2 tcgen05 TF32")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `ops` / `scenes` keys (scene-sized scans and operator roofline points, ~1 min)")
     ap.add_argument("--torch-optimizer", action="store_true", help="torch.optim.AdamW(fused) instead of the one-kernel flat AdamW")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s CPU leg (profiler passes only; never for a reported line)")
     args = ap.parse_args()

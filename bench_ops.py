@@ -30,7 +30,34 @@ def peaks():
 
 
 HBM, TF, PEAK_SRC = peaks()
+TF32 = None        # dense TF32 peak measured on this GPU (measure_tf32_peak), the denominator of the tcgen05 kind::tf32 kernels
 _flush = None
+_SINK = None       # list: emit() collects records here instead of printing (bench.py's `ops` key)
+
+
+def measure_tf32_peak(n=8192, reps=6):
+    """Dense TF32 GEMM throughput of this GPU (cuBLAS through torch.matmul with TF32 allowed), best of `reps`:
+    BASELINE.md section 2 asks for a measured TF32 denominator next to the bf16 one."""
+    global TF32
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn((n, n), device="cuda")
+        b = torch.randn((n, n), device="cuda")
+        torch.matmul(a, b)
+        torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+        TF32 = 2.0 * n ** 3 / best / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return TF32
 
 
 def timeit(fn, reps=10, warm=3, flush=True):
@@ -58,13 +85,18 @@ def emit(op, cfg, sec, nbytes=None, flops=None, ref_sec=None, extra=None):
     if nbytes is not None:
         rec.update(algo_GB=nbytes / 1e9, GBps=nbytes / sec / 1e9, hbm_frac=nbytes / sec / 1e9 / HBM)
     if flops is not None:
-        rec.update(TFLOPs=flops / sec / 1e12, tensor_frac=flops / sec / 1e12 / TF)
+        rec.update(TFLOPs=flops / sec / 1e12, tensor_frac=flops / sec / 1e12 / TF)       # of the measured bf16 dense peak
+        if TF32:
+            rec.update(tf32_frac=flops / sec / 1e12 / TF32)                                # of the measured TF32 dense peak
     if ref_sec is not None:
         rec.update(ref_us=ref_sec * 1e6, speedup_vs_ref_kernel=ref_sec / sec)
     if extra:
         rec.update(extra)
     rec["peak_source"] = PEAK_SRC
-    print(json.dumps(rec), flush=True)
+    if _SINK is not None:
+        _SINK.append(rec)
+    else:
+        print(json.dumps(rec), flush=True)
 
 
 def uniform_cloud(n, d, seed, order="random"):
@@ -104,11 +136,11 @@ def bench_group_norm(nv, widths, cfg0, dev):
         del xg, gy, xr, yr
 
 
-def run(n, d, vals, quick, order="random"):
+def run(n, d, vals, quick, order="random", with_ref=True, with_extras=True):
     from lattice_net_b200 import Lattice, lattice as lm
     from lattice_net_b200._cabi import call, ptr, stream_ptr
     from oracle import ref_cuda
-    have_ref = ref_cuda.available()
+    have_ref = with_ref and ref_cuda.available()
     dev = torch.device("cuda", 0)
     # sigma so that nv ~ n/2: vertices ~ (d+1)! * volume/sigma^d density; tune by a coarse search
     pos = torch.from_numpy(uniform_cloud(n, d, 0, order)).to(dev)
@@ -189,31 +221,38 @@ def run(n, d, vals, quick, order="random"):
         emit("slice_bwd", cfg, timeit(slb, reps=5), nbytes=8 * n * (d + 1) + 4 * nv * V + 4 * n * V, ref_sec=rs)
         del x, lv, out, g, gl
 
-        if V >= 32 and not (quick and V > 64):
+        if V >= 32 and not (quick and V > 128):
             F = 2 * (d + 1) + 1
             fb = torch.randn((F * V, V), device=dev) * 0.05
             lat2._neighbour_table(lat2, 1)
             flops = 2.0 * nv * F * V * V
             cbytes = 4.0 * (nv * V + nv * F + F * V * V + nv * V)
             for prec, name in ((0, "conv_fwd fp32 SIMT"), (1, "conv_fwd tcgen05 3xTF32"), (2, "conv_fwd tcgen05 TF32")):
+                if prec == 0 and quick:
+                    continue
                 lm.set_conv_precision(prec)
                 try:
+                    lm.prepare_filters([(fb, F, V, V, False)])       # filter slabs are prepared once per optimizer step, not per call
                     s = timeit(lambda: lat2.convolve_im2row_standalone(fb, 1, lat2, False), reps=5)
                     emit(name, dict(cfg, c_out=V), s, nbytes=cbytes, flops=flops)
                 finally:
-                    lm.set_conv_precision(0)
+                    lm.set_conv_precision(1)
             if ref is not None and ref.k.has(f"im2row<{d},{V}>"):
                 rs = timeit(lambda: ref.convolve(fb, ref, lvr, 1, False), reps=3)
                 emit("conv_fwd reference (im2row kernel + fp32 mm)", dict(cfg, c_out=V), rs, nbytes=cbytes, flops=flops)
             gout = torch.randn((nv, V), device=dev)
             for prec, name in ((0, "conv_wgrad fp32 SIMT"), (1, "conv_wgrad tcgen05 3xTF32"), (2, "conv_wgrad tcgen05 TF32")):
+                if prec == 0 and quick:
+                    continue
                 lm.set_conv_precision(prec)
                 try:
-                    emit(name, dict(cfg, c_out=V), timeit(lambda: lat2.conv_weight_grad(lat2, gout, F, 1), reps=5), flops=flops)
+                    emit(name, dict(cfg, c_out=V), timeit(lambda: lat2.conv_weight_grad(lat2, gout, F, 1), reps=5), nbytes=cbytes, flops=flops)
                 finally:
-                    lm.set_conv_precision(0)
+                    lm.set_conv_precision(1)
             del fb, gout
         del lat2, lvr
+    if not with_extras:
+        return
     bench_group_norm(nv, [v for v in vals if v >= 32][:2], cfg0, dev)
     # fused slice + classify, widths for which the reference instantiation is built
     for V, nc in [(v, c) for v, c in ((32, 7), (64, 16), (128, 20)) if v in vals]:
@@ -250,6 +289,19 @@ def run(n, d, vals, quick, order="random"):
     emit("neighbour_table", cfg0, timeit(nt, reps=5), nbytes=4 * nv * d + 4 * nv * F + 4 * nv * (d + 1))
 
 
+def headline_ops(n=1000000, vals=(64, 128)):
+    """The `ops` key of bench.py's JSON line: splat / slice / scatter / conv forward / weight gradient at n points, each with
+    its algorithmic GB/s or TFLOP/s and the fraction of the measured peak."""
+    global _SINK
+    _SINK = []
+    try:
+        measure_tf32_peak()
+        run(n, 3, list(vals), True, with_ref=False, with_extras=False)
+        return _SINK
+    finally:
+        _SINK = None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, nargs="*", default=[100000, 1000000])
@@ -257,9 +309,17 @@ def main():
     ap.add_argument("--vals", type=int, nargs="*", default=None)
     ap.add_argument("--order", default="random", choices=["random", "morton"], help="point order of the synthetic cloud")
     ap.add_argument("--gn-only", type=int, default=0, metavar="NV", help="only the GroupNorm entries, on an [NV x C] tensor")
+    ap.add_argument("--pos-dims", type=int, nargs="*", default=None, help="position dimensions to sweep (default: 3, then 5 at half the last n)")
     args = ap.parse_args()
+    measure_tf32_peak()
+    print(json.dumps({"op": "peaks", "hbm_GBps": HBM, "bf16_TFLOPs": TF, "tf32_TFLOPs_measured_here": TF32, "peak_source": PEAK_SRC}), flush=True)
     if args.gn_only:
         bench_group_norm(args.gn_only, args.vals or [32, 64], {"n": 0, "pos_dim": 3, "nv": args.gn_only, "point_order": "-"}, torch.device("cuda", 0))
+        return
+    if args.pos_dims:
+        for d in args.pos_dims:
+            for n in args.n:
+                run(n, d, args.vals if args.vals else [8, 32, 64, 128, 256], args.quick, args.order)
         return
     for n in args.n:
         run(n, 3, args.vals if args.vals else ([8, 32, 64] if args.quick else [1, 8, 32, 64, 128]), args.quick, args.order)

@@ -7,12 +7,13 @@
            lnn_train_scannet.cfg architecture (pointnet start 32, blocks [6,6,8] / 8 / [2,2,2])
 
 For each scene: forward + loss + backward of one scan (ms, scans/s, points/s) and the forward-only inference latency,
-eager launches on the dynamic-shape lattice, L2 flushed before every timed pass, median of --steps passes.
+one CUDA graph per pass on the static-shape lattice (--mode eager: dynamic-shape launches), L2 flushed before every timed
+pass, median of --steps passes.
 
     python bench_scenes.py [--scene kitti|scannet|both] [--impl ours|reference] [--steps 5] [--warmup 2]
 
-`--impl reference` drives the same model through the reference's own CUDA kernels and host algorithm
-(oracle/ref_arm.py, as in `bench.py --impl reference`); run it in its own process.
+`--impl reference` drives the reference's own Python modules and CUDA kernels (oracle/ref_arm.py, as in
+`bench.py --impl reference`); run it in its own process.
 One JSON line per scene on stdout."""
 import argparse
 import json
@@ -70,30 +71,40 @@ def synthetic_scene(name, seed):
     return p.astype(np.float32), vals.astype(np.float32)
 
 
-def run_scene(name, impl, steps, warmup, precision):
+def run_scene(name, impl, steps, warmup, precision, mode="graph"):
+    """mode (ours only): "graph" = static-shape lattice + one CUDA graph per training step / per inference pass
+    (lattice_net_b200/graphed.py); "eager" = dynamic-shape launches."""
     from lattice_net_b200 import Lattice, ModelParams, set_conv_precision
     from lattice_net_b200.losses import segmentation_loss
-    from lattice_net_b200.models import LNN
     spec = SCENES[name]
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     torch.manual_seed(0)
-    if impl == "reference":
-        from oracle import ref_arm
-        ref_arm.patch_modules()
-        lattice = ref_arm.RefHandle(spec["capacity"], [spec["sigma"]] * 3)
-    else:
-        set_conv_precision(precision)
-        lattice = Lattice(spec["capacity"], [(spec["sigma"], 3)])
-    model = LNN(spec["nr_classes"], ModelParams(spec["model"]), device=dev)
     pos_np, vals_np = synthetic_scene(name, 7)
     pos, vals = torch.from_numpy(pos_np).to(dev), torch.from_numpy(vals_np).to(dev)
     labels = torch.from_numpy(np.random.RandomState(1).randint(0, spec["nr_classes"], spec["n"])).to(dev)
     flush = torch.empty((256 << 20) // 4, dtype=torch.float32, device=dev)
+    mp = ModelParams(spec["model"])
+    if impl == "reference":
+        from oracle import ref_arm
+        model = ref_arm.build_reference_model(spec["nr_classes"], mp)
+        from latticenet_py.lattice.lovasz_loss import LovaszSoftmax
+        lattice = ref_arm.RefHandle(spec["capacity"], [spec["sigma"]] * 3)
+        lov, nll = LovaszSoftmax(ignore_index=-100), torch.nn.NLLLoss(ignore_index=-100)
+
+        def loss_fn(logsm, lab):
+            return 0.5 * lov(logsm, lab) + 0.5 * nll(logsm, lab)
+        mode = "eager"
+    else:
+        from lattice_net_b200.models import LNN
+        set_conv_precision(precision)
+        lattice = Lattice(spec["capacity"], [(spec["sigma"], 3)])
+        model = LNN(spec["nr_classes"], mp, device=dev)
+        loss_fn = segmentation_loss
 
     def train_pass():
         logsm, _ = model(lattice, pos, vals)
-        loss = segmentation_loss(logsm, labels)
+        loss = loss_fn(logsm, labels)
         for p in model.parameters():
             p.grad = None
         loss.backward()
@@ -120,18 +131,46 @@ def run_scene(name, impl, steps, warmup, precision):
 
     with torch.no_grad():
         model(lattice, pos, vals)          # lazily created parameters
-    fb_ms = timed(train_pass)
-    loss = float(train_pass().item())
-    inf_ms = timed(infer_pass)
-    nvs = [int(l.nr_lattice_vertices()) for l in getattr(model, "last_level_lattices", [])]
+    execution = "eager launches, dynamic-shape lattice"
+    if mode == "graph":
+        # fwd + loss + bwd (+ a zero-learning-rate AdamW update so that the parameters stay put) as one graph; inference as another
+        from lattice_net_b200.graphed import GraphedTrainStep, estimate_vertex_bounds
+        from lattice_net_b200.optim import FlatAdamW
+        from lattice_net_b200.parallel import GradBucket
+        nr_levels = model.nr_downsamples + 1
+        bounds = estimate_vertex_bounds(spec["capacity"], [(spec["sigma"], 3)], [pos], nr_levels, headroom=1.1)
+        bucket = GradBucket(model.parameters())
+        opt = FlatAdamW(bucket, lr=0.0, weight_decay=0.0)
+        step = GraphedTrainStep(model, lattice, opt, loss_fn, spec["n"], 3, spec["val_dim"], bounds, bucket, example=(pos, vals, labels), warmup=2)
+        fb_ms = timed(lambda: step.graphs[0].replay())
+        loss = float(step.loss.item())
+        # inference graph on the same static-shape lattice
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            infer_pass()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            logits = infer_pass()
+        inf_ms = timed(g.replay)
+        assert step.overflowed_steps() == 0 and bool(torch.isfinite(logits).all())
+        nvs = step.last_vertex_counts()
+        execution = f"one CUDA graph per pass (static-shape lattice, rows per level {bounds})"
+    else:
+        fb_ms = timed(train_pass)
+        loss = float(train_pass().item())
+        inf_ms = timed(infer_pass)
+        nvs = [int(l.nr_lattice_vertices()) for l in getattr(model, "last_level_lattices", [])]
     return {
         "scene": name, "impl": impl, "n_points": spec["n"], "sigma": spec["sigma"], "hash_table_capacity": spec["capacity"],
         "nr_classes": spec["nr_classes"], "vertices_per_level": nvs,
         "fwd_bwd_ms": fb_ms, "scans_per_s": 1e3 / fb_ms, "points_per_s": spec["n"] * 1e3 / fb_ms,
         "inference_ms": inf_ms, "inference_points_per_s": spec["n"] * 1e3 / inf_ms,
         "steps": steps, "warmup": warmup, "loss": loss, "data": "synthetic", "dtype": "f32",
-        "execution": "eager launches, dynamic-shape lattice, L2 flushed before every timed pass",
-        "conv": ("reference kernels: im2row buffer + fp32 mm" if impl == "reference" else
+        "execution": execution + ", L2 flushed before every timed pass, median of the passes",
+        "conv": ("reference Python modules + reference kernels: im2row buffer + fp32 mm" if impl == "reference" else
                  {0: "fp32 FMA on CUDA cores", 1: "tcgen05 3xTF32 split, fp32 accumulate", 2: "tcgen05 TF32"}[precision]),
     }
 
@@ -143,10 +182,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--conv-precision", type=int, default=1, choices=[0, 1, 2])
+    ap.add_argument("--mode", default="graph", choices=["graph", "eager"])
     args = ap.parse_args()
     for name in (["kitti", "scannet"] if args.scene == "both" else [args.scene]):
         try:
-            line = run_scene(name, args.impl, args.steps, args.warmup, args.conv_precision)
+            line = run_scene(name, args.impl, args.steps, args.warmup, args.conv_precision, args.mode)
         except Exception as exc:       # keep going: the other scene is still worth its line
             line = {"scene": name, "impl": args.impl, "error": f"{type(exc).__name__}: {exc}"}
         print(json.dumps(line), flush=True)

@@ -1,20 +1,18 @@
 """TEST / BASELINE INFRASTRUCTURE -- the reference arm of bench.py (`--impl reference`).
 
-The reference is CUDA-only (README.md:20) and its host library cannot be built here (EasyPBR, Boost,
-Eigen, loguru, configuru are absent, no network -- see DESIGN.md).  What CAN run unmodified is its device
-code: oracle/_ref holds the NVRTC build of the reference's own LatticeGPU.cuh / HashTableGPU.cuh
-(oracle/build_ref.py).  This module drives the SAME LatticeNet training step as bench.py's own arm with
-  * the reference's kernels (oracle/ref_cuda.py), launched with the reference's grids,
-  * the reference's host algorithm around them, restated from /root/reference/src/Lattice.cu and
-    /root/reference/src/HashTable.cu: C-sized `fill_` clears, the table clones of distribute(),
-    `positions / sigma` as a separate op, -1 fills of the index tables, a zeros im2row buffer + fp32
-    `torch.mm` per convolution, and one blocking D2H read of the vertex count per cloned handle
-    (Lattice.cu:1326-1338 with the dirty flag of HashTable.cu:15),
-  * the reference's module-level mechanism for the block convolutions: Im2RowLattice + `mm`
-    (lattice_modules.py:240-242) with row2im in the backward pass (lattice_funcs.py:216-246), and
-    the reference's backward algebra for coarsen / finefy (lattice_funcs.py:358-462),
-  * torch scatter ops in place of torch_scatter (absent here).
-None of this repo's kernels are on that path.
+The reference is CUDA-only (README.md:20) and its C++ host library cannot be built here (EasyPBR, Boost, Eigen, loguru,
+configuru are absent, no network -- see DESIGN.md).  What runs UNMODIFIED:
+  * its device code: oracle/_ref holds the NVRTC build of the reference's own LatticeGPU.cuh / HashTableGPU.cuh
+    (oracle/build_ref.py), launched with the reference's grids (oracle/ref_cuda.py);
+  * its Python layer: baseline/_ref/latticenet_py/{lattice/lattice_funcs, lattice_modules, lattice_wrapper, models,
+    utils/utils}.py are byte-for-byte copies of the reference's files (oracle/install_ref_py.py) and are imported as they
+    are -- the reference's autograd Functions, modules, LNN, weight-norm wrappers and initialisers.
+What is restated here is only the piece in between, the compiled `latticenet` module (`RefHandle` below, following
+/root/reference/src/Lattice.cu and src/HashTable.cu: C-sized `fill_` clears, the table clones of distribute(),
+`positions / sigma` as a separate op, -1 fills of the index tables, a zeros im2row buffer + fp32 `torch.mm` per
+convolution, one blocking D2H read of the vertex count per cloned handle, Lattice.cu:1326-1338), plus import shims for
+modules that are not installed: `easypbr` (profiler no-ops), `torch_scatter` (torch scatter_reduce), `termcolor`.
+None of this repo's kernels, modules or optimizer code is on that path.
 """
 import ctypes
 import json
@@ -75,6 +73,18 @@ class RefHandle:
 
     def get_filter_extent(self, n):
         return 2 * (self.pos_dim() + 1) + 1
+
+    m_expected_pos_dim = 3                       # static in the reference (Lattice.cu:44,143), set by the arm before the model is built
+
+    @staticmethod
+    def get_expected_filter_extent(n):
+        return 2 * (RefHandle.m_expected_pos_dim + 1) + 1
+
+    def set_val_dim(self, v):                    # bookkeeping only in the reference
+        pass
+
+    def name(self):
+        return "lattice"
 
     def begin_splat(self, reset=True):
         if self.table is not None:                   # HashTable::clear: 4 fills over C-sized tensors
@@ -197,108 +207,112 @@ class RefHandle:
 
 
 # --------------------------------------------------------------------------------------------------
-def _torch_scatter_max(src, index, nv):
-    """stand-in for torch_scatter.scatter_max (absent here): library scatter ops only"""
+# import shims for what the reference's Python imports but this image does not have
+def _scatter_max(src, index, dim=0, dim_size=None):
+    """torch_scatter.scatter_max(src, index, dim=0): (max per index, row attaining it); library scatter ops only."""
     m, c = src.shape
+    nv = int(index.max().item()) + 1 if dim_size is None else dim_size       # torch_scatter sizes the output the same way (one sync)
     idx = index.long().unsqueeze(1).expand(-1, c)
     out = torch.full((nv, c), float("-inf"), device=src.device).scatter_reduce(0, idx, src, "amax", include_self=True)
     hit = src == out.gather(0, idx)
     rows = torch.where(hit, torch.arange(m, device=src.device).unsqueeze(1).expand(-1, c), torch.full_like(idx, m))
     arg = torch.full((nv, c), m, dtype=torch.int64, device=src.device).scatter_reduce(0, idx, rows, "amin", include_self=True)
     out = src.gather(0, arg.clamp(max=m - 1))          # differentiable w.r.t. src like scatter_max
-    return out, arg.to(torch.int32)
+    return out, arg.clamp(max=m - 1)
 
 
-def _torch_scatter_sum_count(src, index, nv):
-    idx = index.long()
-    out = torch.zeros((nv, src.shape[1]), device=src.device).index_add_(0, idx, src)
-    cnt = torch.zeros((nv,), device=src.device).index_add_(0, idx, torch.ones(idx.shape[0], device=src.device))
-    return out, cnt
+def _scatter_add(src, index, dim=0, dim_size=None):
+    nv = int(index.max().item()) + 1 if dim_size is None else dim_size
+    shape = (nv,) + tuple(src.shape[1:])
+    return torch.zeros(shape, device=src.device, dtype=src.dtype).index_add_(0, index.long(), src)
 
 
-class _RefIm2RowFn(torch.autograd.Function):
-    """Im2RowLattice of the reference (lattice_funcs.py:187-246)."""
-
-    @staticmethod
-    def forward(ctx, lv, lattice, filter_extent, dilation):
-        lattice.set_values(lv)
-        ctx.lattice, ctx.fe, ctx.dil, ctx.vd = lattice, filter_extent, dilation, lattice.val_dim()
-        return lattice.im2row(lattice, filter_extent, dilation, False)
-
-    @staticmethod
-    def backward(ctx, grad_rowified):
-        lat = ctx.lattice
-        if lat.val_dim() != ctx.vd:
-            lat.m_values = grad_rowified.new_zeros((lat.nr_lattice_vertices(), ctx.vd))
-        g = lat.row2im(grad_rowified.contiguous(), ctx.dil, ctx.fe, 0, lat)
-        ctx.lattice = None
-        return g, None, None, None
+def _scatter_mean(src, index, dim=0, dim_size=None):
+    s = _scatter_add(src, index, dim, dim_size)
+    cnt = _scatter_add(torch.ones(index.shape[0], device=src.device), index, 0, s.shape[0]).clamp(min=1)
+    return s / cnt.view(-1, *([1] * (s.dim() - 1)))
 
 
-def _ref_conv_module_forward(self, lattice_values, lattice_structure, residual=None):
-    """ConvLatticeIm2RowModule.forward of the reference (lattice_modules.py:231-250): im2row, mm, clone."""
-    lattice_structure.set_values(lattice_values)
-    fe = lattice_structure.get_filter_extent(self.neighbourhood_size)
-    rowified = _RefIm2RowFn.apply(lattice_values, lattice_structure, fe, self.dilation)
-    lv = rowified.mm(self._filter())
-    new = lattice_structure.clone_lattice()
-    if self.use_bias:
-        lv = lv + self.bias
-    if residual is not None:
-        lv = lv + residual
-    new.set_values(lv)
-    return lv, new
+def install_shims():
+    import sys
+    import types
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_py = os.path.join(here, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref_py, "latticenet_py", "lattice", "models.py")):
+        raise RuntimeError("baseline/_ref/latticenet_py is missing: run `python -m oracle.install_ref_py` where /root/reference is mounted")
+    if ref_py not in sys.path:
+        sys.path.insert(0, ref_py)
+
+    class _Profiler:
+        @staticmethod
+        def is_profiling_gpu():
+            return False
+
+        @staticmethod
+        def start(name):
+            pass
+
+        @staticmethod
+        def end(name):
+            pass
+
+    easypbr = types.ModuleType("easypbr")
+    easypbr.Profiler = _Profiler
+    easypbr.Mesh = type("Mesh", (), {})
+    easypbr.Scene = type("Scene", (), {})
+    easypbr.__all__ = ["Profiler", "Mesh", "Scene"]
+    sys.modules.setdefault("easypbr", easypbr)
+    latticenet = types.ModuleType("latticenet")
+    latticenet.Lattice = RefHandle
+    latticenet.HashTable = RefTable
+    sys.modules.setdefault("latticenet", latticenet)
+    ts = types.ModuleType("torch_scatter")
+    ts.scatter_max, ts.scatter_add, ts.scatter_mean = _scatter_max, _scatter_add, _scatter_mean
+    sys.modules.setdefault("torch_scatter", ts)
+    tc = types.ModuleType("termcolor")
+    tc.colored = lambda text, *a, **k: text
+    sys.modules.setdefault("termcolor", tc)
 
 
-def _torch_linear(x, weight, bias=None, residual=None):
-    y = torch.nn.functional.linear(x, weight, bias)
-    return y if residual is None else y + residual
-
-
-def patch_modules():
-    """Route the module layer to the reference mechanisms (no kernel of this repo stays on the path).  Process-wide:
-    the reference arm always runs in its own process."""
-    import lattice_net_b200.lattice_modules as lm
-    from lattice_net_b200 import Lattice as _L
+def build_reference_model(nr_classes, model_params, pos_dim=3):
+    """The reference's own LNN (latticenet_py/lattice/models.py), imported unmodified."""
+    import contextlib
+    import io
+    install_shims()
     RefKernels.get()
-    lm.scatter_max = lambda src, index, nv: _torch_scatter_max(src, index, nv)
-    lm.scatter_sum_count = _torch_scatter_sum_count
-    lm.ConvLatticeIm2RowModule.forward = _ref_conv_module_forward
-    lm.linear = _torch_linear                  # torch.nn.Linear (cuBLAS), as in the reference's 1x1 layers
-    lm.FUSED_NORM_MAX_ELEMS_PER_GROUP = 0      # torch GroupNorm + ReLU, as in the reference
-    _L.m_expected_position_dimensions = 3            # static pos-dim the module constructors read
+    RefHandle.m_expected_pos_dim = pos_dim
+    from latticenet_py.lattice.models import LNN as RefLNN      # the reference's file
+    with contextlib.redirect_stdout(io.StringIO()):              # its constructor prints one line per block
+        model = RefLNN(nr_classes, model_params)
+    return model
 
 
 def run(args, cloud_fn, cfg):
-    import lattice_net_b200.lattice_modules as lm
-    from lattice_net_b200 import ModelParams
-    from lattice_net_b200.losses import segmentation_loss
-    from lattice_net_b200.models import LNN
-    from lattice_net_b200 import Lattice as _L
+    from lattice_net_b200.params import ModelParams              # plain .cfg value holder with the reference's accessor names
+    install_shims()
+    from latticenet_py.lattice.lovasz_loss import LovaszSoftmax # the reference's loss
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     torch.manual_seed(0)
-    patch_modules()
-    model = LNN(cfg["nr_classes"], ModelParams(), device=dev)
+    model = build_reference_model(cfg["nr_classes"], ModelParams())
     pool = 16
     clouds = [cloud_fn(i) for i in range(pool)]
     dev_clouds = [(torch.from_numpy(p).to(dev), torch.zeros((cfg["nr_points"], 1), device=dev), torch.from_numpy(l).to(dev)) for p, l in clouds]
 
-    def new_lattice():
-        return RefHandle(cfg["capacity"], [cfg["sigma"]] * 3)
-
-    lattice = new_lattice()
+    lattice = RefHandle(cfg["capacity"], [cfg["sigma"]] * 3)
     with torch.no_grad():
-        model(lattice, *dev_clouds[0][:2])
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=3e-4, amsgrad=True)
+        model(lattice, *dev_clouds[0][:2])                       # lazily created layers (the reference creates its optimizer after this too)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=3e-4, amsgrad=True)       # ln_train.py:163-165
+    loss_fn = LovaszSoftmax(ignore_index=-100)                   # ln_train.py:128-130, 156-158
+    secondary_fn = torch.nn.NLLLoss(ignore_index=-100)
     flush = torch.empty((256 << 20) // 4, dtype=torch.float32, device=dev)
 
     def step(i):
         pos, vals, labels = dev_clouds[i % pool]
         logsm, _ = model(lattice, pos, vals)
-        loss = segmentation_loss(logsm, labels)
-        opt.zero_grad(set_to_none=False)
+        loss = 0.5 * loss_fn(logsm, labels) + 0.5 * secondary_fn(logsm, labels)
+        opt.zero_grad()
         loss.backward()
         opt.step()
         return loss
@@ -306,6 +320,16 @@ def run(args, cloud_fn, cfg):
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
+    # GPU-busy share: kernel time of one step (a profiler pass outside the timed region) against the step's wall time
+    busy_ms = None
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(0)
+            torch.cuda.synchronize()
+        busy_ms = sum(e.device_time_total for e in prof.key_averages()) * 1e-3
+    except Exception:
+        pass
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -315,12 +339,32 @@ def run(args, cloud_fn, cfg):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     value = args.steps / (ms * 1e-3)
+    scenes = []
+    if not getattr(args, "no_extras", False):
+        # the scene-sized scans of BASELINE configs[2] / [3] through the same arm (eager, as the reference runs)
+        import bench_scenes
+        del model, opt
+        torch.cuda.empty_cache()
+        for name in ("kitti", "scannet"):
+            try:
+                r = bench_scenes.run_scene(name, "reference", 3, 1, 1, "eager")
+                scenes.append({k: r[k] for k in ("scene", "n_points", "vertices_per_level", "fwd_bwd_ms", "scans_per_s", "points_per_s", "inference_ms",
+                                                  "inference_points_per_s", "execution", "conv")})
+            except Exception as exc:
+                scenes.append({"scene": name, "error": f"{type(exc).__name__}: {exc}"})
+            torch.cuda.empty_cache()
     return {
+        "scenes": scenes,
         "impl": "reference", "metric": "scans/sec fwd+bwd", "value": value, "unit": "scans/s", "n_gpus": int(getattr(args, "gpus", 1) or 1), "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "LatticeNet ShapeNet-part segmentation fwd+bwd+AdamW (lnn_train_shapenet.cfg arch), 2048-pt synthetic clouds, 1 scene/step/GPU",
-                   "arm": "the reference's own CUDA kernels (NVRTC build of the unmodified LatticeGPU.cuh, driver-JITed on this GPU) + its host algorithm (im2row buffer + fp32 mm, C-sized clears, per-handle D2H syncs); the reference has no CPU implementation",
+                   "nr_points": cfg["nr_points"], "nr_classes": cfg["nr_classes"], "sigma": cfg["sigma"], "hash_table_capacity": cfg["capacity"],
+                   "arm": "reference Python modules unmodified (baseline/_ref/latticenet_py: lattice_funcs, lattice_modules, models, LovaszSoftmax, utils) + the "
+                          "reference's own CUDA kernels (NVRTC build of the unmodified LatticeGPU.cuh, driver-JITed on this GPU) under a restatement of its C++ "
+                          "host class (im2row buffer + fp32 mm, C-sized clears, per-handle D2H syncs); eager, torch.optim.AdamW(amsgrad) unfused as upstream; "
+                          "the reference has no CPU implementation",
+                   "gpu_busy_ms_per_step": busy_ms, "gpu_busy_share_of_step": (busy_ms / (ms / args.steps)) if busy_ms else None,
                    "l2": "flushed between steps by a 256 MiB write (inside the timed region)",
                    "ranks_used": "1 (the reference is single-process / single-GPU; under torchrun rank 0 alone runs it)"},
         "cpu_baseline": {"value": value, "unit": "scans/s", "cores": 0, "kind": "reference",

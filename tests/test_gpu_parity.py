@@ -5,6 +5,7 @@ Integers (keys, vertex counts, index tables, neighbour tables) must be bit-exact
 key sort; weights are expected bit-equal; accumulated values within the stated fp32 tolerances.
 """
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -1462,3 +1463,45 @@ def test_weight_norm_kernels_vs_torch(rows, cols, g_dim):
     assert_close(got[0].cpu().numpy(), wr.detach().cpu().numpy(), 1e-6, "weight norm forward")
     assert_close(got[1].cpu().numpy(), v.grad.cpu().numpy(), 1e-5, "weight norm dv")
     assert_close(got[2].cpu().numpy(), g.grad.cpu().numpy(), 1e-5, "weight norm dg")
+
+
+def test_reference_arm_drives_the_reference_python_unmodified():
+    """`bench.py --impl reference`: baseline/_ref holds byte-for-byte copies of the reference's Python layer (sha256
+    manifest), the arm imports THEM (not this repo's modules) and two training steps run on the reference kernels."""
+    import hashlib
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    manifest_path = os.path.join(root, "baseline", "_ref", "MANIFEST.json")
+    if not os.path.isfile(manifest_path):
+        pytest.skip("baseline/_ref not installed (python -m oracle.install_ref_py where /root/reference is mounted)")
+    _ref()
+    with open(manifest_path) as f:
+        manifest = json.load(f)["sha256"]
+    for rel, digest in manifest.items():
+        with open(os.path.join(root, "baseline", "_ref", "latticenet_py", rel), "rb") as f:
+            assert hashlib.sha256(f.read()).hexdigest() == digest, f"{rel} was modified after installation"
+    from lattice_net_b200.params import ModelParams
+    from oracle import ref_arm
+    model = ref_arm.build_reference_model(7, ModelParams())
+    assert type(model).__module__ == "latticenet_py.lattice.models"
+    assert os.path.join("baseline", "_ref") in sys.modules["latticenet_py.lattice.lattice_modules"].__file__
+    pos = cuda(cases.box_surface(2048, 0))
+    vals = torch.zeros((2048, 1), device="cuda")
+    labels = torch.randint(0, 7, (2048,), device="cuda")
+    lat = ref_arm.RefHandle(60000, [0.05] * 3)
+    losses = []
+    for _ in range(2):
+        logsm, logits = model(lat, pos, vals)
+        loss = torch.nn.functional.nll_loss(logsm, labels)
+        for p in model.parameters():
+            p.grad = None
+        loss.backward()
+        losses.append(loss.item())
+    assert all(np.isfinite(losses)) and tuple(logits.shape) == (2048, 7)
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    assert len(grads) > 100 and all(torch.isfinite(g).all().item() for g in grads)
+    # no kernel of this library ran on that path
+    from lattice_net_b200 import _cabi
+    before = _cabi.launch_count()
+    model(lat, pos, vals)
+    assert _cabi.launch_count() == before
