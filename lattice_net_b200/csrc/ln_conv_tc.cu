@@ -269,7 +269,6 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
     int* nbr_sh = (int*)(base + (size_t)stages * stage_bytes);                      // [2][kTileM * F]
     uint64_t* bars = (uint64_t*)(((uintptr_t)(nbr_sh + 2 * kTileM * F) + 15) & ~(uintptr_t)15);
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kMaxStages + 4);
-    float* epi_tile = (float*)(tmem_slot + 4);                                      // [4 epilogue warps][32][33]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -487,16 +486,12 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
             const int a = j & 1;
             mbar_wait(acc_full_bar(a), ((uint32_t)(j >> 1)) & 1u);
             tc_fence_after();
+            const int q = w.q0 + quad * 32 + lane;
+            const bool live = q < nv_query;
+            float* orow = out + (size_t)q * ld_out;     // `out` / `bias` / `residual` already point at this launch's first channel
             const bool add_bias = bias != nullptr && w.split == 0;
-            const bool add_res = residual != nullptr && w.split == 0;
+            const float* rrow = (residual != nullptr && w.split == 0) ? residual + (size_t)q * ld_out : nullptr;
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * n_pad);
-            // tcgen05.ld hands every lane one ROW of the tile (32 columns in registers); written out like that, one store /
-            // reduction instruction of a warp would touch 32 different 128-byte lines.  The 32 x 32 block is transposed
-            // through a warp-private padded tile in shared memory instead, so that 8 lanes cover the 128 bytes of one row
-            // and an instruction touches 4 whole lines (8x fewer L2 transactions for the split-K reductions).
-            float* tile = epi_tile + quad * (32 * 33);
-            const int sub_row = lane >> 3, c4 = (lane & 7) * 4;
-            const bool vec_ok = ((c_out | ld_out) & 3) == 0;      // 16-byte aligned rows and whole float4 groups
             for (int n0 = 0; n0 < n_pad; n0 += 32) {
                 float acc[32];
                 if (n0 + 32 <= n_pad) {
@@ -506,47 +501,35 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
 #pragma unroll
                     for (int k = 16; k < 32; k++) acc[k] = 0.0f;
                 }
-                __syncwarp();                  // the previous block's reads of the tile are done
+                if (!live) continue;
+                if (((c_out | ld_out) & 3) == 0) {      // 16-byte aligned rows and whole float4 groups
 #pragma unroll
-                for (int k = 0; k < 32; k++) tile[lane * 33 + k] = acc[k];
-                __syncwarp();
-                const int col = n0 + c4;
-                if (col >= c_out) continue;    // (warp-uniform per lane group; no barrier below)
-                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (add_bias) {
-                    bv.x = __ldg(bias + col);
-                    if (col + 1 < c_out) bv.y = __ldg(bias + col + 1);
-                    if (col + 2 < c_out) bv.z = __ldg(bias + col + 2);
-                    if (col + 3 < c_out) bv.w = __ldg(bias + col + 3);
-                }
-#pragma unroll
-                for (int r0 = 0; r0 < 32; r0 += 4) {
-                    const int row = r0 + sub_row;
-                    const int q = w.q0 + quad * 32 + row;
-                    if (q >= nv_query) continue;
-                    const float* t = tile + row * 33 + c4;
-                    float4 o = make_float4(t[0] + bv.x, t[1] + bv.y, t[2] + bv.z, t[3] + bv.w);
-                    float* dst = out + (size_t)q * ld_out + col;     // `out` / `bias` / `residual` already point at this launch's first channel
-                    if (vec_ok) {
-                        if (add_res) {
-                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(residual + (size_t)q * ld_out + col));
-                            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-                        }
-                        if (split_k)
-                            atomicAdd(reinterpret_cast<float4*>(dst), o);
-                        else
-                            *reinterpret_cast<float4*>(dst) = o;
-                    } else {
-                        const float ov[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            if (col + k < c_out) {
-                                const float x = ov[k] + (add_res ? __ldg(residual + (size_t)q * ld_out + col + k) : 0.0f);
-                                if (split_k)
-                                    atomicAdd(dst + k, x);
-                                else
-                                    dst[k] = x;
+                    for (int k = 0; k < 32; k += 4) {
+                        if (n0 + k < c_out) {
+                            float4 o = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
+                            if (add_bias) {
+                                o.x += __ldg(bias + n0 + k); o.y += __ldg(bias + n0 + k + 1);
+                                o.z += __ldg(bias + n0 + k + 2); o.w += __ldg(bias + n0 + k + 3);
                             }
+                            if (rrow != nullptr) {
+                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rrow + n0 + k));
+                                o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                            }
+                            if (split_k)
+                                atomicAdd(reinterpret_cast<float4*>(orow + n0 + k), o);
+                            else
+                                *reinterpret_cast<float4*>(orow + n0 + k) = o;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) {
+                        if (n0 + k < c_out) {
+                            const float o = acc[k] + (add_bias ? __ldg(bias + n0 + k) : 0.0f) + (rrow != nullptr ? __ldg(rrow + n0 + k) : 0.0f);
+                            if (split_k)
+                                atomicAdd(orow + n0 + k, o);
+                            else
+                                orow[n0 + k] = o;
                         }
                     }
                 }
@@ -794,36 +777,22 @@ conv_wgrad_tc_kernel(const float* __restrict__ values, const int* __restrict__ n
         if (warp < 4 && num_chunks > 0) {
             mbar_wait(accum_bar, 0);
             tc_fence_after();
-            // all MMAs have retired: the stage ring is free and serves as the transposition tiles (see conv_tc2's epilogue:
-            // 8 lanes cover the 128 bytes of one gradient row, an instruction touches 4 whole lines instead of 32)
-            float* tile = reinterpret_cast<float*>(base) + warp * (32 * 33);
-            const int sub_row = lane >> 3, c4 = (lane & 7) * 4;
-            for (int n0 = 0; n0 < n_pad; n0 += 32) {
-                float acc[32];
-                if (n0 + 32 <= n_pad) {
-                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, acc);
-                } else {
-                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, acc);
+            const int m = warp * 32 + lane;
+            const bool live = m < ci_n;
+            float* orow = grad_filter + ((size_t)slot * c_in + ci0 + m) * ld_g;
+            for (int n0 = 0; n0 < n_pad; n0 += 16) {
+                float acc[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, acc);
+                if (!live) continue;
 #pragma unroll
-                    for (int k = 16; k < 32; k++) acc[k] = 0.0f;
-                }
-                __syncwarp();
-#pragma unroll
-                for (int k = 0; k < 32; k++) tile[lane * 33 + k] = acc[k];
-                __syncwarp();
-                const int col = n0 + c4;
-                if (col >= c_out) continue;               // c_out % 4 == 0: whole float4 groups
-#pragma unroll
-                for (int r0 = 0; r0 < 32; r0 += 4) {
-                    const int m = warp * 32 + r0 + sub_row;
-                    if (m >= ci_n) continue;
-                    const float* t = tile + (r0 + sub_row) * 33 + c4;
-                    const float4 o = make_float4(t[0], t[1], t[2], t[3]);
-                    float* dst = grad_filter + ((size_t)slot * c_in + ci0 + m) * ld_g + col;
-                    if (q_splits > 1)
-                        atomicAdd(reinterpret_cast<float4*>(dst), o);
-                    else
-                        *reinterpret_cast<float4*>(dst) = o;
+                for (int k = 0; k < 16; k += 4) {
+                    if (n0 + k < c_out) {
+                        const float4 o = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
+                        if (q_splits > 1)
+                            atomicAdd(reinterpret_cast<float4*>(orow + n0 + k), o);
+                        else
+                            *reinterpret_cast<float4*>(orow + n0 + k) = o;
+                    }
                 }
             }
             tc_fence_before();
@@ -986,7 +955,7 @@ static int conv_fwd_tc_chunk(const float* nbr_values, const int* neighbours, con
     const float* bias_chunk = bias != nullptr ? bias + n_off : nullptr;
     const float* res_chunk = residual != nullptr ? residual + n_off : nullptr;
     // persistent kernel: one CTA per SM, items = (M tile, K split)
-    const size_t fixed = (size_t)2 * kTileM * F * sizeof(int) + 16 + (2 * kMaxStages + 4) * 8 + 16 + 4 * 32 * 33 * sizeof(float) + 1024;
+    const size_t fixed = (size_t)2 * kTileM * F * sizeof(int) + 16 + (2 * kMaxStages + 4) * 8 + 16 + 1024;
     const int stages = min((int)((227 * 1024 - fixed) / stage_bytes), kMaxStages);
     if (stages < 2) {
         set_error("ln_conv_fwd: tensor-core tile does not fit shared memory (c_out=%d)", c_out);
