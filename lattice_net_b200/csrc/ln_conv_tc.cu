@@ -546,6 +546,326 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
     }
 }
 
+// ---- 3xTF32 kernel with decoupled rings (v3) ----------------------------------------------------------------------
+// ncu on the scene-sized sweep (10^6 points, 64 -> 64: tensor pipe 22 %, L2 throughput 19 %) and on ShapeNet-sized calls
+// (~1 us per extra K block) showed conv_tc2<1> LATENCY-bound: a 3xTF32 stage carries A_hi + A_lo + B_hi + B_lo, so only
+// 2..4 stages fit and at most 1..2 gathers are in flight per thread -- ~48 KB per SM against the ~100 KB an L2 latency of
+// ~1 us needs.  The low part of A, however, is COMPUTED, not loaded: it needs no shared memory while its gather is in
+// flight.  Three rings instead of one:
+//   landing ring  `landing` x 16 KB: raw fp32 rows straight from cp.async, up to 8 K blocks in flight.  Every producer
+//                 thread re-reads exactly the 16-byte units it gathered itself, so a slot is recycled without any barrier;
+//   A ring        2 x (hi 16 KB | lo 16 KB): written by the producers when a block has landed (round-to-nearest TF32 high
+//                 part + residual), consumed by the MMA lane;
+//   B ring        `b_stages` x (hi | lo) pre-split filter slabs, fed by a dedicated bulk-copy warp that runs ahead of the
+//                 MMAs independently of the gathers.
+// Warps: 0-7 producers, 8 MMA issue, 9 filter-slab loader, 10-13 epilogue.
+constexpr int kTc3Threads = kTc2Producers + 32 + 32 + 128;
+constexpr int kTc3AStages = 2;
+constexpr int kTc3MaxB = 4;
+constexpr int kTc3MaxLanding = 8;
+constexpr int kTc3Bars = 2 * kTc3AStages + 2 * kTc3MaxB + 4;
+
+__global__ void __launch_bounds__(kTc3Threads, 1)
+conv_tc3_kernel(const float* __restrict__ values, const int* __restrict__ neighbours,
+                const float* __restrict__ b_hi, const float* __restrict__ b_lo, const float* __restrict__ bias,
+                const float* __restrict__ residual, int nv_query, int F, int c_in, int c_out, int ld_out, int n_pad, int flip,
+                int landing, int b_stages, int m_tiles, int n_items, int kb_per_split, float* __restrict__ out) {
+    pdl_trigger();
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t b_tile_bytes = (uint32_t)n_pad * kRowBytes;
+    const uint32_t a_stage_bytes = 2u * kATileBytes, b_stage_bytes = 2u * b_tile_bytes;
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t base_u32 = smem_u32(base);
+    const uint32_t a_base = base_u32;
+    const uint32_t b_base = a_base + kTc3AStages * a_stage_bytes;
+    const uint32_t land_base = b_base + (uint32_t)b_stages * b_stage_bytes;
+    int* nbr_sh = (int*)(base + (size_t)kTc3AStages * a_stage_bytes + (size_t)b_stages * b_stage_bytes + (size_t)landing * kATileBytes);   // [2][kTileM * F]
+    uint64_t* bars = (uint64_t*)(((uintptr_t)(nbr_sh + 2 * kTileM * F) + 15) & ~(uintptr_t)15);
+    uint32_t* tmem_slot = (uint32_t*)(bars + kTc3Bars);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const uint32_t bars_u32 = smem_u32(bars);
+    auto full_a = [&](int s) { return bars_u32 + 8u * (uint32_t)s; };
+    auto empty_a = [&](int s) { return bars_u32 + 8u * (uint32_t)(kTc3AStages + s); };
+    auto full_b = [&](int s) { return bars_u32 + 8u * (uint32_t)(2 * kTc3AStages + s); };
+    auto empty_b = [&](int s) { return bars_u32 + 8u * (uint32_t)(2 * kTc3AStages + kTc3MaxB + s); };
+    auto acc_full_bar = [&](int a) { return bars_u32 + 8u * (uint32_t)(2 * kTc3AStages + 2 * kTc3MaxB + a); };
+    auto acc_empty_bar = [&](int a) { return bars_u32 + 8u * (uint32_t)(2 * kTc3AStages + 2 * kTc3MaxB + 2 + a); };
+
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < 2 * n_pad) tmem_cols <<= 1;       // two accumulator buffers
+    if (tid == 0) {
+        for (int s = 0; s < kTc3AStages; s++) {
+            mbar_init(full_a(s), kTc2Producers);   // every producer thread has written its units of the hi / lo tiles
+            mbar_init(empty_a(s), 1);              // one tcgen05.commit
+        }
+        for (int s = 0; s < b_stages; s++) {
+            mbar_init(full_b(s), 1);               // the expect_tx arrival of the loader (+ the bytes of the two bulk copies)
+            mbar_init(empty_b(s), 1);              // one tcgen05.commit
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(acc_full_bar(a), 1);         // one tcgen05.commit
+            mbar_init(acc_empty_bar(a), 128);      // the 128 epilogue threads
+        }
+        fence_barrier_init();
+    }
+    if (warp == kTc2ProducerWarps) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();          // everything above ran while the previous kernel was still finishing; global memory from here on
+
+    const int cpb = c_in / kBlockK;          // K blocks per slot
+    const int total_kb = F * cpb;
+    const bool split_k = n_items > m_tiles;
+
+    if (warp < kTc2ProducerWarps) {
+        // ================= producers =================
+        const int chunk = tid & 7;
+        const int row0 = tid >> 3;           // this thread's rows: row0 + 32*i, i < 4; (row & 7) is the same for all of them
+        const uint32_t my_off = (uint32_t)row0 * kRowBytes + (uint32_t)((chunk ^ (row0 & 7)) << 4);
+        const int tile_ids = kTileM * F;
+        const int row_stride = 32 * F;       // neighbour ids between two of this thread's rows
+        const int per_thread = (tile_ids + kTc2Producers - 1) / kTc2Producers;      // ids staged per thread and item (<= 7)
+        int ibuf = 0;
+        {   // neighbour ids of the first item
+            const Tc2Item w = tc2_item(blockIdx.x, m_tiles, total_kb, kb_per_split);
+            for (int i = tid; i < tile_ids; i += kTc2Producers) {
+                const int q = w.q0 + i / F;
+                nbr_sh[i] = (q < nv_query) ? __ldg(neighbours + (size_t)w.q0 * F + i) : -1;
+            }
+        }
+        producer_bar_sync();
+        const uint32_t land_end = land_base + (uint32_t)landing * kATileBytes;
+        uint32_t issue_land = land_base, pub_land = land_base;
+        uint32_t pa_addr = a_base, pa_full = full_a(0), pa_empty = empty_a(0), pa_phase = 0;
+        int in_flight = 0;
+        const float* col0 = values + chunk * 4;
+        auto publish = [&]() {               // the oldest gather of this thread has landed: split it into the A ring, signal the MMA lane
+            mbar_wait(pa_empty, pa_phase ^ 1u);                  // the MMAs that read this A stage two blocks ago have retired
+            const uint32_t src = pub_land + my_off, hi = pa_addr + my_off, lo = hi + kATileBytes;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float4 x = lds128(src + (uint32_t)i * 32u * kRowBytes);
+                const float4 h = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
+                sts128(hi + (uint32_t)i * 32u * kRowBytes, h);
+                sts128(lo + (uint32_t)i * 32u * kRowBytes,
+                       make_float4(to_tf32(x.x - h.x), to_tf32(x.y - h.y), to_tf32(x.z - h.z), to_tf32(x.w - h.w)));
+            }
+            fence_proxy_async();             // generic-proxy writes -> visible to the tensor-core proxy
+            mbar_arrive(pa_full);
+            pub_land += kATileBytes;
+            if (pub_land == land_end) pub_land = land_base;
+            pa_addr += a_stage_bytes;
+            pa_full += 8;
+            pa_empty += 8;
+            if (pa_addr == a_base + kTc3AStages * a_stage_bytes) {
+                pa_addr = a_base;
+                pa_full = full_a(0);
+                pa_empty = empty_a(0);
+                pa_phase ^= 1u;
+            }
+            in_flight--;
+        };
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const Tc2Item w = tc2_item(item, m_tiles, total_kb, kb_per_split);
+            const int* ids = nbr_sh + ibuf * tile_ids + row0 * F;
+            // prefetch the next item's neighbour ids into registers (stored to the other buffer at the end of this item)
+            int next_ids[7];
+            const int next = item + gridDim.x;
+            if (next < n_items) {
+                const Tc2Item wn = tc2_item(next, m_tiles, total_kb, kb_per_split);
+#pragma unroll
+                for (int j = 0; j < 7; j++) {
+                    const int i = tid + kTc2Producers * j;
+                    next_ids[j] = -1;
+                    if (j < per_thread && i < tile_ids && wn.q0 + i / F < nv_query) next_ids[j] = __ldg(neighbours + (size_t)wn.q0 * F + i);
+                }
+            }
+            int slot = w.kb_begin / cpb;
+            int cb = w.kb_begin - slot * cpb;
+            int id[4];
+            bool reload = true;
+            for (int it = 0; it < w.num_kb; it++) {
+                if (reload) {                // a new filter slot: this thread's four neighbour ids change
+                    const int src_slot = (flip && slot < F - 1) ? (slot ^ 1) : slot;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) id[i] = ids[i * row_stride + src_slot];
+                    reload = false;
+                }
+                const uint32_t dst = issue_land + my_off;
+                const float* col = col0 + cb * kBlockK;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const bool have = id[i] >= 0;
+                    const float* src = have ? col + (unsigned long long)(unsigned)id[i] * (unsigned)c_in : values;   // mul.wide.u32
+                    cp_async16(dst + (uint32_t)i * 32u * kRowBytes, src, have ? 16u : 0u);
+                }
+                cp_async_commit();
+                in_flight++;
+                if (++cb == cpb) {
+                    cb = 0;
+                    slot++;
+                    reload = true;
+                }
+                issue_land += kATileBytes;
+                if (issue_land == land_end) issue_land = land_base;
+                if (in_flight == landing) {  // the ring is full: the oldest block must land (cp.async.wait_group takes an immediate)
+                    switch (landing) {
+                        case 1: cp_async_wait<0>(); break;
+                        case 2: cp_async_wait<1>(); break;
+                        case 3: cp_async_wait<2>(); break;
+                        case 4: cp_async_wait<3>(); break;
+                        case 5: cp_async_wait<4>(); break;
+                        case 6: cp_async_wait<5>(); break;
+                        case 7: cp_async_wait<6>(); break;
+                        default: cp_async_wait<7>(); break;
+                    }
+                    publish();
+                }
+            }
+            if (next < n_items) {
+                int* dst_ids = nbr_sh + (ibuf ^ 1) * tile_ids;
+#pragma unroll
+                for (int j = 0; j < 7; j++) {
+                    const int i = tid + kTc2Producers * j;
+                    if (j < per_thread && i < tile_ids) dst_ids[i] = next_ids[j];
+                }
+            }
+            producer_bar_sync();
+            ibuf ^= 1;
+        }
+        cp_async_wait<0>();
+        while (in_flight > 0) publish();
+    } else if (warp == kTc2ProducerWarps) {
+        // ================= MMA issuer (one lane) =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(kTileM, n_pad);
+            int g = 0, j = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, j++) {
+                const Tc2Item w = tc2_item(item, m_tiles, total_kb, kb_per_split);
+                const int a = j & 1;
+                mbar_wait(acc_empty_bar(a), (((uint32_t)(j >> 1)) & 1u) ^ 1u);   // epilogue has drained this buffer
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * n_pad);
+                for (int it = 0; it < w.num_kb; it++, g++) {
+                    const int sa = g % kTc3AStages, sb = g % b_stages;
+                    mbar_wait(full_b(sb), ((uint32_t)(g / b_stages)) & 1u);
+                    mbar_wait(full_a(sa), ((uint32_t)(g / kTc3AStages)) & 1u);
+                    tc_fence_after();
+                    const uint32_t a_addr = a_base + (uint32_t)sa * a_stage_bytes, b_addr = b_base + (uint32_t)sb * b_stage_bytes;
+                    const uint64_t da_hi = umma_desc_kmajor_sw128(a_addr);
+                    const uint64_t da_lo = umma_desc_kmajor_sw128(a_addr + kATileBytes);
+                    const uint64_t db_hi = umma_desc_kmajor_sw128(b_addr);
+                    const uint64_t db_lo = umma_desc_kmajor_sw128(b_addr + b_tile_bytes);
+#pragma unroll
+                    for (int ks = 0; ks < kBlockK / 8; ks++) {   // UMMA K = 8 tf32 = 32 bytes = 2 x 16-byte units
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        umma_tf32(d_tmem, da_lo + adv, db_hi + adv, idesc, (it | ks) != 0 ? 1u : 0u);   // small cross terms first
+                        umma_tf32(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
+                        umma_tf32(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+                    }
+                    umma_commit(empty_a(sa));    // frees the A stage and the B stage when these MMAs have read them
+                    umma_commit(empty_b(sb));
+                }
+                umma_commit(acc_full_bar(a));    // accumulator complete -> epilogue
+            }
+        }
+        __syncwarp();
+    } else if (warp == kTc2ProducerWarps + 1) {
+        // ================= filter-slab loader (one lane): bulk-async copies, b_stages blocks ahead of the MMAs =================
+        if (lane == 0) {
+            const size_t b_block = (size_t)n_pad * kBlockK;          // floats of one B slab
+            int g = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const Tc2Item w = tc2_item(item, m_tiles, total_kb, kb_per_split);
+                const float* src_hi = b_hi + (size_t)w.kb_begin * b_block;
+                const float* src_lo = b_lo + (size_t)w.kb_begin * b_block;
+                for (int it = 0; it < w.num_kb; it++, g++) {
+                    const int sb = g % b_stages;
+                    mbar_wait(empty_b(sb), (((uint32_t)(g / b_stages)) & 1u) ^ 1u);
+                    const uint32_t dst = b_base + (uint32_t)sb * b_stage_bytes;
+                    mbar_arrive_expect_tx(full_b(sb), 2u * b_tile_bytes);
+                    bulk_copy_g2s(dst, src_hi, b_tile_bytes, full_b(sb));
+                    bulk_copy_g2s(dst + b_tile_bytes, src_lo, b_tile_bytes, full_b(sb));
+                    src_hi += b_block;
+                    src_lo += b_block;
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue (4 warps; TMEM lane quadrant = warp % 4) =================
+        const int quad = warp & 3;
+        int j = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, j++) {
+            const Tc2Item w = tc2_item(item, m_tiles, total_kb, kb_per_split);
+            const int a = j & 1;
+            mbar_wait(acc_full_bar(a), ((uint32_t)(j >> 1)) & 1u);
+            tc_fence_after();
+            const int q = w.q0 + quad * 32 + lane;
+            const bool live = q < nv_query;
+            float* orow = out + (size_t)q * ld_out;     // `out` / `bias` / `residual` already point at this launch's first channel
+            const bool add_bias = bias != nullptr && w.split == 0;
+            const float* rrow = (residual != nullptr && w.split == 0) ? residual + (size_t)q * ld_out : nullptr;
+            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * n_pad);
+            for (int n0 = 0; n0 < n_pad; n0 += 32) {
+                float acc[32];
+                if (n0 + 32 <= n_pad) {
+                    tmem_ld32(t_row + (uint32_t)n0, acc);
+                } else {                       // n_pad is a multiple of 16: a 16-column tail
+                    tmem_ld16(t_row + (uint32_t)n0, acc);
+#pragma unroll
+                    for (int k = 16; k < 32; k++) acc[k] = 0.0f;
+                }
+                if (!live) continue;
+                if (((c_out | ld_out) & 3) == 0) {      // 16-byte aligned rows and whole float4 groups
+#pragma unroll
+                    for (int k = 0; k < 32; k += 4) {
+                        if (n0 + k < c_out) {
+                            float4 o = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
+                            if (add_bias) {
+                                o.x += __ldg(bias + n0 + k); o.y += __ldg(bias + n0 + k + 1);
+                                o.z += __ldg(bias + n0 + k + 2); o.w += __ldg(bias + n0 + k + 3);
+                            }
+                            if (rrow != nullptr) {
+                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rrow + n0 + k));
+                                o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                            }
+                            if (split_k)
+                                atomicAdd(reinterpret_cast<float4*>(orow + n0 + k), o);
+                            else
+                                *reinterpret_cast<float4*>(orow + n0 + k) = o;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) {
+                        if (n0 + k < c_out) {
+                            const float o = acc[k] + (add_bias ? __ldg(bias + n0 + k) : 0.0f) + (rrow != nullptr ? __ldg(rrow + n0 + k) : 0.0f);
+                            if (split_k)
+                                atomicAdd(orow + n0 + k, o);
+                            else
+                                orow[n0 + k] = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acc_empty_bar(a));     // this thread has read its rows of the buffer
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kTc2ProducerWarps) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
 // floats of the prepared slabs of one bank reading (both parts are always reserved, the low half stays unused in
 // single-pass TF32 mode, so a buffer survives a precision change)
 size_t conv_tc_workspace_bytes(int F, int c_in, int c_out) {
@@ -955,29 +1275,47 @@ static int conv_fwd_tc_chunk(const float* nbr_values, const int* neighbours, con
     const float* bias_chunk = bias != nullptr ? bias + n_off : nullptr;
     const float* res_chunk = residual != nullptr ? residual + n_off : nullptr;
     // persistent kernel: one CTA per SM, items = (M tile, K split)
+    const int n_items = m_tiles * splits;
+    const int grid = min(n_items, cta_budget > 0 ? min(cta_budget, sm_count()) : sm_count());
+    cudaError_t err;
+    if (split) {
+        // 3xTF32: decoupled landing / A / B rings (conv_tc3)
+        const size_t fixed3 = (size_t)2 * kTileM * F * sizeof(int) + 16 + kTc3Bars * 8 + 16 + 1024;
+        const size_t b_pair = 2 * b_tile;
+        int b_stages = b_pair <= 8 * 1024 ? 4 : b_pair <= 16 * 1024 ? 3 : 2;
+        const size_t avail = 227 * 1024 - fixed3 - (size_t)kTc3AStages * 2 * kATileBytes;
+        if (avail < b_stages * b_pair + kATileBytes) b_stages = 2;
+        if (avail < 2 * b_pair + kATileBytes) {
+            set_error("ln_conv_fwd: tensor-core tile does not fit shared memory (c_out=%d)", c_out);
+            return LN_ERR_UNSUPPORTED;
+        }
+        int landing = (int)min((size_t)kTc3MaxLanding, (avail - b_stages * b_pair) / kATileBytes);
+        landing = max(1, min(landing, cdiv(n_items, grid) * kb_per_split));      // never deeper than the work of a CTA
+        const size_t smem = max(fixed3 + (size_t)kTc3AStages * 2 * kATileBytes + b_stages * b_pair + (size_t)landing * kATileBytes, (size_t)120 * 1024);
+        err = allow_max_smem((const void*)conv_tc3_kernel);
+        if (err == cudaSuccess)
+            launch_k(conv_tc3_kernel, dim3(grid), dim3(kTc3Threads), smem, s, nbr_values, neighbours, b_hi, b_lo, bias_chunk, res_chunk, nv_query, F,
+                     c_in, c_out, ld_n, n_pad, flip, landing, b_stages, m_tiles, n_items, kb_per_split, out_chunk);
+        if (err != cudaSuccess) {
+            set_error("conv_tc3: %s", cudaGetErrorString(err));
+            return LN_ERR_CUDA;
+        }
+        count_launch();
+        return check_launch("conv_tc3");
+    }
     const size_t fixed = (size_t)2 * kTileM * F * sizeof(int) + 16 + (2 * kMaxStages + 4) * 8 + 16 + 1024;
     const int stages = min((int)((227 * 1024 - fixed) / stage_bytes), kMaxStages);
     if (stages < 2) {
         set_error("ln_conv_fwd: tensor-core tile does not fit shared memory (c_out=%d)", c_out);
         return LN_ERR_UNSUPPORTED;
     }
-    const int n_items = m_tiles * splits;
-    const int grid = min(n_items, cta_budget > 0 ? min(cta_budget, sm_count()) : sm_count());
     const int lookahead = lookahead_for(stages, cdiv(n_items, grid) * kb_per_split);
     // > half of the SM's shared memory: exactly one CTA per SM, so the 2*n_pad TMEM columns are always available
     const size_t smem = max((size_t)stages * stage_bytes + fixed, (size_t)120 * 1024);
-    cudaError_t err;
-    if (split) {
-        err = allow_max_smem((const void*)conv_tc2_kernel<1>);
-        if (err == cudaSuccess)
-            launch_k(conv_tc2_kernel<1>, dim3(grid), dim3(kTc2Threads), smem, s, nbr_values, neighbours, b_hi, b_lo, bias_chunk, res_chunk, nv_query, F, c_in, c_out, ld_n,
-                                                                n_pad, flip, stages, lookahead, m_tiles, n_items, kb_per_split, out_chunk);
-    } else {
-        err = allow_max_smem((const void*)conv_tc2_kernel<0>);
-        if (err == cudaSuccess)
-            launch_k(conv_tc2_kernel<0>, dim3(grid), dim3(kTc2Threads), smem, s, nbr_values, neighbours, b_hi, b_lo, bias_chunk, res_chunk, nv_query, F, c_in, c_out, ld_n,
-                                                                n_pad, flip, stages, lookahead, m_tiles, n_items, kb_per_split, out_chunk);
-    }
+    err = allow_max_smem((const void*)conv_tc2_kernel<0>);
+    if (err == cudaSuccess)
+        launch_k(conv_tc2_kernel<0>, dim3(grid), dim3(kTc2Threads), smem, s, nbr_values, neighbours, b_hi, b_lo, bias_chunk, res_chunk, nv_query, F, c_in, c_out, ld_n,
+                 n_pad, flip, stages, lookahead, m_tiles, n_items, kb_per_split, out_chunk);
     if (err != cudaSuccess) {
         set_error("conv_tc2: %s", cudaGetErrorString(err));
         return LN_ERR_CUDA;
