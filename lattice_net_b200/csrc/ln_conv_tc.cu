@@ -554,22 +554,22 @@ conv_tc2_kernel(const float* __restrict__ values, const int* __restrict__ neighb
 // flight.  Three rings instead of one:
 //   landing ring  `landing` x 16 KB: raw fp32 rows straight from cp.async, up to 8 K blocks in flight.  Every producer
 //                 thread re-reads exactly the 16-byte units it gathered itself, so a slot is recycled without any barrier;
-//   A ring        2 x (hi 16 KB | lo 16 KB): written by the producers when a block has landed (round-to-nearest TF32 high
+//   A ring        `a_stages` (2..4) x (hi 16 KB | lo 16 KB): written by the producers when a block has landed (round-to-nearest TF32 high
 //                 part + residual), consumed by the MMA lane;
 //   B ring        `b_stages` x (hi | lo) pre-split filter slabs, fed by a dedicated bulk-copy warp that runs ahead of the
 //                 MMAs independently of the gathers.
 // Warps: 0-7 producers, 8 MMA issue, 9 filter-slab loader, 10-13 epilogue.
 constexpr int kTc3Threads = kTc2Producers + 32 + 32 + 128;
-constexpr int kTc3AStages = 2;
+constexpr int kTc3MaxA = 4;
 constexpr int kTc3MaxB = 4;
 constexpr int kTc3MaxLanding = 8;
-constexpr int kTc3Bars = 2 * kTc3AStages + 2 * kTc3MaxB + 4;
+constexpr int kTc3Bars = 2 * kTc3MaxA + 2 * kTc3MaxB + 4;
 
 __global__ void __launch_bounds__(kTc3Threads, 1)
 conv_tc3_kernel(const float* __restrict__ values, const int* __restrict__ neighbours,
                 const float* __restrict__ b_hi, const float* __restrict__ b_lo, const float* __restrict__ bias,
                 const float* __restrict__ residual, int nv_query, int F, int c_in, int c_out, int ld_out, int n_pad, int flip,
-                int landing, int b_stages, int m_tiles, int n_items, int kb_per_split, float* __restrict__ out) {
+                int landing, int a_stages, int b_stages, int m_tiles, int n_items, int kb_per_split, float* __restrict__ out) {
     pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t b_tile_bytes = (uint32_t)n_pad * kRowBytes;
@@ -577,9 +577,9 @@ conv_tc3_kernel(const float* __restrict__ values, const int* __restrict__ neighb
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t base_u32 = smem_u32(base);
     const uint32_t a_base = base_u32;
-    const uint32_t b_base = a_base + kTc3AStages * a_stage_bytes;
+    const uint32_t b_base = a_base + (uint32_t)a_stages * a_stage_bytes;
     const uint32_t land_base = b_base + (uint32_t)b_stages * b_stage_bytes;
-    int* nbr_sh = (int*)(base + (size_t)kTc3AStages * a_stage_bytes + (size_t)b_stages * b_stage_bytes + (size_t)landing * kATileBytes);   // [2][kTileM * F]
+    int* nbr_sh = (int*)(base + (size_t)a_stages * a_stage_bytes + (size_t)b_stages * b_stage_bytes + (size_t)landing * kATileBytes);   // [2][kTileM * F]
     uint64_t* bars = (uint64_t*)(((uintptr_t)(nbr_sh + 2 * kTileM * F) + 15) & ~(uintptr_t)15);
     uint32_t* tmem_slot = (uint32_t*)(bars + kTc3Bars);
 
@@ -588,16 +588,16 @@ conv_tc3_kernel(const float* __restrict__ values, const int* __restrict__ neighb
     const int lane = tid & 31;
     const uint32_t bars_u32 = smem_u32(bars);
     auto full_a = [&](int s) { return bars_u32 + 8u * (uint32_t)s; };
-    auto empty_a = [&](int s) { return bars_u32 + 8u * (uint32_t)(kTc3AStages + s); };
-    auto full_b = [&](int s) { return bars_u32 + 8u * (uint32_t)(2 * kTc3AStages + s); };
-    auto empty_b = [&](int s) { return bars_u32 + 8u * (uint32_t)(2 * kTc3AStages + kTc3MaxB + s); };
-    auto acc_full_bar = [&](int a) { return bars_u32 + 8u * (uint32_t)(2 * kTc3AStages + 2 * kTc3MaxB + a); };
-    auto acc_empty_bar = [&](int a) { return bars_u32 + 8u * (uint32_t)(2 * kTc3AStages + 2 * kTc3MaxB + 2 + a); };
+    auto empty_a = [&](int s) { return bars_u32 + 8u * (uint32_t)(kTc3MaxA + s); };
+    auto full_b = [&](int s) { return bars_u32 + 8u * (uint32_t)(2 * kTc3MaxA + s); };
+    auto empty_b = [&](int s) { return bars_u32 + 8u * (uint32_t)(2 * kTc3MaxA + kTc3MaxB + s); };
+    auto acc_full_bar = [&](int a) { return bars_u32 + 8u * (uint32_t)(2 * kTc3MaxA + 2 * kTc3MaxB + a); };
+    auto acc_empty_bar = [&](int a) { return bars_u32 + 8u * (uint32_t)(2 * kTc3MaxA + 2 * kTc3MaxB + 2 + a); };
 
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < 2 * n_pad) tmem_cols <<= 1;       // two accumulator buffers
     if (tid == 0) {
-        for (int s = 0; s < kTc3AStages; s++) {
+        for (int s = 0; s < a_stages; s++) {
             mbar_init(full_a(s), kTc2Producers);   // every producer thread has written its units of the hi / lo tiles
             mbar_init(empty_a(s), 1);              // one tcgen05.commit
         }
@@ -662,7 +662,7 @@ conv_tc3_kernel(const float* __restrict__ values, const int* __restrict__ neighb
             pa_addr += a_stage_bytes;
             pa_full += 8;
             pa_empty += 8;
-            if (pa_addr == a_base + kTc3AStages * a_stage_bytes) {
+            if (pa_addr == a_base + (uint32_t)a_stages * a_stage_bytes) {
                 pa_addr = a_base;
                 pa_full = full_a(0);
                 pa_empty = empty_a(0);
@@ -752,9 +752,9 @@ conv_tc3_kernel(const float* __restrict__ values, const int* __restrict__ neighb
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(a * n_pad);
                 for (int it = 0; it < w.num_kb; it++, g++) {
-                    const int sa = g % kTc3AStages, sb = g % b_stages;
+                    const int sa = g % a_stages, sb = g % b_stages;
                     mbar_wait(full_b(sb), ((uint32_t)(g / b_stages)) & 1u);
-                    mbar_wait(full_a(sa), ((uint32_t)(g / kTc3AStages)) & 1u);
+                    mbar_wait(full_a(sa), ((uint32_t)(g / a_stages)) & 1u);
                     tc_fence_after();
                     const uint32_t a_addr = a_base + (uint32_t)sa * a_stage_bytes, b_addr = b_base + (uint32_t)sb * b_stage_bytes;
                     const uint64_t da_hi = umma_desc_kmajor_sw128(a_addr);
@@ -1281,21 +1281,24 @@ static int conv_fwd_tc_chunk(const float* nbr_values, const int* neighbours, con
     if (split) {
         // 3xTF32: decoupled landing / A / B rings (conv_tc3)
         const size_t fixed3 = (size_t)2 * kTileM * F * sizeof(int) + 16 + kTc3Bars * 8 + 16 + 1024;
-        const size_t b_pair = 2 * b_tile;
-        int b_stages = b_pair <= 8 * 1024 ? 4 : b_pair <= 16 * 1024 ? 3 : 2;
-        const size_t avail = 227 * 1024 - fixed3 - (size_t)kTc3AStages * 2 * kATileBytes;
-        if (avail < b_stages * b_pair + kATileBytes) b_stages = 2;
-        if (avail < 2 * b_pair + kATileBytes) {
+        const size_t b_pair = 2 * b_tile, a_pair = 2 * kATileBytes;
+        const size_t budget = 227 * 1024 - fixed3;
+        // ring depths: the A ring hides the publish -> MMA hand-over latency (3 deep when it fits), the B ring runs 2..4 slabs
+        // ahead, what is left becomes landing slots (gathers in flight)
+        int a_stages = 3, b_stages = b_pair <= 8 * 1024 ? 4 : b_pair <= 16 * 1024 ? 3 : 2;
+        if (budget < a_stages * a_pair + b_stages * b_pair + 2 * kATileBytes) b_stages = 2;
+        if (budget < a_stages * a_pair + b_stages * b_pair + 2 * kATileBytes) a_stages = 2;
+        if (budget < a_stages * a_pair + b_stages * b_pair + kATileBytes) {
             set_error("ln_conv_fwd: tensor-core tile does not fit shared memory (c_out=%d)", c_out);
             return LN_ERR_UNSUPPORTED;
         }
-        int landing = (int)min((size_t)kTc3MaxLanding, (avail - b_stages * b_pair) / kATileBytes);
+        int landing = (int)min((size_t)kTc3MaxLanding, (budget - a_stages * a_pair - b_stages * b_pair) / kATileBytes);
         landing = max(1, min(landing, cdiv(n_items, grid) * kb_per_split));      // never deeper than the work of a CTA
-        const size_t smem = max(fixed3 + (size_t)kTc3AStages * 2 * kATileBytes + b_stages * b_pair + (size_t)landing * kATileBytes, (size_t)120 * 1024);
+        const size_t smem = max(fixed3 + a_stages * a_pair + b_stages * b_pair + (size_t)landing * kATileBytes, (size_t)120 * 1024);
         err = allow_max_smem((const void*)conv_tc3_kernel);
         if (err == cudaSuccess)
             launch_k(conv_tc3_kernel, dim3(grid), dim3(kTc3Threads), smem, s, nbr_values, neighbours, b_hi, b_lo, bias_chunk, res_chunk, nv_query, F,
-                     c_in, c_out, ld_n, n_pad, flip, landing, b_stages, m_tiles, n_items, kb_per_split, out_chunk);
+                     c_in, c_out, ld_n, n_pad, flip, landing, a_stages, b_stages, m_tiles, n_items, kb_per_split, out_chunk);
         if (err != cudaSuccess) {
             set_error("conv_tc3: %s", cudaGetErrorString(err));
             return LN_ERR_CUDA;
