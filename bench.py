@@ -243,6 +243,8 @@ def extra_measurements(args):
             scenes.append({k: r[k] for k in ("scene", "n_points", "vertices_per_level", "fwd_bwd_ms", "scans_per_s", "points_per_s", "inference_ms",
                                               "inference_points_per_s", "execution", "conv")})
         except Exception as exc:
+            import traceback
+            traceback.print_exc(file=sys.stderr)
             scenes.append({"scene": name, "error": f"{type(exc).__name__}: {exc}"})
         torch.cuda.empty_cache()
     out["scenes"] = scenes

@@ -188,6 +188,8 @@ def main():
         try:
             line = run_scene(name, args.impl, args.steps, args.warmup, args.conv_precision, args.mode)
         except Exception as exc:       # keep going: the other scene is still worth its line
+            import traceback
+            traceback.print_exc(file=sys.stderr)
             line = {"scene": name, "impl": args.impl, "error": f"{type(exc).__name__}: {exc}"}
         print(json.dumps(line), flush=True)
 
