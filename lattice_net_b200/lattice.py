@@ -92,12 +92,16 @@ def prepare_filters(readings):
         if entry.version != t._version or entry.precision != CONV_PRECISION:
             stale = True
         todo.append((t, entry, key))
-    if not todo or not (stale or torch.cuda.is_current_stream_capturing()):
+    if not todo:
         return 0
     device = todo[0][0].device
+    capturing = torch.cuda.is_current_stream_capturing()
     sig = (CONV_PRECISION,) + tuple((k, e.dims, e.slabs.data_ptr()) for _, e, k in todo)
     table = _JOB_TABLES.get(sig)
-    if table is None:
+    if table is None and capturing:
+        raise RuntimeError("prepare_filters: this set of filter banks was never prepared outside a CUDA-graph capture (its job table "
+                           "needs a host-to-device copy): run one warm-up pass of the same model call before capturing")
+    if table is None:      # built on the first call with this set of banks, also when nothing is stale: a later capture needs it
         blob, first = b"", 0
         for t, e, (ptr_, transposed) in todo:
             F, c_in, c_out = e.dims
@@ -108,6 +112,8 @@ def prepare_filters(readings):
         if len(_JOB_TABLES) > 64:
             _JOB_TABLES.clear()
         table = _JOB_TABLES[sig] = (host.to(device), len(todo), first)
+    if not (stale or capturing):
+        return 0
     call("ln_filter_prepare_batch", ptr(table[0]), table[1], table[2], stream_ptr(device))
     for t, e, _ in todo:
         e.version, e.precision = t._version, CONV_PRECISION
