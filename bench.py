@@ -288,7 +288,8 @@ def run_ours(args):
         nr_levels = model.nr_downsamples + 1
         bounds = estimate_vertex_bounds(CAPACITY, [(SIGMA, 3)], [c[0] for c in dev_clouds], nr_levels, headroom=1.3)
         step = GraphedTrainStep(model, lattice, optimizer, segmentation_loss, NR_POINTS, 3, 1, bounds, bucket, world,
-                                warmup=3, capture_collective=args.capture_collective, example=dev_clouds[0])
+                                warmup=3, capture_collective=args.capture_collective, example=dev_clouds[0],
+                                overlap_allreduce=not args.no_overlap_allreduce)
         launches_per_step = step.launches_per_step
 
         def step_resident(i):
@@ -350,7 +351,8 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "LatticeNet ShapeNet-part segmentation fwd+bwd+AdamW (lnn_train_shapenet.cfg arch), 2048-pt synthetic clouds, 1 scene/step/GPU",
                    "nr_points": NR_POINTS, "nr_classes": NR_CLASSES, "sigma": SIGMA, "hash_table_capacity": CAPACITY,
-                   "parallelism": f"scene-parallel dp{world}, one flat NCCL all-reduce of {bucket.nbytes} grad bytes/step",
+                   "parallelism": (f"scene-parallel dp{world}, {bucket.nbytes} gradient bytes all-reduced per step over NCCL"
+                                   + (", in two chunks: decoder + slice head under the encoder's backward pass, the rest after it" if (graphed and getattr(step, "split", None) is not None) else ", one flat all-reduce")),
                    "replicas_bit_identical_after_run": in_sync,
                    "execution": ("%s (static-shape lattice, rows per level %s; %d step(s) skipped for exceeding them)"
                                  % ("one CUDA graph per step" + (", NCCL all-reduce captured inside it" if world > 1 else "") if len(step.graphs) == 1
@@ -401,6 +403,8 @@ def main():
                     help="N>1: two graphs per step with an eager NCCL all-reduce between them")
     ap.add_argument("--conv-precision", type=int, default=1, choices=[0, 1, 2],
                     help="0 fp32 CUDA cores, 1 tcgen05 3xTF32 (fp32-equivalent, default), 2 tcgen05 TF32")
+    ap.add_argument("--no-overlap-allreduce", action="store_true",
+                    help="N>1: one all-reduce after the backward pass instead of two chunks, the late one under the encoder's backward")
     ap.add_argument("--no-extras", action="store_true", help="skip the `ops` / `scenes` keys (scene-sized scans and operator roofline points, ~1 min)")
     ap.add_argument("--torch-optimizer", action="store_true", help="torch.optim.AdamW(fused) instead of the one-kernel flat AdamW")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s CPU leg (profiler passes only; never for a reported line)")

@@ -48,7 +48,7 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model, lattice, optimizer, loss_fn, nr_points, pos_dim, val_dim, bounds, bucket, world=1,
-                 warmup=3, capture_collective=False, example=None):
+                 warmup=3, capture_collective=False, example=None, overlap_allreduce=True):
         self.model, self.lattice, self.optimizer, self.loss_fn = model, lattice, optimizer, loss_fn
         self.bucket, self.world = bucket, world
         dev = bucket.flat.device
@@ -73,34 +73,67 @@ class GraphedTrainStep:
         self.launches_per_step = 0
         # zeroed outputs of the split-K convolutions: one buffer, one memset per step (sized by a dry run in _capture)
         self.arena = _lattice.ZeroArena(0, None)
+        # world > 1: the gradient all-reduce runs in two chunks.  The LATE chunk (decoder + slice head, ~80 % of the bytes,
+        # complete when the backward pass reaches the bottleneck) goes out on a side stream under the encoder's backward;
+        # the early chunk follows at the end.  Both are captured inside the step graph.
+        self.split = None
+        self.side = None
+        if self.capture_collective and overlap_allreduce and hasattr(model, "finefy_list") and hasattr(model, "grad_sync_hook"):
+            first_late = next(iter(model.finefy_list.parameters()), None)
+            if first_late is not None:
+                self.split = bucket.split_offset(first_late)
+                self.side = torch.cuda.Stream(device=dev)
+                model.grad_sync_hook = self._late_chunk_ready
         self._capture(warmup)
 
     # -- the three phases of a step; `_allreduce` is the only part that may have to stay outside a graph
-    def _forward_backward(self):
-        self.arena.reset()                       # one memset for every output a split-K convolution accumulates into
-        self.bucket.begin_direct_step()          # one memset for every weight gradient; .grad <- None
-        prev = _lattice.set_zero_arena(self.arena)
-        try:
-            logsoftmax, _ = self.model(self.lattice, self.pos, self.vals)
-            loss = self.loss_fn(logsoftmax, self.labels)
-            loss.backward()
-        finally:
-            _lattice.set_zero_arena(prev)
-            self.bucket.end_direct_step()
-        self.loss.copy_(loss.detach())
+    def _levels_status(self):
         import ctypes
         from ._cabi import call, ptr, stream_ptr
         sts = [l.m_hash_table.structure for l in self.model.last_level_lattices]
         call("ln_levels_status", (ctypes.c_void_p * len(sts))(*[s.nr_filled.data_ptr() for s in sts]),
              (ctypes.c_void_p * len(sts))(*[s.status.data_ptr() for s in sts]), len(sts), ptr(self.nv_actual), ptr(self.found_inf),
              stream_ptr(self.device))
+
+    def _late_chunk_ready(self, _grad):
+        """Backward-pass hook at the bottleneck (LNN.forward): the gradients of every later layer are final.  Collect the few
+        that are not in the bucket yet, append the overflow flag, and all-reduce that chunk on the side stream."""
+        self.bucket.pack(extra=self.found_inf, first=self.split)
+        cur = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            dist.all_reduce(self.bucket.flat_with_extra[self.split:], op=dist.ReduceOp.SUM)
+        self._late_sent = True
+        return None
+
+    def _forward_backward(self):
+        self.arena.reset()                       # one memset for every output a split-K convolution accumulates into
+        self.bucket.begin_direct_step()          # one memset for every weight gradient; .grad <- None
+        self._late_sent = False
+        prev = _lattice.set_zero_arena(self.arena)
+        try:
+            logsoftmax, _ = self.model(self.lattice, self.pos, self.vals)
+            self._levels_status()                # the lattice pyramid is complete after the forward pass: overflow flag, vertex counts
+            loss = self.loss_fn(logsoftmax, self.labels)
+            loss.backward()
+        finally:
+            _lattice.set_zero_arena(prev)
+            self.bucket.end_direct_step()
+        self.loss.copy_(loss.detach())
         if self.world > 1 or self.flat_optimizer:
-            # gradients that did not land in the bucket by themselves (a handful: weight-norm, slice-head scalars) are copied in
-            self.bucket.pack(extra=self.found_inf)
+            # gradients that did not land in the bucket by themselves (a handful: biases, weight-norm gains) are copied in
+            if self._late_sent:
+                self.bucket.pack(last=self.split)
+            else:
+                self.bucket.pack(extra=self.found_inf)
 
     def _allreduce(self):
         if self.world > 1:
-            dist.all_reduce(self.bucket.flat_with_extra, op=dist.ReduceOp.SUM)
+            if self._late_sent:
+                dist.all_reduce(self.bucket.flat[:self.split], op=dist.ReduceOp.SUM)
+                torch.cuda.current_stream(self.device).wait_stream(self.side)
+            else:
+                dist.all_reduce(self.bucket.flat_with_extra, op=dist.ReduceOp.SUM)
 
     def _update(self):
         if self.world > 1:

@@ -26,6 +26,7 @@ class LNN(torch.nn.Module):
         compression = mp.compression_factor()
         log = print if verbose else (lambda *a, **k: None)
 
+        self.grad_sync_hook = None       # callable(grad) -> None, see forward(); set by graphed.GraphedTrainStep for world > 1
         self.fused_point_net = True      # False: the module-by-module path of the reference (distribute rows, torch MLP, scatter ops)
         self.distribute = DistributeLatticeModule()
         self.pointnet_channels_per_layer = list(mp.pointnet_channels_per_layer())
@@ -114,6 +115,10 @@ class LNN(torch.nn.Module):
 
         for block in self.resnet_blocks_bottleneck:
             lv, ls = block(lv, ls)
+        if self.grad_sync_hook is not None and lv.requires_grad:
+            # fires in the backward pass once every layer after this point has its gradients (decoder + slice head: most of
+            # the parameter bytes): scene-parallel training starts their all-reduce here, under the rest of the backward
+            lv.register_hook(self.grad_sync_hook)
 
         for lvl in range(self.nr_downsamples):
             skip_values = fine_values.pop()

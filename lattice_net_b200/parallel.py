@@ -89,10 +89,22 @@ class GradBucket:
         from . import lattice as _lattice
         _lattice.set_grad_targets_active(False)
 
-    def pack(self, extra=None):
-        """Call after backward: flat <- the grads that are not already there (one fused copy), .grad <- views of flat."""
+    def split_offset(self, first_late_param):
+        """Flat offset of `first_late_param`: parameters from it to the end form the LATE chunk -- the layers nearest the loss,
+        whose gradients are complete first in a backward pass -- so its all-reduce can overlap the rest of the backward."""
+        for p, off in zip(self.params, self.offsets):
+            if p is first_late_param:
+                return off
+        raise ValueError("parameter is not in this bucket")
+
+    def pack(self, extra=None, first=0, last=None):
+        """Call after backward: flat <- the grads that are not already there (one fused copy), .grad <- views of flat.
+        first / last: restrict to the parameters whose slices start in [first, last) (flat offsets)."""
         dst, src = [], []
-        for p, v in zip(self.params, self.views):
+        last = self.flat.numel() if last is None else last
+        for p, v, off in zip(self.params, self.views, self.offsets):
+            if off < first or off >= last:
+                continue
             if p.grad is None:
                 if not self._direct:
                     v.zero_()                  # no memset cleared the buffer this step: drop the previous step's values
@@ -102,8 +114,9 @@ class GradBucket:
                 src.append(p.grad)
         if dst:
             torch._foreach_copy_(dst, src)
-        for p, v in zip(self.params, self.views):
-            p.grad = v
+        for p, v, off in zip(self.params, self.views, self.offsets):
+            if first <= off < last:
+                p.grad = v
         if extra is not None:
             self.extra.copy_(extra.reshape(1))
 
