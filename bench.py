@@ -414,6 +414,9 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
