@@ -297,8 +297,15 @@ def run_ours(args):
 
         losses = []
 
+        from lattice_net_b200.data import PinnedCloudFeeder
+        feeder = PinnedCloudFeeder(NR_POINTS, 3, 1, device)      # pinned double buffer: the H2D of cloud i+1 runs under step i
+        feeder.stage(*host_clouds[0])
+
         def step_e2e(i):
-            loss = step(*host_clouds[i % POOL])                      # H2D of the cloud from pinned memory
+            slot, (pos, vals, labels) = feeder.current()
+            feeder.stage(*host_clouds[(i + 1) % POOL])               # host -> pinned -> device copy of the NEXT cloud, on the copy stream
+            loss = step(pos, vals, labels)
+            feeder.release(slot)
             losses.append(float(loss.item()))                       # D2H read of the step's result
     else:
         def step_resident(i):

@@ -1506,3 +1506,46 @@ def test_reference_arm_drives_the_reference_python_unmodified():
     before = _cabi.launch_count()
     model(lat, pos, vals)
     assert _cabi.launch_count() == before
+
+
+def test_input_path_prepare_cloud_and_pinned_feeder(tmp_path):
+    """prepare_cloud's position / value modes (models.py:18-66), the SemanticKITTI file formats, and the
+    double-buffered pinned feeder delivering every cloud intact while the previous one is being consumed."""
+    from lattice_net_b200.data import PinnedCloudFeeder, SyntheticCloud, prepare_cloud, read_semantic_kitti_scan, write_label_file
+    from lattice_net_b200.params import ModelParams
+    c = SyntheticCloud(500, 7, 3, with_colour=True, with_intensity=True)
+    for pm, vm, pd, vd in [("xyz", "none", 3, 1), ("xyz+rgb", "intensity", 6, 1), ("xyz+intensity", "rgb+height", 4, 4), ("xyz", "rgb+xyz", 3, 6),
+                           ("xyz", "height", 3, 1), ("xyz", "xyz", 3, 3), ("xyz", "rgb", 3, 3)]:
+        pos, vals, tgt = prepare_cloud(c, ModelParams(dict(positions_mode=pm, values_mode=vm)))
+        assert tuple(pos.shape) == (500, pd) and tuple(vals.shape) == (500, vd) and tgt.dtype == torch.int64 and tuple(tgt.shape) == (500,)
+        assert pos.is_cuda and pos.is_contiguous() and vals.is_contiguous()
+        assert bits_equal(pos[:, :3].cpu().numpy(), c.V) == 0
+    pos, vals, _ = prepare_cloud(c, ModelParams(dict(positions_mode="xyz", values_mode="rgb+height")))
+    assert bits_equal(vals[:, 3].cpu().numpy(), c.V[:, 1]) == 0 and bits_equal(vals[:, :3].cpu().numpy(), c.C) == 0
+    # SemanticKITTI formats
+    scan = np.concatenate([c.V, c.I], 1).astype(np.float32)
+    scan.tofile(tmp_path / "000000.bin")
+    (c.L_gt.reshape(-1).astype(np.uint32) | np.uint32(5 << 16)).tofile(tmp_path / "000000.label")     # upper 16 bits: instance id
+    k = read_semantic_kitti_scan(str(tmp_path / "000000.bin"), str(tmp_path / "000000.label"))
+    assert bits_equal(k.V, c.V) == 0 and np.array_equal(k.L_gt, c.L_gt)
+    logsm = torch.log_softmax(torch.randn(500, 7, device="cuda"), 1)
+    written = write_label_file(logsm, str(tmp_path / "pred" / "000000.label"))
+    assert np.array_equal(np.fromfile(tmp_path / "pred" / "000000.label", dtype=np.uint32), logsm.argmax(1).cpu().numpy().astype(np.uint32))
+    assert written.dtype == np.uint32
+    # feeder: 7 clouds through 2 slots, consumed by a slow kernel so that staging really overlaps
+    n = 4096
+    clouds = [(np.random.RandomState(i).rand(n, 3).astype(np.float32), np.full((n, 1), i, np.float32), np.full((n,), i, np.int64)) for i in range(7)]
+    feeder = PinnedCloudFeeder(n, 3, 1, torch.device("cuda", 0))
+    feeder.stage(*clouds[0])
+    sink = torch.zeros((2048, 2048), device="cuda")
+    seen = []
+    for i in range(7):
+        slot, (p, v, l) = feeder.current()
+        if i + 1 < 7:
+            feeder.stage(*clouds[i + 1])
+        sink = sink @ sink                                   # keeps the compute stream busy
+        seen.append((p.clone(), v.clone(), l.clone()))
+        feeder.release(slot)
+    torch.cuda.synchronize()
+    for i, (p, v, l) in enumerate(seen):
+        assert bits_equal(p.cpu().numpy(), clouds[i][0]) == 0 and float(v.min()) == float(v.max()) == float(i) and int(l[0]) == i
