@@ -221,7 +221,7 @@ def run(n, d, vals, quick, order="random", with_ref=True, with_extras=True):
         emit("slice_bwd", cfg, timeit(slb, reps=5), nbytes=8 * n * (d + 1) + 4 * nv * V + 4 * n * V, ref_sec=rs)
         del x, lv, out, g, gl
 
-        if V >= 32 and not (quick and V > 128):
+        if V >= 32:
             F = 2 * (d + 1) + 1
             fb = torch.randn((F * V, V), device=dev) * 0.05
             lat2._neighbour_table(lat2, 1)
@@ -309,6 +309,7 @@ def main():
     ap.add_argument("--vals", type=int, nargs="*", default=None)
     ap.add_argument("--order", default="random", choices=["random", "morton"], help="point order of the synthetic cloud")
     ap.add_argument("--gn-only", type=int, default=0, metavar="NV", help="only the GroupNorm entries, on an [NV x C] tensor")
+    ap.add_argument("--no-ref", action="store_true", help="skip the reference-kernel columns (their im2row buffer is F x the activations)")
     ap.add_argument("--pos-dims", type=int, nargs="*", default=None, help="position dimensions to sweep (default: 3, then 5 at half the last n)")
     args = ap.parse_args()
     measure_tf32_peak()
@@ -319,7 +320,7 @@ def main():
     if args.pos_dims:
         for d in args.pos_dims:
             for n in args.n:
-                run(n, d, args.vals if args.vals else [8, 32, 64, 128, 256], args.quick, args.order)
+                run(n, d, args.vals if args.vals else [8, 32, 64, 128, 256], args.quick, args.order, with_ref=not args.no_ref and n <= 1000000)
         return
     for n in args.n:
         run(n, 3, args.vals if args.vals else ([8, 32, 64] if args.quick else [1, 8, 32, 64, 128]), args.quick, args.order)
