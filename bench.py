@@ -330,6 +330,8 @@ def run_ours(args):
     _cabi.reset_launch_count()
     ms = timed_region(step_resident, args.steps, world, device, flush_buf)
     launches = _cabi.launch_count() if not graphed else launches_per_step * args.steps
+    # the headline region is K steps = a few tens of milliseconds: four more identical regions show how stable it is
+    repeats = [ms] + [timed_region(step_resident, args.steps, world, device, flush_buf) for _ in range(4)]
     for i in range(max(1, args.warmup // 2)):
         step_e2e(i)
     ms_e2e = timed_region(step_e2e, args.steps, world, device, flush_buf)
@@ -371,6 +373,8 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "final_loss": losses[-1] if losses else None,
+        "stability": {"ms_per_step_of_5_regions": [r / args.steps for r in repeats], "median_value": scans / (float(np.median(repeats)) * 1e-3),
+                      "note": "`value` is the FIRST region (the contract's K timed steps); the other four follow it back to back"},
     }
     line.update(extras)
     print(json.dumps(line))

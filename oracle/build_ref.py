@@ -33,6 +33,7 @@ VALS_SMALL = (1, 3, 4, 8)
 VALS_ALL = (1, 3, 4, 8, 16, 32, 64, 128)
 VALS_CONV = (1, 3, 4, 8, 16, 32, 64, 96, 128, 192, 256, 384, 512)   # channel widths met by the LatticeNet architectures (ShapeNet, ScanNet, SemanticKITTI)
 CLASSIFY = ((32, 7), (64, 16), (128, 7), (128, 20), (8, 4), (256, 20), (128, 21))
+CLASSIFY_D5 = ((32, 7), (64, 16), (8, 4))          # pos_dim 5 (xyz + rgb lattices): enough to pin the d = 5 code path
 
 
 def name_expressions():
@@ -53,10 +54,9 @@ def name_expressions():
             names.append(f"im2rowindices<{d},{v}>")
             names.append(f"gather_with_precomputation<{d},{v}>")
             names.append(f"gather_backwards_with_precomputation<{d},{v}>")
-        if d == 3:
-            for v, nc in CLASSIFY:
-                names.append(f"slice_classify_with_precomputation<{d},{v},{nc}>")
-                names.append(f"slice_classify_backwards_with_precomputation<{d},{v},{nc}>")
+        for v, nc in (CLASSIFY if d == 3 else CLASSIFY_D5):
+            names.append(f"slice_classify_with_precomputation<{d},{v},{nc}>")
+            names.append(f"slice_classify_backwards_with_precomputation<{d},{v},{nc}>")
     return names
 
 

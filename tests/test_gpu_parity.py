@@ -184,8 +184,8 @@ def test_gather_fwd_bwd(built):
 @pytest.mark.parametrize("V,nc", [(32, 7), (128, 20), (8, 4), (64, 16), (256, 20)])
 def test_slice_classify(built, V, nc):
     b = built
-    if b["d"] != 3:
-        pytest.skip("reference slice_classify instantiations are built for pos_dim 3")
+    if b["d"] != 3 and (V, nc) not in ((32, 7), (64, 16), (8, 4)):
+        pytest.skip("reference slice_classify instantiations for pos_dim 5 are built for three (V, nc) pairs")
     n, d = b["n"], b["d"]
     lv = cases.randn((b["nv"], V), 20 + V)
     dw = (cases.randn((n, d + 1), 50) * 0.05).astype(np.float32)
