@@ -303,9 +303,9 @@ def run_ours(args):
 
         def step_e2e(i):
             slot, (pos, vals, labels) = feeder.current()
-            feeder.stage(*host_clouds[(i + 1) % POOL])               # host -> pinned -> device copy of the NEXT cloud, on the copy stream
-            loss = step(pos, vals, labels)
+            loss = step(pos, vals, labels)                           # asynchronous: input copies + one graph launch
             feeder.release(slot)
+            feeder.stage(*host_clouds[(i + 1) % POOL])               # host -> pinned -> device copy of the NEXT cloud, under this step
             losses.append(float(loss.item()))                       # D2H read of the step's result
     else:
         def step_resident(i):
