@@ -200,11 +200,17 @@ int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* g
  *   grad_filter [F*c_in x c_out]    = im2row(nbr_values)^T . grad_out                 NULL = not wanted
  * The two run side by side (the weight gradient on an internal second stream, joined before returning).
  * slabs_bwd / slabs_prepared: prepared TRANSPOSED reading of `filter` (ln_conv_workspace_bytes(F, c_out, c_in, precision)
- * bytes), as in ln_conv_fwd.  *_is_zero: as in ln_conv_fwd / ln_conv_wgrad. */
+ * bytes), as in ln_conv_fwd.  *_is_zero: as in ln_conv_fwd / ln_conv_wgrad.
+ * linear_weight != 0 (filter_extent 1): `filter` is a torch.nn.Linear weight [c_out x c_in], i.e. the bank stored
+ * transposed: grad_nbr_values = grad_out . filter (its plain reading) and grad_filter [c_out x c_in] = grad_out^T . nbr_values.
+ * defer_join != 0: do not make `stream` wait for the weight gradient; the caller calls ln_conv_bwd_join(stream) before
+ * anything reads a grad_filter and keeps nbr_values / grad_out alive until then (the weight gradients of a whole backward
+ * pass then trail the data-gradient chain instead of holding it up layer by layer). */
 int ln_conv_bwd(const float* nbr_values, const int* neighbours_fwd, const float* grad_out, const int* neighbours_bwd,
                 const float* filter, int nv_query, int nv_nbr, int filter_extent, int c_in, int c_out, int precision,
                 float* slabs_bwd, int slabs_prepared, float* grad_nbr_values, int grad_nbr_is_zero, float* grad_filter,
-                int grad_filter_is_zero, void* stream);
+                int grad_filter_is_zero, int linear_weight, int defer_join, void* stream);
+int ln_conv_bwd_join(void* stream);
 
 /* filter_bw[(slot*c_out + co), ci] = filter[(slot*c_in + ci), co]: the re-layout done with
  * transpose/view/contiguous in lattice_funcs.py:304-311. */

@@ -32,7 +32,8 @@ _SIGNATURES = {
     "ln_filter_prepare": [_P, _I, _I, _I, _I, _I, _P, _P],
     "ln_filter_prepare_batch": [_P, _I, ctypes.c_longlong, _P],
     "ln_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
-    "ln_conv_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P],
+    "ln_conv_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _I, _P],
+    "ln_conv_bwd_join": [_P],
     "ln_filter_for_dgrad": [_P, _I, _I, _I, _P, _P],
     "ln_slice_fwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "ln_slice_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P],

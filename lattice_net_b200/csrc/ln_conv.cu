@@ -316,10 +316,11 @@ int ln_conv_wgrad(const float* nbr_values, const int* neighbours, const float* g
 int ln_conv_bwd(const float* nbr_values, const int* neighbours_fwd, const float* grad_out, const int* neighbours_bwd,
                 const float* filter, int nv_query, int nv_nbr, int filter_extent, int c_in, int c_out, int precision,
                 float* slabs_bwd, int slabs_prepared, float* grad_nbr_values, int grad_nbr_is_zero, float* grad_filter,
-                int grad_filter_is_zero, void* stream) {
+                int grad_filter_is_zero, int linear_weight, int defer_join, void* stream) {
     LN_REQUIRE(nbr_values && neighbours_fwd && grad_out && filter, "ln_conv_bwd: null pointer");
     LN_REQUIRE(nv_query >= 0 && nv_nbr >= 0 && filter_extent >= 1 && c_in >= 1 && c_out >= 1, "ln_conv_bwd: bad size");
     LN_REQUIRE(grad_nbr_values == nullptr || neighbours_bwd != nullptr, "ln_conv_bwd: the data gradient needs the reverse neighbour table");
+    LN_REQUIRE(!linear_weight || filter_extent == 1, "ln_conv_bwd: a Linear weight is a filter bank of extent 1");
     cudaStream_t s = (cudaStream_t)stream;
     const bool want_dgrad = grad_nbr_values != nullptr && nv_nbr > 0;
     // weight gradient on the side stream while the data gradient runs on the caller's
@@ -335,16 +336,33 @@ int ln_conv_bwd(const float* nbr_values, const int* neighbours_fwd, const float*
         if (cdiv(nv_nbr, 128) < sms && cdiv(nv_query, 128) < sms) half = sms / 2;
     }
     int rw = LN_OK;
-    if (grad_filter != nullptr)
-        rw = conv_wgrad_launch(nbr_values, neighbours_fwd, grad_out, nv_query, filter_extent, c_in, c_out, precision, grad_filter,
-                               grad_filter_is_zero != 0, half, ss ? ss->stream : s);
+    if (grad_filter != nullptr) {
+        if (linear_weight)   // dW [c_out x c_in] = G^T X: the weight gradient of the transposed problem (roles of X and G swapped)
+            rw = conv_wgrad_launch(grad_out, neighbours_fwd, nbr_values, nv_query, 1, c_out, c_in, precision, grad_filter, grad_filter_is_zero != 0,
+                                   half, ss ? ss->stream : s);
+        else
+            rw = conv_wgrad_launch(nbr_values, neighbours_fwd, grad_out, nv_query, filter_extent, c_in, c_out, precision, grad_filter,
+                                   grad_filter_is_zero != 0, half, ss ? ss->stream : s);
+    }
     int rd = LN_OK;
-    if (want_dgrad)   // flipped convolution of grad_out at the neighbour lattice's vertices, forward bank read transposed (c_in <-> c_out)
-        rd = conv_launch(grad_out, neighbours_bwd, filter, nullptr, nullptr, nv_nbr, filter_extent, c_out, c_in, 1, 1, precision, slabs_bwd,
-                         slabs_prepared, grad_nbr_is_zero, grad_nbr_values, half, s, "conv_dgrad_simt");
-    if (ss != nullptr && (cudaEventRecord(ss->join, ss->stream) != cudaSuccess || cudaStreamWaitEvent(s, ss->join, 0) != cudaSuccess))
+    if (want_dgrad)   // flipped convolution of grad_out at the neighbour lattice's vertices, forward bank read transposed (c_in <-> c_out);
+                      // a Linear weight [c_out x c_in] is stored transposed already: dx = dy W is its plain reading
+        rd = conv_launch(grad_out, neighbours_bwd, filter, nullptr, nullptr, nv_nbr, filter_extent, c_out, c_in, linear_weight ? 0 : 1,
+                         linear_weight ? 0 : 1, precision, slabs_bwd, slabs_prepared, grad_nbr_is_zero, grad_nbr_values, half, s, "conv_dgrad_simt");
+    // defer_join: the caller promises to call ln_conv_bwd_join() before anything reads grad_filter and to keep nbr_values /
+    // grad_out alive until then -- the weight gradients of a whole backward pass then trail the data-gradient chain on
+    // the side stream instead of holding it up layer by layer
+    if (ss != nullptr && !defer_join && (cudaEventRecord(ss->join, ss->stream) != cudaSuccess || cudaStreamWaitEvent(s, ss->join, 0) != cudaSuccess))
         return check_launch("conv_bwd join");
     return rw != LN_OK ? rw : rd;
+}
+
+int ln_conv_bwd_join(void* stream) {
+    SideStream* ss = side_stream();
+    if (ss == nullptr) return LN_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaEventRecord(ss->join, ss->stream) != cudaSuccess || cudaStreamWaitEvent(s, ss->join, 0) != cudaSuccess) return check_launch("conv_bwd join");
+    return LN_OK;
 }
 
 int ln_filter_for_dgrad(const float* filter, int filter_extent, int c_in, int c_out, float* filter_bw, void* stream) {

@@ -98,6 +98,7 @@ class GraphedTrainStep:
     def _late_chunk_ready(self, _grad):
         """Backward-pass hook at the bottleneck (LNN.forward): the gradients of every later layer are final.  Collect the few
         that are not in the bucket yet, append the overflow flag, and all-reduce that chunk on the side stream."""
+        _lattice.join_deferred_wgrads(self.device)           # the late layers' weight gradients trail on the side stream
         self.bucket.pack(extra=self.found_inf, first=self.split)
         cur = torch.cuda.current_stream(self.device)
         self.side.wait_stream(cur)
@@ -111,12 +112,15 @@ class GraphedTrainStep:
         self.bucket.begin_direct_step()          # one memset for every weight gradient; .grad <- None
         self._late_sent = False
         prev = _lattice.set_zero_arena(self.arena)
+        prev_defer = _lattice.set_defer_wgrad_join(True)     # weight gradients trail the data-gradient chain; joined below
         try:
             logsoftmax, _ = self.model(self.lattice, self.pos, self.vals)
             self._levels_status()                # the lattice pyramid is complete after the forward pass: overflow flag, vertex counts
             loss = self.loss_fn(logsoftmax, self.labels)
             loss.backward()
         finally:
+            _lattice.set_defer_wgrad_join(prev_defer)
+            _lattice.join_deferred_wgrads(self.device)
             _lattice.set_zero_arena(prev)
             self.bucket.end_direct_step()
         self.loss.copy_(loss.detach())

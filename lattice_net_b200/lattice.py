@@ -271,19 +271,36 @@ def _conv_bwd_call(nbr_vals, table_fwd, g, table_bwd, fb, nv_q, nv_n, F, c_in, c
         grad_in = _zeroed(nv_n, c_in, dev) if in_zero else torch.empty((nv_n, c_in), dtype=torch.float32, device=dev)
     target = grad_target(grad_param) if grad_param is not None else None
     if fb_is_linear_weight:
-        # dW [c_out x c_in] = G^T X is the weight gradient of the transposed problem: swap the roles of X and G
         _check(F == 1, "a Linear weight is a filter bank of extent 1")
         grad_filter = target if target is not None else torch.empty((c_out, c_in), dtype=torch.float32, device=dev)
-        if grad_in is not None:
-            call("ln_conv_fwd", ptr(g), ptr(table_bwd), ptr(fb), None, None, nv_n, 1, c_out, c_in, 0, 0, CONV_PRECISION, ptr(slabs), prepared,
-                 in_zero, ptr(grad_in), stream_ptr(dev))
-        call("ln_conv_wgrad", ptr(g), ptr(table_fwd), ptr(nbr_vals), nv_q, 1, c_out, c_in, CONV_PRECISION, 1 if target is not None else 0,
-             ptr(grad_filter), stream_ptr(dev))
-        return grad_in, grad_filter
-    grad_filter = target if target is not None else torch.empty((F * c_in, c_out), dtype=torch.float32, device=dev)
+    else:
+        grad_filter = target if target is not None else torch.empty((F * c_in, c_out), dtype=torch.float32, device=dev)
+    defer = 1 if (_DEFER_WGRAD_JOIN and grad_in is not None) else 0
     call("ln_conv_bwd", ptr(nbr_vals), ptr(table_fwd), ptr(g), ptr(table_bwd), ptr(fb), nv_q, nv_n, F, c_in, c_out, CONV_PRECISION,
-         ptr(slabs), prepared, ptr(grad_in), in_zero, ptr(grad_filter), 1 if target is not None else 0, stream_ptr(dev))
+         ptr(slabs), prepared, ptr(grad_in), in_zero, ptr(grad_filter), 1 if target is not None else 0, 1 if fb_is_linear_weight else 0, defer,
+         stream_ptr(dev))
+    if defer:
+        _DEFERRED.append((nbr_vals, g, table_fwd))     # the side-stream kernel reads these: no reuse of their memory before the join
     return grad_in, grad_filter
+
+
+# Deferred join of the weight-gradient stream (see ln_conv_bwd): off unless a caller that controls the whole backward pass
+# (graphed.GraphedTrainStep) switches it on and calls join_deferred_wgrads() before the gradients are consumed.
+_DEFER_WGRAD_JOIN = False
+_DEFERRED = []
+
+
+def set_defer_wgrad_join(flag):
+    global _DEFER_WGRAD_JOIN
+    prev, _DEFER_WGRAD_JOIN = _DEFER_WGRAD_JOIN, bool(flag)
+    return prev
+
+
+def join_deferred_wgrads(device):
+    """Make the current stream of `device` wait for every weight gradient still running on the library's side stream."""
+    if _DEFERRED:
+        call("ln_conv_bwd_join", stream_ptr(device))
+        _DEFERRED.clear()
 
 
 def identity_table(nv, device):
