@@ -348,7 +348,8 @@ int ln_conv_bwd(const float* nbr_values, const int* neighbours_fwd, const float*
     if (want_dgrad)   // flipped convolution of grad_out at the neighbour lattice's vertices, forward bank read transposed (c_in <-> c_out);
                       // a Linear weight [c_out x c_in] is stored transposed already: dx = dy W is its plain reading
         rd = conv_launch(grad_out, neighbours_bwd, filter, nullptr, nullptr, nv_nbr, filter_extent, c_out, c_in, linear_weight ? 0 : 1,
-                         linear_weight ? 0 : 1, precision, slabs_bwd, slabs_prepared, grad_nbr_is_zero, grad_nbr_values, half, s, "conv_dgrad_simt");
+                         linear_weight ? 0 : 1, precision, slabs_bwd, slabs_prepared, grad_nbr_is_zero, grad_nbr_values, half, s,
+                         "conv_dgrad_simt");
     // defer_join: the caller promises to call ln_conv_bwd_join() before anything reads grad_filter and to keep nbr_values /
     // grad_out alive until then -- the weight gradients of a whole backward pass then trail the data-gradient chain on
     // the side stream instead of holding it up layer by layer

@@ -1,5 +1,5 @@
-"""ncu raw CSV of scripts/ncu_bench_conv.py -> profiles/roofline_traffic.json (DRAM bytes per ln_conv_fwd call =
-filter_prep + conv_tc2, last captured pair: warm L2 for the re-laid-out filter is what the step sees too).
+"""ncu raw CSV of scripts/ncu_bench_conv.py -> profiles/roofline_traffic.json (DRAM bytes of one conv_tc3 launch -- the
+kernel bench.py's `roofline` times; filter slabs are prepared once per step by a separate batched launch).
     python scripts/roofline_traffic.py gpurun_out/bench_conv_raw.csv profiles/roofline_traffic.json"""
 import csv
 import json
@@ -22,8 +22,8 @@ def main(src, dst):
         wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
         per.append({"kernel": r[col["Kernel Name"]].split("(")[0], "dram_read": rd, "dram_write": wr,
                     "duration_us": float(r[col["gpu__time_duration.sum"]].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}[units[col["gpu__time_duration.sum"]]]})
-    last_prep = max(i for i, k in enumerate(per) if "filter_prep" in k["kernel"])
-    pair = per[last_prep:last_prep + 2]
+    convs = [k for k in per if "conv_tc3" in k["kernel"]]
+    pair = convs[-1:]                     # the last launch: the prepared slabs and the values sit in L2, as inside the step
     out = {"source": "ncu --set full --clock-control none, scripts/ncu_bench_conv.py (B200)", "launches": pair,
            "traffic_bytes_per_call": sum(k["dram_read"] + k["dram_write"] for k in pair)}
     json.dump(out, open(dst, "w"), indent=1)
