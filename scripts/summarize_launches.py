@@ -1,7 +1,7 @@
 """Summarise an ncu `--metrics gpu__time_duration.sum --csv` launch list into per-kernel tables.
 usage: python scripts/summarize_launches.py gpurun_out/launches.csv[.gz] > profiles/rNN_launches.md
 
-Two tables: (1) ONE training step -- the launches between the last two groups of fused-optimizer kernels, i.e. one
+Two tables: (1) ONE training step -- the launches between the last two optimizer kernels (ln::adamw_amsgrad_kernel), i.e. one
 replay of the step graph, which is what the shares of the step must be read from; (2) the whole capture (which
 also holds model initialisation, eager warm-up passes and the graph-capture pass)."""
 import collections
@@ -45,7 +45,7 @@ def table(launches, top=45):
     print()
 
 
-def last_step(launches, marker="FusedOptimizer"):
+def last_step(launches, marker="adamw_amsgrad"):
     hits = [i for i, (n, _) in enumerate(launches) if marker in n]
     groups = []
     for i in hits:
