@@ -176,8 +176,9 @@ int ln_conv_needs_zero(int nv_query, int filter_extent, int c_in, int c_out, int
  * ln_filter_prepare_batch: n_jobs banks in ONE launch; jobs_device = device array of 48-byte records
  *   { const float* src; float* dst; int k_total (= F*c_in of the reading); int c_in; int c_out; int transposed;
  *     int split (1 = write the low parts, precision 1); int pad; long long first_thread; }
- * with first_thread the running sum of k_total * n_pad_sum(c_out) over the preceding jobs (n_pad_sum = c_out rounded up
- * to 16 within every 256-column chunk) and total_threads that sum over all jobs. */
+ * with first_thread the running sum of (k_total / 32) * ceil(n_pad_sum(c_out) / 32) -- the job's number of 32 x 32 tiles, one
+ * CTA each -- over the preceding jobs (n_pad_sum = c_out rounded up to 16 within every 256-column chunk) and total_threads
+ * that sum over all jobs. */
 int ln_filter_prepare(const float* filter, int filter_extent, int c_in, int c_out, int transposed_filter, int precision,
                       float* slabs, void* stream);
 int ln_filter_prepare_batch(const void* jobs_device, int n_jobs, long long total_threads, void* stream);

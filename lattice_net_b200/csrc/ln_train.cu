@@ -267,27 +267,26 @@ weight_norm_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
                        int gain_per_col, float* __restrict__ dv, float* __restrict__ dg) {
     LN_PDL_ENTRY();
     __shared__ float red[33];
+    extern __shared__ float gain_acc[];          // [n_gain]: sum over each gain's slice of dw * v
     const int n = rows * cols;
+    const int n_gain = gain_per_col ? cols : rows;
+    for (int j = threadIdx.x; j < n_gain; j += kLossThreads) gain_acc[j] = 0.0f;
+    __syncthreads();
     float s = 0.0f, dot = 0.0f;
     for (int i = threadIdx.x; i < n; i += kLossThreads) {
         const float x = __ldg(v + i);
+        const int j = gain_per_col ? i % cols : i / cols;
+        const float p = __ldg(dw + i) * x;
         s = fmaf(x, x, s);
-        dot = fmaf(__ldg(dw + i) * x, __ldg(g + (gain_per_col ? i % cols : i / cols)), dot);
+        dot = fmaf(p, __ldg(g + j), dot);
+        atomicAdd(gain_acc + j, p);              // shared-memory reduction: lanes of a warp hit consecutive (or one) gain
     }
     const float n2 = block_sum_1024(s, red);
     const float total = block_sum_1024(dot, red);
     const float norm = sqrtf(n2);
     for (int i = threadIdx.x; i < n; i += kLossThreads)
         dv[i] = __ldg(dw + i) * (__ldg(g + (gain_per_col ? i % cols : i / cols)) / norm) - __ldg(v + i) * (total / (n2 * norm));
-    const int n_gain = gain_per_col ? cols : rows;
-    for (int j = threadIdx.x; j < n_gain; j += kLossThreads) {
-        float d = 0.0f;
-        if (gain_per_col)
-            for (int r = 0; r < rows; r++) d = fmaf(__ldg(dw + (size_t)r * cols + j), __ldg(v + (size_t)r * cols + j), d);
-        else
-            for (int c = 0; c < cols; c++) d = fmaf(__ldg(dw + (size_t)j * cols + c), __ldg(v + (size_t)j * cols + c), d);
-        dg[j] = d / norm;
-    }
+    for (int j = threadIdx.x; j < n_gain; j += kLossThreads) dg[j] = gain_acc[j] / norm;
 }
 
 }  // namespace ln
@@ -354,7 +353,9 @@ int ln_weight_norm_fwd(const float* v, const float* g, int rows, int cols, int g
 int ln_weight_norm_bwd(const float* v, const float* g, const float* dw, int rows, int cols, int gain_per_col, float* dv, float* dg,
                        void* stream) {
     LN_REQUIRE(v && g && dw && dv && dg && rows >= 1 && cols >= 1, "ln_weight_norm_bwd: bad argument");
-    launch_k(weight_norm_bwd_kernel, dim3(1), dim3(kLossThreads), 0, (cudaStream_t)stream, v, g, dw, rows, cols, gain_per_col, dv, dg);
+    const int n_gain = gain_per_col ? cols : rows;
+    LN_REQUIRE(n_gain <= 8192, "ln_weight_norm_bwd: at most 8192 gains");
+    launch_k(weight_norm_bwd_kernel, dim3(1), dim3(kLossThreads), (size_t)n_gain * sizeof(float), (cudaStream_t)stream, v, g, dw, rows, cols, gain_per_col, dv, dg);
     count_launch();
     return check_launch("weight_norm_bwd");
 }

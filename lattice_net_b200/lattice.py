@@ -107,7 +107,7 @@ def prepare_filters(readings):
             F, c_in, c_out = e.dims
             blob += struct.pack("<QQiiiiiiq", t.data_ptr(), e.slabs.data_ptr(), F * c_in, c_in, c_out, 1 if transposed else 0,
                                 1 if CONV_PRECISION == 1 else 0, 0, first)
-            first += F * c_in * _n_pad_sum(c_out)
+            first += (F * c_in // 32) * ((_n_pad_sum(c_out) + 31) // 32)       # tiles of 32 x 32 slab elements, one CTA each
         host = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
         if len(_JOB_TABLES) > 64:
             _JOB_TABLES.clear()
