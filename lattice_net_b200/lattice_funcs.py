@@ -221,6 +221,13 @@ class SliceClassifyLattice(Function):
     def forward(ctx, lattice_values, lattice_structure, positions, delta_weights, linear_clasify_weight,
                 linear_clasify_bias, nr_classes, splatting_indices, splatting_weights):
         lattice_structure.set_values(lattice_values)
+        if lattice_values.is_cuda and any(ctx.needs_input_grad):
+            # the limits of the backward kernels (ln_slice_classify_bwd), checked here so that an unsupported head fails
+            # before training starts rather than in the first backward()
+            v, nc = int(lattice_values.shape[1]), int(nr_classes)
+            if v > 256 or nc * v > 6144 or nc > 256:
+                raise RuntimeError(f"slice_classify backward is built for val_dim <= 256, nr_classes <= 256 and nr_classes * val_dim <= 6144 "
+                                   f"(got val_dim {v}, nr_classes {nc}); run the head under torch.no_grad() or use SliceLattice + a Linear layer")
         logits = lattice_structure.slice_classify_with_precomputation(
             positions, delta_weights, linear_clasify_weight, linear_clasify_bias, nr_classes, splatting_indices, splatting_weights)
         ctx.save_for_backward(positions, lattice_values, delta_weights, linear_clasify_weight, linear_clasify_bias,
