@@ -213,7 +213,7 @@ def kernel_roofline(device):
             traffic = float(json.load(f)["traffic_bytes_per_call"])
     except Exception:
         pass
-    return {"bound": "tensor", "kernel": "conv_tc2_kernel<1>: lattice conv fwd 128->128 (K=1152), nv=%d, precision mode %d (3xTF32: three tcgen05 kind::tf32 passes per "
+    return {"bound": "tensor", "kernel": "conv_tc3_kernel: lattice conv fwd 128->128 (K=1152), nv=%d, precision mode %d (3xTF32: three tcgen05 kind::tf32 passes per "
                                          "algorithmic flop); one launch = the tcgen05 kernel alone (filter slabs prepared once per step), device time from a CUDA-graph "
                                          "replay of 20 back-to-back launches (working set stays in L2, as inside the step)" % (nv, lattice_mod.CONV_PRECISION),
             "achieved": achieved, "peak": peak, "peak_source": "measured bf16 burst (MEASURED_PEAKS.json)" if peaks else "fallback",

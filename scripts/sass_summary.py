@@ -1,6 +1,6 @@
 """Static evidence from the built library: per kernel, the SASS mnemonics that identify the Blackwell paths
 (B200_PROFILING.md "What proves a Blackwell-native kernel"), plus registers / spills from cuobjdump's resource usage.
-    python scripts/sass_summary.py > profiles/r01_sass_summary.md        (no GPU needed)"""
+    python scripts/sass_summary.py > profiles/r02_sass_summary.md        (no GPU needed)"""
 import collections
 import os
 import re
