@@ -7,6 +7,10 @@
   * `SyntheticCloud`, `read_semantic_kitti_scan`, `write_label_file` -- the SemanticKITTI on-disk formats the reference's
     loader / eval script handle (`.bin` float32 x,y,z,intensity; `.label` uint32, lower 16 bits = class;
     /root/reference/latticenet_py/ln_eval.py:168-193 writes predictions as uint32 `.label` files).
+  * `read_ply_cloud`, `write_ply_cloud` -- the ScanNet on-disk format (`*_vh_clean_2.ply` / `*_vh_clean_2.labels.ply`: PLY vertex
+    elements x, y, z float, red, green, blue, alpha uchar, optional label ushort; ascii or binary), and the `_pred.ply` /
+    `_gt.ply` files ln_eval.py:143-147 names; `write_scannet_evaluation_file`: the benchmark's one-label-id-per-line text file
+    (ln_eval.py:160-163 hands this to the loader's `write_for_evaluating_on_scannet_server`).
   * `PinnedCloudFeeder` -- double-buffered pinned-memory H2D staging for the graphed step: while the GPU replays the step
     graph of cloud i, cloud i+1 is copied into the other set of device buffers on a copy stream, so the end-to-end rate
     does not pay the host-to-device copy.
@@ -92,6 +96,130 @@ def write_label_file(pred_logsoftmax, path):
     l_pred = pred_logsoftmax.detach().argmax(dim=1).cpu().numpy().reshape(-1).astype(np.uint32)
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
     l_pred.tofile(path)
+    return l_pred
+
+
+_PLY_TYPES = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2", "ushort": "u2", "uint16": "u2",
+              "int": "i4", "int32": "i4", "uint": "u4", "uint32": "u4", "float": "f4", "float32": "f4", "double": "f8", "float64": "f8"}
+
+
+def _read_ply_vertices(path):
+    """Vertex element of a PLY file as a numpy structured array (other elements, e.g. faces, are not read)."""
+    with open(path, "rb") as f:
+        if f.readline().strip() != b"ply":
+            raise ValueError(f"{path}: not a PLY file")
+        fmt = None
+        elements = []          # (name, count, [(prop name, dtype) | None for list properties])
+        while True:
+            line = f.readline()
+            if not line:
+                raise ValueError(f"{path}: PLY header without end_header")
+            tok = line.decode("ascii", "replace").split()
+            if not tok or tok[0] in ("comment", "obj_info"):
+                continue
+            if tok[0] == "format":
+                fmt = tok[1]
+            elif tok[0] == "element":
+                elements.append((tok[1], int(tok[2]), []))
+            elif tok[0] == "property":
+                if tok[1] == "list":
+                    elements[-1][2].append(None)
+                else:
+                    if tok[1] not in _PLY_TYPES:
+                        raise ValueError(f"{path}: PLY property type {tok[1]} unknown")
+                    elements[-1][2].append((tok[2], _PLY_TYPES[tok[1]]))
+            elif tok[0] == "end_header":
+                break
+        if fmt not in ("ascii", "binary_little_endian", "binary_big_endian"):
+            raise ValueError(f"{path}: PLY format {fmt} unknown")
+        if not elements or elements[0][0] != "vertex":
+            raise ValueError(f"{path}: the first PLY element must be `vertex`")
+        _, count, props = elements[0]
+        if any(p is None for p in props):
+            raise ValueError(f"{path}: list properties on vertices are not supported")
+        order = "<" if fmt != "binary_big_endian" else ">"
+        dtype = np.dtype([(n, order + t) for n, t in props])
+        if fmt == "ascii":
+            rows = np.loadtxt(f, dtype=np.float64, max_rows=count, ndmin=2) if count else np.zeros((0, len(props)))
+            if rows.shape != (count, len(props)):
+                raise ValueError(f"{path}: expected {count} vertex rows of {len(props)} values")
+            out = np.zeros(count, dtype=dtype)
+            for i, (n, _) in enumerate(props):
+                out[n] = rows[:, i]
+            return out
+        raw = f.read(count * dtype.itemsize)
+        if len(raw) != count * dtype.itemsize:
+            raise ValueError(f"{path}: truncated PLY vertex data")
+        return np.frombuffer(raw, dtype=dtype, count=count)
+
+
+def read_ply_cloud(path, labels_path=None):
+    """A cloud (V, C in [0,1], I zeros, L_gt) from a PLY file; per-vertex labels come from the `label` property of `labels_path`
+    (ScanNet keeps them in a second file with the same vertices) or of `path` itself, else zeros."""
+    v = _read_ply_vertices(path)
+    names = v.dtype.names
+    n = len(v)
+    c = types.SimpleNamespace(V=np.stack([v["x"], v["y"], v["z"]], 1).astype(np.float32) if n else np.zeros((0, 3), np.float32))
+    if all(k in names for k in ("red", "green", "blue")):
+        rgb = np.stack([v["red"], v["green"], v["blue"]], 1)
+        c.C = (rgb.astype(np.float32) / 255.0) if rgb.dtype.kind in "ui" else rgb.astype(np.float32)
+    else:
+        c.C = np.zeros((n, 3), np.float32)
+    c.I = np.zeros((n, 1), np.float32)
+    lab = None
+    if labels_path is not None:
+        lv = _read_ply_vertices(labels_path)
+        if len(lv) != n:
+            raise ValueError(f"{labels_path}: {len(lv)} vertices, the cloud has {n}")
+        if "label" not in lv.dtype.names:
+            raise ValueError(f"{labels_path}: no `label` vertex property")
+        lab = lv["label"]
+    elif "label" in names:
+        lab = v["label"]
+    c.L_gt = (lab.astype(np.int32) if lab is not None else np.zeros(n, np.int32)).reshape(-1, 1)
+    c.m_disk_path = path
+    c.name = os.path.splitext(os.path.basename(path))[0]
+    return c
+
+
+def write_ply_cloud(path, positions, colours=None, labels=None, binary=True):
+    """Positions [N x 3] (+ colours in [0,1] [N x 3], + labels [N]) as a PLY vertex cloud -- the `_pred.ply` / `_gt.ply` of ln_eval.py."""
+    pos = np.asarray(positions, dtype=np.float32).reshape(-1, 3)
+    fields = [("x", "<f4"), ("y", "<f4"), ("z", "<f4")]
+    header = ["ply", "format %s 1.0" % ("binary_little_endian" if binary else "ascii"), "element vertex %d" % len(pos),
+              "property float x", "property float y", "property float z"]
+    if colours is not None:
+        fields += [("red", "u1"), ("green", "u1"), ("blue", "u1")]
+        header += ["property uchar red", "property uchar green", "property uchar blue"]
+    if labels is not None:
+        fields += [("label", "<u2")]
+        header += ["property ushort label"]
+    header.append("end_header")
+    rec = np.zeros(len(pos), dtype=np.dtype(fields))
+    rec["x"], rec["y"], rec["z"] = pos[:, 0], pos[:, 1], pos[:, 2]
+    if colours is not None:
+        col = np.clip(np.rint(np.asarray(colours, dtype=np.float32).reshape(-1, 3) * 255.0), 0, 255).astype(np.uint8)
+        rec["red"], rec["green"], rec["blue"] = col[:, 0], col[:, 1], col[:, 2]
+    if labels is not None:
+        rec["label"] = np.asarray(labels).reshape(-1).astype(np.uint16)
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    with open(path, "wb") as f:
+        f.write(("\n".join(header) + "\n").encode("ascii"))
+        if binary:
+            f.write(rec.tobytes())
+        else:
+            for r in rec:
+                f.write((" ".join(repr(x.item()) if isinstance(x, np.floating) else str(x.item()) for x in r) + "\n").encode("ascii"))
+
+
+def write_scannet_evaluation_file(pred_logsoftmax, path, class_to_benchmark_id=None):
+    """One label id per line, in vertex order (the ScanNet benchmark's submission format).  `class_to_benchmark_id` maps the
+    network's class index to the benchmark's id (e.g. the NYU40 ids of the 20 evaluated classes); identity when None."""
+    l_pred = pred_logsoftmax.detach().argmax(dim=1).cpu().numpy().reshape(-1).astype(np.int64)
+    if class_to_benchmark_id is not None:
+        l_pred = np.asarray(class_to_benchmark_id, dtype=np.int64)[l_pred]
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    np.savetxt(path, l_pred, fmt="%d")
     return l_pred
 
 

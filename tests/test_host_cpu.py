@@ -264,3 +264,92 @@ def test_python_surface_of_the_reference_is_kept():
         obj = lattice if cls_name == "Lattice" else cls
         missing = [n for n in names if not hasattr(obj, n)]
         assert not missing, f"{cls_name} lacks {missing}"
+
+
+def test_input_path_file_formats(tmp_path):
+    """the on-disk formats either side of the path (ScanNet .ply, SemanticKITTI .bin / .label, prediction files)
+    and prepare_cloud's positions / values modes (reference models.py:18-66) -- host code, no GPU."""
+    import types
+    import numpy as np
+    import torch
+    from lattice_net_b200 import data
+
+    rng = np.random.RandomState(3)
+    n = 257
+    pos = rng.randn(n, 3).astype(np.float32)
+    col = rng.randint(0, 256, (n, 3)).astype(np.float32) / 255.0
+    lab = rng.randint(0, 21, n)
+    for binary in (True, False):
+        p = str(tmp_path / ("cloud_%d.ply" % binary))
+        data.write_ply_cloud(p, pos, col, lab, binary=binary)
+        c = data.read_ply_cloud(p)
+        assert c.V.dtype == np.float32 and np.array_equal(c.V, pos)          # float32 round-trips exactly (repr in ascii)
+        assert np.allclose(c.C, col, atol=0.5 / 255.0 + 1e-7) and c.C.max() <= 1.0
+        assert np.array_equal(c.L_gt.reshape(-1), lab) and c.L_gt.shape == (n, 1)
+        assert c.name == "cloud_%d" % binary
+    # ScanNet layout: geometry + colour (+ alpha, + faces) in one file, labels in a second file with the same vertices
+    mesh = str(tmp_path / "scene0000_00_vh_clean_2.ply")
+    rec = np.zeros(n, dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("red", "u1"), ("green", "u1"), ("blue", "u1"), ("alpha", "u1")])
+    rec["x"], rec["y"], rec["z"] = pos.T
+    rec["red"], rec["green"], rec["blue"] = np.rint(col * 255).astype(np.uint8).T
+    with open(mesh, "wb") as f:
+        f.write(("ply\nformat binary_little_endian 1.0\ncomment VCGLIB generated\nelement vertex %d\nproperty float x\nproperty float y\n"
+                 "property float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nproperty uchar alpha\nelement face 1\n"
+                 "property list uchar int vertex_indices\nend_header\n" % n).encode())
+        f.write(rec.tobytes())
+        f.write(bytes([3]) + np.array([0, 1, 2], "<i4").tobytes())
+    labels = str(tmp_path / "scene0000_00_vh_clean_2.labels.ply")
+    data.write_ply_cloud(labels, pos, col, lab)
+    c = data.read_ply_cloud(mesh, labels)
+    assert np.array_equal(c.V, pos) and np.array_equal(c.L_gt.reshape(-1), lab) and np.allclose(c.C, col, atol=1e-6)
+    assert np.array_equal(data.read_ply_cloud(mesh).L_gt, np.zeros((n, 1), np.int32))
+    with pytest.raises(ValueError):
+        data.write_ply_cloud(str(tmp_path / "short.ply"), pos[:5], None, lab[:5])
+        data.read_ply_cloud(mesh, str(tmp_path / "short.ply"))
+    with open(str(tmp_path / "trunc.ply"), "wb") as f:
+        f.write(open(mesh, "rb").read()[:400])
+    with pytest.raises(ValueError):
+        data.read_ply_cloud(str(tmp_path / "trunc.ply"))
+    with pytest.raises(ValueError):
+        data.read_ply_cloud(__file__)
+
+    # SemanticKITTI: .bin float32 x y z remission, .label uint32 with the instance id in the upper 16 bits
+    scan = rng.randn(100, 4).astype(np.float32)
+    sem = rng.randint(0, 20, 100).astype(np.uint32)
+    (scan).tofile(str(tmp_path / "000000.bin"))
+    (sem | (rng.randint(0, 1000, 100).astype(np.uint32) << 16)).tofile(str(tmp_path / "000000.label"))
+    k = data.read_semantic_kitti_scan(str(tmp_path / "000000.bin"), str(tmp_path / "000000.label"))
+    assert np.array_equal(k.V, scan[:, :3]) and np.array_equal(k.I, scan[:, 3:4]) and np.array_equal(k.L_gt.reshape(-1), sem.astype(np.int32))
+    assert np.array_equal(data.read_semantic_kitti_scan(str(tmp_path / "000000.bin")).L_gt, np.zeros((100, 1), np.int32))
+
+    # prediction writers (ln_eval.py:160-191)
+    logits = torch.from_numpy(rng.randn(100, 20).astype(np.float32))
+    out = data.write_label_file(logits, str(tmp_path / "pred" / "000000.label"))
+    back = np.fromfile(str(tmp_path / "pred" / "000000.label"), dtype=np.uint32)
+    assert back.dtype == np.uint32 and np.array_equal(back, logits.argmax(1).numpy()) and np.array_equal(out, back)
+    ids = np.arange(20) * 2 + 1
+    data.write_scannet_evaluation_file(logits, str(tmp_path / "eval" / "scene0000_00.txt"), ids)
+    txt = np.loadtxt(str(tmp_path / "eval" / "scene0000_00.txt"), dtype=np.int64)
+    assert np.array_equal(txt, ids[logits.argmax(1).numpy()])
+
+    # prepare_cloud: every positions / values mode of reference models.py:18-66
+    cloud = types.SimpleNamespace(V=pos, C=col.astype(np.float32), I=rng.rand(n, 1).astype(np.float32), L_gt=lab.reshape(-1, 1).astype(np.int32))
+
+    def mp(pm, vm):
+        return types.SimpleNamespace(positions_mode=lambda: pm, values_mode=lambda: vm)
+
+    T = torch.from_numpy
+    want_pos = {"xyz": T(pos), "xyz+rgb": torch.cat((T(pos), T(cloud.C)), 1), "xyz+intensity": torch.cat((T(pos), T(cloud.I)), 1)}
+    want_val = {"none": torch.zeros(n, 1), "intensity": T(cloud.I), "rgb": T(cloud.C), "rgb+height": torch.cat((T(cloud.C), T(pos[:, 1:2].copy())), 1),
+                "rgb+xyz": torch.cat((T(cloud.C), T(pos)), 1), "height": T(pos[:, 1:2].copy()), "xyz": T(pos)}
+    for pm, wp in want_pos.items():
+        for vm, wv in want_val.items():
+            p_, v_, t_ = data.prepare_cloud(cloud, mp(pm, vm), device="cpu")
+            assert torch.equal(p_, wp) and torch.equal(v_, wv) and p_.is_contiguous() and v_.is_contiguous()
+            assert t_.dtype == torch.int64 and torch.equal(t_, T(lab.astype(np.int64)))
+    as_dict = {"V": cloud.V, "C": cloud.C, "I": cloud.I, "L_gt": cloud.L_gt}
+    assert torch.equal(data.prepare_cloud(as_dict, mp("xyz", "rgb"), device="cpu")[1], T(cloud.C))
+    with pytest.raises(SystemExit):
+        data.prepare_cloud(cloud, mp("uvw", "none"), device="cpu")
+    with pytest.raises(SystemExit):
+        data.prepare_cloud(cloud, mp("xyz", "normals"), device="cpu")
